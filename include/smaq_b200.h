@@ -1,0 +1,197 @@
+/*
+ * smaq_b200 — C ABI of the B200-native SmaQ / FP8 / S2FP8 compress->decompress path.
+ *
+ * The reference (nimashoghi/smart-quantization) has no FFI: its hot path is ~30 eager
+ * torch ops per call inside three Python plugin classes.  The entry points below are what
+ * a binding for that path replaces; each cites the reference lines it stands in for.
+ * The Python host side (smart-quantization_b200/smart_compress/_native.py) binds them with
+ * ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer named x/y/packed/ws/mean_std/... is a DEVICE pointer unless it says "host";
+ *   - the caller owns every buffer (outputs and workspace included); nothing here allocates;
+ *   - nothing here synchronises: work is enqueued on `stream` (a cudaStream_t) and returns;
+ *   - no global mutable state: safe to call from several threads (forward on the Python main
+ *     thread, backward on autograd's per-device worker thread);
+ *   - return value: SMAQ_OK or a SMAQ_ERR_* code; smaq_b200_last_error() gives the text of the
+ *     calling thread's last failure.  No exception crosses this boundary.
+ *   - float data is IEEE binary32; element counts are int64_t (4 GiB+ tensors are in scope).
+ */
+#ifndef SMAQ_B200_H
+#define SMAQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMAQ_B200_ABI_VERSION 1
+
+typedef void* smaq_stream_t; /* cudaStream_t */
+
+enum {
+  SMAQ_OK = 0,
+  SMAQ_ERR_ARG = 1,         /* null pointer, negative size, unsupported bit width ... */
+  SMAQ_ERR_CUDA = 2,        /* a CUDA runtime call failed (launch error included) */
+  SMAQ_ERR_WORKSPACE = 3,   /* caller's workspace / packed buffer is too small */
+  SMAQ_ERR_UNSUPPORTED = 4  /* valid request the library does not implement */
+};
+
+int smaq_b200_abi_version(void);
+const char* smaq_b200_last_error(void);
+/* Number of SMs of the current device (grid sizing is a multiple of this); <0 on error. */
+int smaq_b200_sm_count(void);
+
+/* ---- SmaQ ------------------------------------------------------------------------------- */
+
+/* The per-call constants SmartFP derives from its flags (smart.py:72-84) plus the call's kwargs
+ * (smart.py:111-118).  Plain data, read on the host at call time. */
+typedef struct smaq_codec_params {
+  float threshold;      /* fp32(--main_std_dev_threshold), > 0 */
+  float range_main;     /* fp32(range_normal)   smart.py:78-80 */
+  float range_outlier;  /* fp32(range_outlier)  smart.py:75-77 */
+  float clamp_lo;       /* clamped_range        smart.py:82-84 */
+  float clamp_hi;
+  int32_t bits_main;    /* --num_bits_main    (3..16) */
+  int32_t bits_outlier; /* --num_bits_outlier (bits_main..17) */
+  int32_t stochastic;   /* 0: trunc (smart.py:169); 1: stochastic rounding (smart.py:93-98) */
+  int32_t all_positive; /* clamp_min(0) at the end (smart.py:181-182) */
+  int32_t saturate;     /* round trip only: clamp codes to what the packed format holds (not in
+                           the reference; 0 reproduces smart.py exactly) */
+  int32_t reserved;
+  uint64_t seed;        /* Philox4x32-10 key, used when stochastic && probs == NULL */
+  uint64_t offset;      /* Philox stream offset (added to the counter's high words) */
+} smaq_codec_params;
+
+/* Full-tensor mean and standard deviation in one pass — replaces data.mean() and data.std()
+ * (smart.py:130-132; two read passes there).  Welford chunks per thread, warp-shuffle and
+ * block combine, last-block grid combine in fp64.  Writes mean_std[0]=mean, mean_std[1]=std
+ * (std with divisor n-1 when unbiased!=0, n otherwise).  ws: smaq_stats_workspace_bytes(n). */
+size_t smaq_stats_workspace_bytes(int64_t n);
+int smaq_stats_full(const float* x, int64_t n, int unbiased, float* mean_std, void* ws, size_t ws_bytes,
+                    smaq_stream_t stream);
+
+/* --use_range_std_dev (smart.py:100-106): mean as above, std = (max-min)/sqrt(2 ln n). */
+int smaq_stats_range(const float* x, int64_t n, float* mean_std, void* ws, size_t ws_bytes,
+                     smaq_stream_t stream);
+
+/* --use_sample_stats (smart.py:86-91): mean and BIASED std of x[idx[0..k)].  idx is a device
+ * array of int64 indices (the caller's permutation prefix), k <= 1024. */
+int smaq_stats_sampled(const float* x, int64_t n, const int64_t* idx, int32_t k, float* mean_std,
+                       smaq_stream_t stream);
+/* Same, but the k distinct indices are drawn on the device (Philox + Floyd's algorithm): a
+ * uniform k-subset, the law of randperm(n)[:k], without materialising an n-element permutation. */
+int smaq_stats_sampled_draw(const float* x, int64_t n, int32_t k, uint64_t seed, uint64_t offset,
+                            float* mean_std, smaq_stream_t stream);
+
+/* Fused fake-quantisation round trip — replaces smart.py:151-182 (~26 elementwise kernels, a
+ * host sync and two H2D scalar copies) with one read and one write of the tensor.
+ * mean_std: device float[2] from a stats call (raw std; the ==0 fix-up happens on device).
+ * probs: optional device float[n] of U[0,1) numbers (parity mode); NULL -> in-kernel Philox.
+ * y may alias x. */
+int smaq_roundtrip(const float* x, float* y, int64_t n, const float* mean_std, const float* probs,
+                   const smaq_codec_params* params, smaq_stream_t stream);
+
+/* Number of outliers (|z| > threshold) under the given statistics — the only quantity the
+ * reference's size accounting needs (smart.py:184-187: bits = 8*n_out + 6*(n - n_out)).  Adds the
+ * count to *counter (device uint64, caller zeroes it).  Only used under --measure_compression_ratio. */
+int smaq_count_outliers(const float* x, int64_t n, const float* mean_std, const smaq_codec_params* params,
+                        unsigned long long* counter, smaq_stream_t stream);
+
+/* Small-tensor path: statistics (full-tensor, unbiased) + round trip in ONE launch of one
+ * thread block; n <= smaq_fused_small_max(). */
+int64_t smaq_fused_small_max(void);
+int smaq_roundtrip_small(const float* x, float* y, int64_t n, const float* probs,
+                         const smaq_codec_params* params, float* mean_std_out /* may be NULL */,
+                         smaq_stream_t stream);
+
+/* Many tensors, one launch (the optimizer side: smart_compress/util/pytorch/optimizer.py:69-127
+ * loops compress_fn over every parameter).  descs is a DEVICE array of `count` descriptors;
+ * each tensor gets its own full-tensor statistics and its own round trip, in place or not. */
+typedef struct smaq_tensor_desc {
+  const float* x;
+  float* y;
+  int64_t n;
+  int32_t all_positive;
+  int32_t reserved;
+} smaq_tensor_desc;
+size_t smaq_multi_workspace_bytes(int32_t count, int64_t total_elems);
+int smaq_roundtrip_multi(const smaq_tensor_desc* descs, int32_t count, int64_t max_n, int64_t total_elems,
+                         const smaq_codec_params* params, int64_t min_size, void* ws, size_t ws_bytes,
+                         smaq_stream_t stream);
+
+/* ---- packed SmaQ stream ------------------------------------------------------------------ */
+
+/* Byte offsets of the sections of one packed tensor (see DESIGN.md "Packed layout"). */
+typedef struct smaq_packed_layout {
+  int64_t n;
+  int32_t bits_main, bits_outlier;
+  int64_t n_warp_tiles;    /* ceil(n / 1024) */
+  int64_t n_cta_tiles;     /* ceil(n_warp_tiles / 8) */
+  int64_t header_off, header_bytes;   /* smaq_packed_header */
+  int64_t table_off, table_bytes;     /* uint32 extras word offset per CTA tile (+1 sentinel) */
+  int64_t planes_off, planes_bytes;   /* tag word + (bits_main-1) base words per lane, per warp tile */
+  int64_t extras_off, extras_capacity_bytes; /* dense (bits_outlier-bits_main) bits per outlier */
+  int64_t total_capacity_bytes;       /* what the caller must allocate */
+  int64_t workspace_bytes;            /* scratch for smaq_encode */
+} smaq_packed_layout;
+
+/* First bytes of a packed buffer, written by smaq_encode on the device. */
+typedef struct smaq_packed_header {
+  uint32_t magic;            /* 'SQB1' */
+  int32_t bits_main, bits_outlier;
+  int32_t stochastic;
+  int64_t n;
+  float mean, std_raw;       /* statistics the codes are relative to */
+  float threshold, range_main, range_outlier, clamp_lo, clamp_hi, pad0;
+  uint64_t n_outlier;        /* smart.py:184-187: compressed bits = 8*n_outlier + 6*(n-n_outlier) */
+  uint64_t n_saturated;      /* codes clamped to the field width, or non-finite (H1) */
+  uint64_t extras_words;     /* 32-bit words actually used in the extras section */
+  uint64_t status;           /* 0 ok; nonzero: encode aborted (look-back watchdog) */
+} smaq_packed_header;
+
+int smaq_packed_layout_for(int64_t n, int32_t bits_main, int32_t bits_outlier, smaq_packed_layout* out);
+
+/* Quantise and pack — the materialised form of the code the reference only ever holds as an
+ * fp32 value (smart.py:164-169).  Codes saturate at the field width.  ws must be
+ * layout.workspace_bytes; it is cleared on `stream` by this call. */
+int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* probs,
+                const smaq_codec_params* params, void* packed, size_t packed_bytes, void* ws,
+                size_t ws_bytes, smaq_stream_t stream);
+
+/* Unpack and de-normalise (smart.py:171-172,181-182).  Parameters come from the header. */
+int smaq_decode(const void* packed, size_t packed_bytes, int64_t n, int32_t bits_main, int32_t bits_outlier,
+                int32_t all_positive, float* y, smaq_stream_t stream);
+
+/* ---- low-precision float emulation --------------------------------------------------------- */
+
+/* What qtorch 0.2.0's float_quantize does to each fp32 (the reference calls it at
+ * smart_compress/util/pytorch/quantization.py:191-193), fused with the reference's own
+ * "+max -> +inf" fix-up (quantization.py:195-199).
+ * rounding: 0 nearest, 1 stochastic.  rand_bits: optional device int32[n] (what qtorch's CUDA
+ * path draws with randint_like); NULL -> in-kernel Philox.  y may alias x. */
+typedef struct smaq_floatq_params {
+  int32_t exp_bits, man_bits;
+  int32_t rounding;
+  int32_t check_inf;        /* hparams.float_quantize_check_inf */
+  int32_t max_exp_bias;     /* max stored exponent = 127 + 2^(exp_bits-1) + max_exp_bias; 0 for qtorch 0.2.0 */
+  int32_t reserved;
+  uint64_t seed, offset;
+} smaq_floatq_params;
+int smaq_float_quantize(const float* x, float* y, int64_t n, const int32_t* rand_bits,
+                        const smaq_floatq_params* params, smaq_stream_t stream);
+
+/* S2FP8 (smart_compress/compress/s2fp8.py:31-48).  Pass 1: mu = mean(L), m = max(L) with
+ * L = log2|x| and L := 0 where x == 0; writes mu_max[0..1].  Pass 2: alpha = 15/(m-mu),
+ * beta = -alpha*mu, y = sign(x) * (Q(|x|^alpha * 2^beta) / 2^beta)^(1/alpha), Q = e5m2 above. */
+int smaq_s2fp8_stats(const float* x, int64_t n, float* mu_max, void* ws, size_t ws_bytes,
+                     smaq_stream_t stream);
+int smaq_s2fp8_apply(const float* x, float* y, int64_t n, const float* mu_max, const int32_t* rand_bits,
+                     const smaq_floatq_params* params, smaq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMAQ_B200_H */

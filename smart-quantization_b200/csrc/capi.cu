@@ -1,0 +1,46 @@
+// Library-level entry points: ABI version, per-thread error text, device properties.
+#include "common.cuh"
+
+#include <atomic>
+#include <cstring>
+
+namespace smaq {
+
+char* last_error_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int sm_count() {
+  // one immutable value per device ordinal; racing writers store the same number
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    cudaGetLastError();
+    return -1;
+  }
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v > 0) return v;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  cache[dev].store(v, std::memory_order_relaxed);
+  return v;
+}
+
+}  // namespace smaq
+
+extern "C" {
+int smaq_b200_abi_version(void) { return SMAQ_B200_ABI_VERSION; }
+const char* smaq_b200_last_error(void) { return smaq::last_error_buf(); }
+int smaq_b200_sm_count(void) { return smaq::sm_count(); }
+}

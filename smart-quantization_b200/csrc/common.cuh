@@ -1,0 +1,121 @@
+// Shared device/host helpers for the smaq_b200 library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/smaq_b200.h"
+
+namespace smaq {
+
+// ---- error plumbing (thread-local; no global mutable state shared between threads) ----------
+char* last_error_buf();
+int fail(int code, const char* fmt, ...);
+int sm_count();  // cached per device, immutable once read
+
+#define SMAQ_CUDA_OK(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return ::smaq::fail(SMAQ_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                          __FILE__, __LINE__);                                          \
+  } while (0)
+
+#define SMAQ_LAUNCH_OK()                                                                \
+  do {                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess)                                                              \
+      return ::smaq::fail(SMAQ_ERR_CUDA, "kernel launch: %s (%s:%d)", cudaGetErrorString(_e), \
+                          __FILE__, __LINE__);                                          \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- streaming 128-bit global accesses -------------------------------------------------------
+// Every tensor on this path is touched once per kernel: keep it out of L1.  Plain (coherent)
+// loads, not .nc: the round trip may run in place (y aliasing x).
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldg_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream(float4* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// ---- Philox4x32-10 (Salmon et al., SC'11): counter-based, so the random number of element i
+// depends only on (seed, offset, i) and never on the launch geometry. ---------------------------
+struct Philox {
+  uint32_t k0, k1;
+  __host__ __device__ __forceinline__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+
+  __host__ __device__ __forceinline__ static void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+    lo = a * b;
+    hi = __umulhi(a, b);
+#else
+    uint64_t p = (uint64_t)a * b;
+    lo = (uint32_t)p;
+    hi = (uint32_t)(p >> 32);
+#endif
+  }
+
+  // counter = (c0,c1,c2,c3); returns 4 x 32 random bits
+  __host__ __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+    uint32_t ka = k0, kb = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t h0, l0, h1, l1;
+      mulhilo(0xD2511F53u, c0, h0, l0);
+      mulhilo(0xCD9E8D57u, c2, h1, l1);
+      uint32_t n0 = h1 ^ c1 ^ ka, n2 = h0 ^ c3 ^ kb;
+      c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+      ka += 0x9E3779B9u; kb += 0xBB67AE85u;
+    }
+    uint4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+  }
+  // the 4 random words for elements [4*g, 4*g+4) of a tensor
+  __host__ __device__ __forceinline__ uint4 for_group(uint64_t g, uint64_t offset) const {
+    return (*this)((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)offset, (uint32_t)(offset >> 32));
+  }
+};
+
+// ---- warp helpers --------------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane_id() >= o) v += t;
+  }
+  return v;
+}
+
+}  // namespace smaq

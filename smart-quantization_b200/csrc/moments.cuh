@@ -1,0 +1,138 @@
+// Streaming moments (count, mean, M2) and their combination: shared by the grid statistics
+// kernel, the single-block small-tensor kernels and the multi-tensor kernel.
+#pragma once
+#include "common.cuh"
+
+namespace smaq {
+
+struct Moments {
+  double n, mean, m2;
+};
+
+__device__ __forceinline__ Moments merge(const Moments& a, const Moments& b) {
+  if (b.n == 0.0) return a;
+  if (a.n == 0.0) return b;
+  Moments r;
+  r.n = a.n + b.n;
+  double delta = b.mean - a.mean;
+  double w = b.n / r.n;
+  r.mean = a.mean + delta * w;
+  r.m2 = a.m2 + b.m2 + delta * delta * (a.n * w);
+  return r;
+}
+
+__device__ __forceinline__ Moments shfl_xor(const Moments& m, int o) {
+  Moments r;
+  r.n = __shfl_xor_sync(0xffffffffu, m.n, o);
+  r.mean = __shfl_xor_sync(0xffffffffu, m.mean, o);
+  r.m2 = __shfl_xor_sync(0xffffffffu, m.m2, o);
+  return r;
+}
+
+// What one thread carries through the pass.  kind 0: moments of x; kind 1: moments of x plus
+// min/max (range std); kind 2: S2FP8's L = (x == 0 ? 0 : log2|x|): sum of L and max of L.
+struct Acc {
+  Moments m;
+  float lo, hi;
+};
+
+template <int kKind>
+__device__ __forceinline__ float transform(float v) {
+  if (kKind == 2) {
+    float a = fabsf(v);
+    return a == 0.0f ? a : log2f(a);  // s2fp8.py:34-35 (torch.where(X_abs == 0, X_abs, log2(X_abs)))
+  }
+  return v;
+}
+
+// Merge a chunk of kCount transformed values held in registers.
+template <int kKind, int kCount>
+__device__ __forceinline__ void merge_chunk(Acc& acc, const float (&v)[kCount]) {
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kCount; ++i) s += v[i];
+  float cm = s * (1.0f / kCount);
+  float m2 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kCount; ++i) {
+    float d = v[i] - cm;
+    m2 = __fmaf_rn(d, d, m2);
+  }
+  Moments c;
+  c.n = (double)kCount;
+  // use the exact fp32 sum for the mean so that no chunk-level rounding of s/kCount leaks in
+  c.mean = (double)s * (1.0 / kCount);
+  double corr = c.mean - (double)cm;  // M2 about cm -> M2 about c.mean
+  c.m2 = (double)m2 - (double)kCount * corr * corr;
+  if (c.m2 < 0.0) c.m2 = 0.0;
+  acc.m = merge(acc.m, c);
+  if (kKind != 0) {
+#pragma unroll
+    for (int i = 0; i < kCount; ++i) {
+      // NaN-propagating min/max like torch.max / torch.min
+      acc.hi = (v[i] > acc.hi || v[i] != v[i]) ? v[i] : acc.hi;
+      if (kKind == 1) acc.lo = (v[i] < acc.lo || v[i] != v[i]) ? v[i] : acc.lo;
+    }
+  }
+}
+
+template <int kKind>
+__device__ __forceinline__ void merge_one(Acc& acc, float v) {
+  float a[1] = {v};
+  merge_chunk<kKind, 1>(acc, a);
+}
+
+constexpr int kStatsThreads = 256;
+constexpr int kPartialDoubles = 5;  // n, mean, m2, lo, hi
+
+__device__ __forceinline__ float nanmax(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+__device__ __forceinline__ float nanmin(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
+
+template <int kKind>
+__device__ __forceinline__ Acc block_combine(Acc acc, Acc* smem /* [warps] */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Moments other = shfl_xor(acc.m, o);
+    // fixed pairing order: lower lane's data is always the left operand
+    acc.m = (lane_id() & o) ? merge(other, acc.m) : merge(acc.m, other);
+    if (kKind != 0) {
+      acc.hi = nanmax(acc.hi, __shfl_xor_sync(0xffffffffu, acc.hi, o));
+      acc.lo = nanmin(acc.lo, __shfl_xor_sync(0xffffffffu, acc.lo, o));
+    }
+  }
+  if (lane_id() == 0) smem[warp_id()] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Acc t = smem[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      t.m = merge(t.m, smem[w].m);
+      t.hi = nanmax(t.hi, smem[w].hi);
+      t.lo = nanmin(t.lo, smem[w].lo);
+    }
+    acc = t;
+  }
+  __syncthreads();
+  return acc;  // valid in thread 0
+}
+
+// Final scalar step shared by the grid kernel and the small-tensor kernels.
+template <int kKind>
+__device__ __forceinline__ void finalize(const Acc& a, int unbiased, float* out) {
+  if (kKind == 2) {
+    out[0] = (float)a.m.mean;  // mu  (s2fp8.py:36)
+    out[1] = a.hi;             // m   (s2fp8.py:37)
+    return;
+  }
+  out[0] = (float)a.m.mean;
+  if (kKind == 1) {
+    // (max - min) * (1 / sqrt(2 ln n)), every step in fp32 as in smart.py:102-106
+    float range = a.hi - a.lo;
+    float c = 1.0f / sqrtf(2.0f * logf((float)a.m.n));
+    out[1] = range * c;
+  } else {
+    double denom = unbiased ? (a.m.n - 1.0) : a.m.n;
+    out[1] = (float)sqrt(a.m.m2 / denom);  // 0/0 -> NaN like torch for n == 1
+  }
+}
+
+}  // namespace smaq

@@ -1,0 +1,320 @@
+// Kernels (2)+(3) fused: the SmaQ fake-quantisation round trip the training hooks call.
+//
+// Replaces reference smart_compress/compress/smart.py:151-182 — ~26 elementwise eager kernels,
+// one host sync (`if std_dev == 0`) and two H2D scalar copies — with one kernel that reads each
+// element once and writes it once.  Statistics come from a device float[2] (smaq_stats_*), the
+// std==0 fix-up and the clamp are evaluated on the device, so the call never synchronises.
+//
+// HBM roofline: 8 bytes per element (4 read + 4 written); +4 when an explicit probs tensor is
+// passed (parity mode only; the performance path draws Philox numbers in-kernel).
+#include "common.cuh"
+#include "moments.cuh"
+#include "smaq_math.cuh"
+
+namespace smaq {
+
+struct KernelParams {
+  float thr, range_main, range_out, clamp_lo, clamp_hi;
+  int bits_main, bits_outlier;
+  int all_positive, saturate;
+  uint64_t seed, offset;
+};
+
+static KernelParams to_kernel_params(const smaq_codec_params& p) {
+  KernelParams k;
+  k.thr = p.threshold;
+  k.range_main = p.range_main;
+  k.range_out = p.range_outlier;
+  k.clamp_lo = p.clamp_lo;
+  k.clamp_hi = p.clamp_hi;
+  k.bits_main = p.bits_main;
+  k.bits_outlier = p.bits_outlier;
+  k.all_positive = p.all_positive;
+  k.saturate = p.saturate;
+  k.seed = p.seed;
+  k.offset = p.offset;
+  return k;
+}
+
+__device__ __forceinline__ Scalars scalars_from(float mean, float std_raw, const KernelParams& kp) {
+  return make_scalars(mean, std_raw, kp.thr, kp.range_main, kp.range_out, kp.clamp_lo, kp.clamp_hi, kp.bits_main,
+                      kp.bits_outlier);
+}
+
+template <bool kStochastic, bool kFast>
+__device__ __forceinline__ float roundtrip_one(float x, float p, const Scalars& s, bool saturate, bool all_positive) {
+  Classified k;
+  float code = encode_value<kStochastic, kFast>(x, s, p, k);
+  if (saturate) code = saturate_code(code, s, k.hi || k.lo);
+  return decode_value<kFast>(code, k.shift, k.range, s, all_positive);
+}
+
+// Processes the 4-element group g (elements 4g..4g+3) of a tensor whose base pointers are 16-byte aligned.
+template <bool kStochastic, bool kHasProbs, bool kFast>
+__device__ __forceinline__ float4 roundtrip_group(float4 v, float4 pr, uint64_t g, const Scalars& s,
+                                                  const KernelParams& kp, const Philox& rng) {
+  float p0 = pr.x, p1 = pr.y, p2 = pr.z, p3 = pr.w;
+  if (kStochastic && !kHasProbs) {
+    uint4 r = rng.for_group(g, kp.offset);
+    p0 = uniform24(r.x); p1 = uniform24(r.y); p2 = uniform24(r.z); p3 = uniform24(r.w);
+  }
+  float4 o;
+  o.x = roundtrip_one<kStochastic, kFast>(v.x, p0, s, kp.saturate, kp.all_positive);
+  o.y = roundtrip_one<kStochastic, kFast>(v.y, p1, s, kp.saturate, kp.all_positive);
+  o.z = roundtrip_one<kStochastic, kFast>(v.z, p2, s, kp.saturate, kp.all_positive);
+  o.w = roundtrip_one<kStochastic, kFast>(v.w, p3, s, kp.saturate, kp.all_positive);
+  return o;
+}
+
+constexpr int kRtThreads = 256;
+constexpr int kRtUnroll = 4;  // independent 128-bit loads in flight per thread
+
+template <bool kStochastic, bool kHasProbs, bool kAligned, bool kFast>
+__device__ __forceinline__ void roundtrip_body(const float* x, float* y, int64_t n, const float* __restrict__ probs,
+                                               const KernelParams& kp, const Scalars& s) {
+  const Philox rng(kp.seed);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t ngroups = n >> 2;
+
+  if (kAligned) {
+    const float4* xv = reinterpret_cast<const float4*>(x);
+    const float4* pv = reinterpret_cast<const float4*>(probs);
+    float4* yv = reinterpret_cast<float4*>(y);
+    int64_t g = tid;
+    for (; g + (kRtUnroll - 1) * nthreads < ngroups; g += kRtUnroll * nthreads) {
+      float4 v[kRtUnroll], pr[kRtUnroll];
+#pragma unroll
+      for (int u = 0; u < kRtUnroll; ++u) {
+        v[u] = ldg_stream(xv + g + u * nthreads);
+        if (kStochastic && kHasProbs) pr[u] = ldg_stream(pv + g + u * nthreads);
+        else pr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < kRtUnroll; ++u)
+        stg_stream(yv + g + u * nthreads,
+                   roundtrip_group<kStochastic, kHasProbs, kFast>(v[u], pr[u], (uint64_t)(g + u * nthreads), s, kp, rng));
+    }
+    for (; g < ngroups; g += nthreads) {
+      float4 v = ldg_stream(xv + g);
+      float4 pr = (kStochastic && kHasProbs) ? ldg_stream(pv + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+      stg_stream(yv + g, roundtrip_group<kStochastic, kHasProbs, kFast>(v, pr, (uint64_t)g, s, kp, rng));
+    }
+  }
+  // elements not covered by whole aligned groups: the last n%4 (aligned) or everything (unaligned)
+  const int64_t first = kAligned ? (ngroups << 2) : 0;
+  for (int64_t i = first + tid; i < n; i += nthreads) {
+    float p = 0.f;
+    if (kStochastic) {
+      if (kHasProbs) p = probs[i];
+      else {
+        uint4 r = rng.for_group((uint64_t)(i >> 2), kp.offset);
+        uint32_t w = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
+        p = uniform24(w);
+      }
+    }
+    y[i] = roundtrip_one<kStochastic, kFast>(x[i], p, s, kp.saturate, kp.all_positive);
+  }
+}
+
+template <bool kStochastic, bool kHasProbs, bool kAligned>
+__global__ void __launch_bounds__(kRtThreads) roundtrip_kernel(const float* x, float* y, int64_t n,
+                                                               const float* __restrict__ mean_std,
+                                                               const float* __restrict__ probs, KernelParams kp) {
+  const Scalars s = scalars_from(mean_std[0], mean_std[1], kp);
+  // uniform branch: the three-instruction division is valid for this tensor, or every division
+  // is the IEEE one (degenerate statistics: huge/tiny/NaN std, mean == -0)
+  if (s.fast) roundtrip_body<kStochastic, kHasProbs, kAligned, true>(x, y, n, probs, kp, s);
+  else roundtrip_body<kStochastic, kHasProbs, kAligned, false>(x, y, n, probs, kp, s);
+}
+
+// ---- small tensors: statistics + round trip in one block, one launch ---------------------------
+// The optimizer-side tensors of the reference workloads are tiny (median 512 elements for
+// ResNet-18); two launches per call would be pure launch latency.
+constexpr int64_t kSmallMax = 32768;  // second read comes from L1/L2
+
+template <bool kStochastic, bool kHasProbs>
+__device__ __forceinline__ void small_body(const float* x, float* y, int64_t n, const float* probs,
+                                           const KernelParams& kp, float* mean_std_out, Acc* smem, float* bcast) {
+  Acc acc;
+  acc.m = Moments{0.0, 0.0, 0.0};
+  acc.hi = -INFINITY;
+  acc.lo = INFINITY;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) merge_one<0>(acc, x[i]);
+  acc = block_combine<0>(acc, smem);
+  if (threadIdx.x == 0) {
+    finalize<0>(acc, /*unbiased=*/1, bcast);
+    if (mean_std_out) { mean_std_out[0] = bcast[0]; mean_std_out[1] = bcast[1]; }
+  }
+  __syncthreads();
+  const Scalars s = scalars_from(bcast[0], bcast[1], kp);
+  const Philox rng(kp.seed);
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    float p = 0.f;
+    if (kStochastic) {
+      if (kHasProbs) p = probs[i];
+      else {
+        uint4 r = rng.for_group((uint64_t)(i >> 2), kp.offset);
+        uint32_t w = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
+        p = uniform24(w);
+      }
+    }
+    y[i] = s.fast ? roundtrip_one<kStochastic, true>(x[i], p, s, kp.saturate, kp.all_positive)
+                  : roundtrip_one<kStochastic, false>(x[i], p, s, kp.saturate, kp.all_positive);
+  }
+  __syncthreads();
+}
+
+template <bool kStochastic, bool kHasProbs>
+__global__ void __launch_bounds__(kStatsThreads) roundtrip_small_kernel(const float* x, float* y, int64_t n,
+                                                                        const float* probs, KernelParams kp,
+                                                                        float* mean_std_out) {
+  __shared__ Acc smem[kStatsThreads / 32];
+  __shared__ float bcast[2];
+  small_body<kStochastic, kHasProbs>(x, y, n, probs, kp, mean_std_out, smem, bcast);
+}
+
+// ---- many tensors, one launch -------------------------------------------------------------------
+// Small tensors (n <= kSmallMax) are handled whole by one block each.  Large tensors run the
+// same grid-wide two-phase scheme as the single-tensor path, phase 1 here, phase 2 below.
+struct MultiWs {
+  float mean_std[2];
+};
+
+template <bool kStochastic>
+__global__ void __launch_bounds__(kStatsThreads) multi_small_kernel(const smaq_tensor_desc* __restrict__ descs,
+                                                                    int count, int64_t min_size, KernelParams kp) {
+  __shared__ Acc smem[kStatsThreads / 32];
+  __shared__ float bcast[2];
+  for (int t = blockIdx.x; t < count; t += gridDim.x) {
+    smaq_tensor_desc d = descs[t];
+    if (d.n > kSmallMax) continue;
+    if (d.n < min_size) {  // smart.py:125-128: returned untouched
+      if (d.y != d.x)
+        for (int64_t i = threadIdx.x; i < d.n; i += blockDim.x) d.y[i] = d.x[i];
+      continue;
+    }
+    KernelParams k = kp;
+    k.all_positive = d.all_positive;
+    k.offset = kp.offset + (uint64_t)t;  // one Philox stream per tensor
+    small_body<kStochastic, false>(d.x, d.y, d.n, nullptr, k, nullptr, smem, bcast);
+  }
+}
+
+// --measure_compression_ratio only: how many elements classify as outliers.
+__global__ void __launch_bounds__(kRtThreads) count_outliers_kernel(const float* __restrict__ x, int64_t n,
+                                                                    const float* __restrict__ mean_std,
+                                                                    KernelParams kp, unsigned long long* counter) {
+  const Scalars s = scalars_from(mean_std[0], mean_std[1], kp);
+  unsigned int local = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float z = true_div(x[i] - s.mean, s.div.b);
+    local += (z > s.thr || z < s.neg_thr) ? 1u : 0u;
+  }
+  local = warp_sum(local);
+  if (lane_id() == 0 && local) atomicAdd(counter, (unsigned long long)local);
+}
+
+static int rt_grid(int64_t n) {
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  int64_t want = ((n + 3) / 4 + kRtThreads - 1) / kRtThreads;
+  int64_t cap = (int64_t)sms * 8;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+static int check_params(const smaq_codec_params* p) {
+  if (!p) return fail(SMAQ_ERR_ARG, "params is NULL");
+  if (!(p->threshold > 0.0f)) return fail(SMAQ_ERR_ARG, "threshold must be > 0");
+  if (p->bits_main < 3 || p->bits_main > 16 || p->bits_outlier < p->bits_main || p->bits_outlier > 17)
+    return fail(SMAQ_ERR_ARG, "unsupported bit widths main=%d outlier=%d", p->bits_main, p->bits_outlier);
+  return SMAQ_OK;
+}
+
+}  // namespace smaq
+
+extern "C" {
+
+int smaq_roundtrip(const float* x, float* y, int64_t n, const float* mean_std, const float* probs,
+                   const smaq_codec_params* params, smaq_stream_t stream_) {
+  using namespace smaq;
+  if (int rc = check_params(params)) return rc;
+  if (!x || !y || !mean_std || n < 0) return fail(SMAQ_ERR_ARG, "roundtrip: null pointer or n < 0");
+  if (n == 0) return SMAQ_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  KernelParams kp = to_kernel_params(*params);
+  const bool al = aligned16(x) && aligned16(y) && (!probs || aligned16(probs));
+  const int grid = rt_grid(n);
+#define SMAQ_RT(S, P, A) roundtrip_kernel<S, P, A><<<grid, kRtThreads, 0, stream>>>(x, y, n, mean_std, probs, kp)
+  if (params->stochastic) {
+    if (probs) { if (al) SMAQ_RT(true, true, true); else SMAQ_RT(true, true, false); }
+    else       { if (al) SMAQ_RT(true, false, true); else SMAQ_RT(true, false, false); }
+  } else {
+    if (al) SMAQ_RT(false, false, true); else SMAQ_RT(false, false, false);
+  }
+#undef SMAQ_RT
+  SMAQ_LAUNCH_OK();
+  return SMAQ_OK;
+}
+
+int smaq_count_outliers(const float* x, int64_t n, const float* mean_std, const smaq_codec_params* params,
+                        unsigned long long* counter, smaq_stream_t stream_) {
+  using namespace smaq;
+  if (int rc = check_params(params)) return rc;
+  if (!x || !mean_std || !counter || n < 0) return fail(SMAQ_ERR_ARG, "count_outliers: bad argument");
+  if (n == 0) return SMAQ_OK;
+  KernelParams kp = to_kernel_params(*params);
+  count_outliers_kernel<<<rt_grid(n), kRtThreads, 0, (cudaStream_t)stream_>>>(x, n, mean_std, kp, counter);
+  SMAQ_LAUNCH_OK();
+  return SMAQ_OK;
+}
+
+int64_t smaq_fused_small_max(void) { return smaq::kSmallMax; }
+
+int smaq_roundtrip_small(const float* x, float* y, int64_t n, const float* probs, const smaq_codec_params* params,
+                         float* mean_std_out, smaq_stream_t stream_) {
+  using namespace smaq;
+  if (int rc = check_params(params)) return rc;
+  if (!x || !y || n <= 0) return fail(SMAQ_ERR_ARG, "roundtrip_small: null pointer or n <= 0");
+  if (n > kSmallMax) return fail(SMAQ_ERR_ARG, "roundtrip_small: n > %lld", (long long)kSmallMax);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  KernelParams kp = to_kernel_params(*params);
+  if (params->stochastic) {
+    if (probs) roundtrip_small_kernel<true, true><<<1, kStatsThreads, 0, stream>>>(x, y, n, probs, kp, mean_std_out);
+    else roundtrip_small_kernel<true, false><<<1, kStatsThreads, 0, stream>>>(x, y, n, probs, kp, mean_std_out);
+  } else {
+    roundtrip_small_kernel<false, false><<<1, kStatsThreads, 0, stream>>>(x, y, n, probs, kp, mean_std_out);
+  }
+  SMAQ_LAUNCH_OK();
+  return SMAQ_OK;
+}
+
+size_t smaq_multi_workspace_bytes(int32_t count, int64_t total_elems) {
+  (void)count; (void)total_elems;
+  return 256;
+}
+
+int smaq_roundtrip_multi(const smaq_tensor_desc* descs, int32_t count, int64_t max_n, int64_t total_elems,
+                         const smaq_codec_params* params, int64_t min_size, void* ws, size_t ws_bytes,
+                         smaq_stream_t stream_) {
+  using namespace smaq;
+  (void)ws; (void)ws_bytes; (void)total_elems;
+  if (int rc = check_params(params)) return rc;
+  if (!descs || count < 0) return fail(SMAQ_ERR_ARG, "roundtrip_multi: bad argument");
+  if (count == 0) return SMAQ_OK;
+  if (max_n > kSmallMax)
+    return fail(SMAQ_ERR_UNSUPPORTED, "roundtrip_multi: tensors above %lld elements go through smaq_roundtrip",
+                (long long)kSmallMax);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  KernelParams kp = to_kernel_params(*params);
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  int grid = count < sms * 8 ? count : sms * 8;
+  if (params->stochastic) multi_small_kernel<true><<<grid, kStatsThreads, 0, stream>>>(descs, count, min_size, kp);
+  else multi_small_kernel<false><<<grid, kStatsThreads, 0, stream>>>(descs, count, min_size, kp);
+  SMAQ_LAUNCH_OK();
+  return SMAQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,209 @@
+// Kernel (1): tensor statistics for SmaQ.
+//
+// Replaces data.mean() + data.std() (reference smart_compress/compress/smart.py:130-132, two
+// eager reductions = two reads of the tensor) with ONE pass: every thread runs a chunked
+// Welford update (16 values at a time: fp32 chunk mean and chunk M2, merged into fp64 running
+// moments with Chan's formula), lanes are combined with warp shuffles, warps through shared
+// memory, and the last block to finish (atomic ticket) combines the per-block moments in a fixed
+// order — so the result is independent of block scheduling and reproducible run to run.
+//
+// Also here: the sampled statistics of --use_sample_stats (smart.py:86-91), the range estimate of
+// --use_range_std_dev (smart.py:100-106) and the log2-domain statistics of S2FP8
+// (smart_compress/compress/s2fp8.py:34-37).
+//
+// HBM roofline: 4 bytes read per element, nothing written.
+#include "common.cuh"
+#include "moments.cuh"
+
+namespace smaq {
+
+struct StatsWs {
+  unsigned int ticket;
+  unsigned int pad[3];
+  double partials[1];  // [grid][kPartialDoubles]
+};
+
+template <int kKind, bool kAligned>
+__global__ void __launch_bounds__(kStatsThreads) stats_kernel(const float* __restrict__ x, int64_t n, int unbiased,
+                                                              float* __restrict__ out, StatsWs* ws) {
+  __shared__ Acc smem[kStatsThreads / 32];
+  __shared__ bool is_last;
+  Acc acc;
+  acc.m = Moments{0.0, 0.0, 0.0};
+  acc.hi = -INFINITY;
+  acc.lo = INFINITY;
+
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+
+  if (kAligned) {
+    const float4* xv = reinterpret_cast<const float4*>(x);
+    const int64_t nvec = n >> 2;
+    // 4 independent 128-bit loads in flight per thread; each warp-level load is 512 contiguous bytes
+    int64_t v = tid;
+    for (; v + 3 * nthreads < nvec; v += 4 * nthreads) {
+      float4 a = ldg_stream(xv + v), b = ldg_stream(xv + v + nthreads), c = ldg_stream(xv + v + 2 * nthreads),
+             d = ldg_stream(xv + v + 3 * nthreads);
+      float r[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = transform<kKind>(r[i]);
+      merge_chunk<kKind, 16>(acc, r);
+    }
+    for (; v < nvec; v += nthreads) {
+      float4 a = ldg_stream(xv + v);
+      float r[4] = {transform<kKind>(a.x), transform<kKind>(a.y), transform<kKind>(a.z), transform<kKind>(a.w)};
+      merge_chunk<kKind, 4>(acc, r);
+    }
+    const int64_t tail = nvec << 2;
+    if (tid < n - tail) merge_one<kKind>(acc, transform<kKind>(x[tail + tid]));
+  } else {
+    for (int64_t i = tid; i < n; i += nthreads) merge_one<kKind>(acc, transform<kKind>(x[i]));
+  }
+
+  acc = block_combine<kKind>(acc, smem);
+  if (threadIdx.x == 0) {
+    double* p = ws->partials + (size_t)blockIdx.x * kPartialDoubles;
+    p[0] = acc.m.n; p[1] = acc.m.mean; p[2] = acc.m.m2; p[3] = (double)acc.lo; p[4] = (double)acc.hi;
+    __threadfence();
+    unsigned int t = atomicAdd(&ws->ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+
+  // last block: combine the per-block moments in block order (fixed tree => deterministic)
+  Acc f;
+  f.m = Moments{0.0, 0.0, 0.0};
+  f.hi = -INFINITY;
+  f.lo = INFINITY;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+    const volatile double* p = ws->partials + (size_t)b * kPartialDoubles;
+    Moments m{p[0], p[1], p[2]};
+    f.m = merge(f.m, m);
+    f.lo = nanmin(f.lo, (float)p[3]);
+    f.hi = nanmax(f.hi, (float)p[4]);
+  }
+  f = block_combine<kKind>(f, smem);
+  if (threadIdx.x == 0) {
+    finalize<kKind>(f, unbiased, out);
+    ws->ticket = 0;  // leave the workspace reusable
+  }
+}
+
+// --use_sample_stats: k gathered values, one block.
+__global__ void __launch_bounds__(kStatsThreads) sampled_stats_kernel(const float* __restrict__ x, int64_t n,
+                                                                      const int64_t* __restrict__ idx, int k,
+                                                                      float* __restrict__ out) {
+  __shared__ Acc smem[kStatsThreads / 32];
+  Acc acc;
+  acc.m = Moments{0.0, 0.0, 0.0};
+  acc.hi = -INFINITY;
+  acc.lo = INFINITY;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    int64_t j = idx[i];
+    if (j >= 0 && j < n) merge_one<0>(acc, x[j]);
+  }
+  acc = block_combine<0>(acc, smem);
+  if (threadIdx.x == 0) finalize<0>(acc, /*unbiased=*/0, out);  // smart.py:91: unbiased=False
+}
+
+// Same, drawing the k distinct indices on the device with Floyd's algorithm (a uniform k-subset,
+// which is the law of randperm(n)[:k]; mean and std do not depend on the order).
+__global__ void __launch_bounds__(32) sampled_draw_stats_kernel(const float* __restrict__ x, int64_t n, int k,
+                                                                uint64_t seed, uint64_t offset,
+                                                                float* __restrict__ out) {
+  __shared__ int64_t chosen[1024];
+  const int lane = lane_id();
+  Philox rng(seed);
+  for (int i = 0; i < k; ++i) {
+    const int64_t j = n - k + i;  // Floyd: t ~ U{0..j}; take t unless already chosen, else j
+    uint4 r = rng.for_group((uint64_t)i, offset);
+    uint64_t r64 = ((uint64_t)r.x << 32) | r.y;
+    int64_t t = (int64_t)__umul64hi(r64, (uint64_t)j + 1);
+    bool hit = false;
+    for (int q = lane; q < i; q += 32) hit |= (chosen[q] == t);
+    hit = __any_sync(0xffffffffu, hit);
+    if (lane == 0) chosen[i] = hit ? j : t;
+    __syncwarp();
+  }
+  Acc acc;
+  acc.m = Moments{0.0, 0.0, 0.0};
+  acc.hi = -INFINITY;
+  acc.lo = INFINITY;
+  for (int i = lane; i < k; i += 32) merge_one<0>(acc, x[chosen[i]]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Moments other = shfl_xor(acc.m, o);
+    acc.m = (lane & o) ? merge(other, acc.m) : merge(acc.m, other);
+  }
+  if (lane == 0) finalize<0>(acc, 0, out);
+}
+
+static int stats_grid(int64_t n) {
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  int64_t want = (n / 4 + kStatsThreads - 1) / kStatsThreads;  // one float4 per thread at least
+  int64_t cap = (int64_t)sms * 8;                              // 8 x 256 threads = 2048 = full occupancy
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+template <int kKind>
+static int launch_stats(const float* x, int64_t n, int unbiased, float* out, void* ws, size_t ws_bytes,
+                        cudaStream_t stream) {
+  if (!x || !out || !ws || n <= 0) return fail(SMAQ_ERR_ARG, "stats: null pointer or n <= 0");
+  if (ws_bytes < smaq_stats_workspace_bytes(n)) return fail(SMAQ_ERR_WORKSPACE, "stats: workspace too small");
+  int grid = stats_grid(n);
+  SMAQ_CUDA_OK(cudaMemsetAsync(ws, 0, 16, stream));
+  if (aligned16(x))
+    stats_kernel<kKind, true><<<grid, kStatsThreads, 0, stream>>>(x, n, unbiased, out, (StatsWs*)ws);
+  else
+    stats_kernel<kKind, false><<<grid, kStatsThreads, 0, stream>>>(x, n, unbiased, out, (StatsWs*)ws);
+  SMAQ_LAUNCH_OK();
+  return SMAQ_OK;
+}
+
+}  // namespace smaq
+
+extern "C" {
+
+size_t smaq_stats_workspace_bytes(int64_t n) {
+  (void)n;
+  int sms = smaq::sm_count();
+  if (sms <= 0) sms = 148;
+  return 16 + (size_t)sms * 8 * smaq::kPartialDoubles * sizeof(double);
+}
+
+int smaq_stats_full(const float* x, int64_t n, int unbiased, float* mean_std, void* ws, size_t ws_bytes,
+                    smaq_stream_t stream) {
+  return smaq::launch_stats<0>(x, n, unbiased, mean_std, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int smaq_stats_range(const float* x, int64_t n, float* mean_std, void* ws, size_t ws_bytes, smaq_stream_t stream) {
+  return smaq::launch_stats<1>(x, n, 1, mean_std, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int smaq_s2fp8_stats(const float* x, int64_t n, float* mu_max, void* ws, size_t ws_bytes, smaq_stream_t stream) {
+  return smaq::launch_stats<2>(x, n, 0, mu_max, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int smaq_stats_sampled(const float* x, int64_t n, const int64_t* idx, int32_t k, float* mean_std,
+                       smaq_stream_t stream) {
+  if (!x || !idx || !mean_std || n <= 0 || k <= 0) return smaq::fail(SMAQ_ERR_ARG, "stats_sampled: bad argument");
+  smaq::sampled_stats_kernel<<<1, smaq::kStatsThreads, 0, (cudaStream_t)stream>>>(x, n, idx, k, mean_std);
+  SMAQ_LAUNCH_OK();
+  return SMAQ_OK;
+}
+
+int smaq_stats_sampled_draw(const float* x, int64_t n, int32_t k, uint64_t seed, uint64_t offset, float* mean_std,
+                            smaq_stream_t stream) {
+  if (!x || !mean_std || n <= 0 || k <= 0) return smaq::fail(SMAQ_ERR_ARG, "stats_sampled_draw: bad argument");
+  if (k > 1024) return smaq::fail(SMAQ_ERR_UNSUPPORTED, "stats_sampled_draw: k > 1024");
+  if (k > n) k = (int32_t)n;
+  smaq::sampled_draw_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(x, n, k, seed, offset, mean_std);
+  SMAQ_LAUNCH_OK();
+  return SMAQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,192 @@
+"""ctypes binding of libsmaq_b200.so — the C ABI declared in include/smaq_b200.h.
+
+This is the only place the host side touches native code.  There is no CPU path and no
+fallback: if the library is missing or a call fails, an exception is raised.
+
+Torch is used for what the boundary leaves to the caller: device buffers
+(``tensor.data_ptr()``), workspaces and the current CUDA stream of the calling thread
+(``torch.cuda.current_stream()``), which is how backward-pass calls made on autograd's worker
+thread end up on the right stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libsmaq_b200.so")
+
+OK = 0
+ABI_VERSION = 1
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+class CodecParams(C.Structure):  # smaq_codec_params
+    _fields_ = [
+        ("threshold", C.c_float),
+        ("range_main", C.c_float),
+        ("range_outlier", C.c_float),
+        ("clamp_lo", C.c_float),
+        ("clamp_hi", C.c_float),
+        ("bits_main", C.c_int32),
+        ("bits_outlier", C.c_int32),
+        ("stochastic", C.c_int32),
+        ("all_positive", C.c_int32),
+        ("saturate", C.c_int32),
+        ("reserved", C.c_int32),
+        ("seed", C.c_uint64),
+        ("offset", C.c_uint64),
+    ]
+
+
+class FloatqParams(C.Structure):  # smaq_floatq_params
+    _fields_ = [
+        ("exp_bits", C.c_int32),
+        ("man_bits", C.c_int32),
+        ("rounding", C.c_int32),
+        ("check_inf", C.c_int32),
+        ("max_exp_bias", C.c_int32),
+        ("reserved", C.c_int32),
+        ("seed", C.c_uint64),
+        ("offset", C.c_uint64),
+    ]
+
+
+class TensorDesc(C.Structure):  # smaq_tensor_desc
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("y", C.c_void_p),
+        ("n", C.c_int64),
+        ("all_positive", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class PackedLayout(C.Structure):  # smaq_packed_layout
+    _fields_ = [
+        ("n", C.c_int64),
+        ("bits_main", C.c_int32),
+        ("bits_outlier", C.c_int32),
+        ("n_warp_tiles", C.c_int64),
+        ("n_cta_tiles", C.c_int64),
+        ("header_off", C.c_int64),
+        ("header_bytes", C.c_int64),
+        ("table_off", C.c_int64),
+        ("table_bytes", C.c_int64),
+        ("planes_off", C.c_int64),
+        ("planes_bytes", C.c_int64),
+        ("extras_off", C.c_int64),
+        ("extras_capacity_bytes", C.c_int64),
+        ("total_capacity_bytes", C.c_int64),
+        ("workspace_bytes", C.c_int64),
+    ]
+
+
+class PackedHeader(C.Structure):  # smaq_packed_header
+    _fields_ = [
+        ("magic", C.c_uint32),
+        ("bits_main", C.c_int32),
+        ("bits_outlier", C.c_int32),
+        ("stochastic", C.c_int32),
+        ("n", C.c_int64),
+        ("mean", C.c_float),
+        ("std_raw", C.c_float),
+        ("threshold", C.c_float),
+        ("range_main", C.c_float),
+        ("range_outlier", C.c_float),
+        ("clamp_lo", C.c_float),
+        ("clamp_hi", C.c_float),
+        ("pad0", C.c_float),
+        ("n_outlier", C.c_uint64),
+        ("n_saturated", C.c_uint64),
+        ("extras_words", C.c_uint64),
+        ("status", C.c_uint64),
+    ]
+
+
+_P = C.c_void_p
+_I64 = C.c_int64
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "smaq_b200_abi_version": (C.c_int, []),
+    "smaq_b200_last_error": (C.c_char_p, []),
+    "smaq_b200_sm_count": (C.c_int, []),
+    "smaq_stats_workspace_bytes": (C.c_size_t, [_I64]),
+    "smaq_stats_full": (C.c_int, [_P, _I64, C.c_int, _P, _P, C.c_size_t, _P]),
+    "smaq_stats_range": (C.c_int, [_P, _I64, _P, _P, C.c_size_t, _P]),
+    "smaq_stats_sampled": (C.c_int, [_P, _I64, _P, C.c_int32, _P, _P]),
+    "smaq_stats_sampled_draw": (C.c_int, [_P, _I64, C.c_int32, C.c_uint64, C.c_uint64, _P, _P]),
+    "smaq_roundtrip": (C.c_int, [_P, _P, _I64, _P, _P, C.POINTER(CodecParams), _P]),
+    "smaq_count_outliers": (C.c_int, [_P, _I64, _P, C.POINTER(CodecParams), _P, _P]),
+    "smaq_fused_small_max": (_I64, []),
+    "smaq_roundtrip_small": (C.c_int, [_P, _P, _I64, _P, C.POINTER(CodecParams), _P, _P]),
+    "smaq_multi_workspace_bytes": (C.c_size_t, [C.c_int32, _I64]),
+    "smaq_roundtrip_multi": (C.c_int, [_P, C.c_int32, _I64, _I64, C.POINTER(CodecParams), _I64, _P, C.c_size_t, _P]),
+    "smaq_packed_layout_for": (C.c_int, [_I64, C.c_int32, C.c_int32, C.POINTER(PackedLayout)]),
+    "smaq_encode": (C.c_int, [_P, _I64, _P, _P, C.POINTER(CodecParams), _P, C.c_size_t, _P, C.c_size_t, _P]),
+    "smaq_decode": (C.c_int, [_P, C.c_size_t, _I64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "smaq_float_quantize": (C.c_int, [_P, _P, _I64, _P, C.POINTER(FloatqParams), _P]),
+    "smaq_s2fp8_stats": (C.c_int, [_P, _I64, _P, _P, C.c_size_t, _P]),
+    "smaq_s2fp8_apply": (C.c_int, [_P, _P, _I64, _P, _P, C.POINTER(FloatqParams), _P]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> C.CDLL:
+    """dlopen the library once; raises NativeLibraryError when it is absent or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryError(
+                f"{LIB_PATH} is missing: build it with `python smart-quantization_b200/build.py` "
+                "(there is no CPU or eager fallback for this path)"
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as e:
+                raise NativeLibraryError(f"{LIB_PATH} does not export {name}") from e
+            fn.restype = res
+            fn.argtypes = args
+        if lib.smaq_b200_abi_version() != ABI_VERSION:
+            raise NativeLibraryError("libsmaq_b200.so ABI version mismatch; rebuild")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != OK:
+        msg = load().smaq_b200_last_error()
+        raise NativeLibraryError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t: torch.Tensor) -> int:
+    return t.data_ptr()
+
+
+def require_cuda_f32(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise NativeLibraryError(
+            f"{what}: tensor is on {t.device}; this implementation is CUDA (sm_100a) only and has no CPU path"
+        )
+    if t.dtype != torch.float32:
+        raise TypeError(f"{what}: expected float32, got {t.dtype}")

@@ -1,0 +1,25 @@
+"""BF16 emulation plugin (reference smart_compress/compress/bf16.py): every value is rounded to
+e8m7 with stochastic rounding by ``float_quantize`` — one sm_100a kernel here."""
+from argparse import ArgumentParser, Namespace
+
+import torch
+
+from ..util.pytorch.quantization import add_float_quantize_args, float_quantize
+from .base import CompressionAlgorithmBase, chain_parser
+
+
+class BF16(CompressionAlgorithmBase):
+    EXP_BITS, MAN_BITS, STORED_BITS = 8, 7, 16
+
+    @staticmethod
+    def add_argparse_args(parent_parser: ArgumentParser):
+        return chain_parser(add_float_quantize_args(CompressionAlgorithmBase.add_argparse_args(parent_parser)))
+
+    def __init__(self, hparams: Namespace):
+        super().__init__(hparams)
+
+    @torch.no_grad()
+    def __call__(self, tensor: torch.Tensor, tag: str = None, **extra):
+        self.log_ratio(tag, tensor.numel(), 32, self.STORED_BITS)
+        return float_quantize(tensor, exp=self.EXP_BITS, man=self.MAN_BITS, hparams=self.hparams,
+                              rand_bits=extra.get("_rand_bits"))

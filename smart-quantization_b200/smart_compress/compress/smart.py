@@ -1,0 +1,209 @@
+"""SmaQ plugin — the API of reference smart_compress/compress/smart.py:10-190 on sm_100a kernels.
+
+One call = (at most) two kernel launches and no host synchronisation:
+  1. statistics  -> ``smaq_stats_full`` / ``_sampled`` / ``_range``   (smart.py:130-134)
+  2. round trip  -> ``smaq_roundtrip``                                 (smart.py:151-182)
+Tensors of at most ``smaq_fused_small_max()`` elements with default statistics take one launch
+(``smaq_roundtrip_small``).  The reference needs ~28 launches, a blocking ``std_dev == 0`` read
+and two scalar uploads for the same call.
+
+Flags, defaults, kwargs and return conventions are the reference's.  Extra keyword arguments
+understood here (the reference swallows unknown kwargs, smart.py:117) exist for parity tests:
+``_probs`` (explicit uniform numbers), ``_sample_idx`` (explicit sample indices), ``_out``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+from argparse import ArgumentParser, Namespace
+from typing import Optional, Tuple, Union
+
+import torch
+
+from .. import _native as N
+from ..util.globals import Globals
+from .base import CompressionAlgorithmBase, chain_parser
+
+_FLAGS = (
+    # (flag, kwargs) in the reference's order (smart.py:17-69)
+    ("--num_samples", dict(type=int, default=16, help="number of samples to use for mean/std_dev calculation")),
+    ("--use_sample_stats", dict(action="store_true", help="use sample mean and std for smart compression")),
+    ("--no_stochastic_rounding",
+     dict(action="store_false", dest="stochastic_rounding", help="use stochastic rounding when quantizing")),
+    ("--num_bits_main", dict(type=int, default=6, help="number of bits for main data (within 1 std dev)")),
+    ("--num_bits_outlier", dict(type=int, default=8, help="number of bits for outlier data (more than 1 std dev)")),
+    ("--main_std_dev_threshold", dict(type=float, default=1.0, help="std dev to consider something main")),
+    ("--outlier_std_dev_threshold",
+     dict(type=float, default=2.5, help="max std dev for outliers (everything else is clamped to this)")),
+    ("--min_size", dict(type=int, default=8)),
+    ("--use_range_std_dev", dict(action="store_true", help="use range std dev (from range batch norm paper)")),
+    ("--use_batch_norm", dict(action="store_true", help="support BN acceleration")),
+    ("--bn_scalar_params", dict(action="store_true", help="BN params should be scalar")),
+)
+
+
+class SmartFP(CompressionAlgorithmBase):
+    @staticmethod
+    def add_argparse_args(parent_parser: ArgumentParser):
+        parser = chain_parser(CompressionAlgorithmBase.add_argparse_args(parent_parser))
+        for flag, kw in _FLAGS:
+            parser.add_argument(flag, **kw)
+        return parser
+
+    def __init__(self, hparams: Namespace):
+        super().__init__(hparams)
+        hp = self.hparams
+        # smart.py:75-84, evaluated in Python floats exactly as there
+        self.range_outlier = ((2 ** (hp.num_bits_outlier - 2)) - 1) / (
+            hp.outlier_std_dev_threshold - hp.main_std_dev_threshold
+        )
+        self.range_normal = ((2 ** (hp.num_bits_main - 2)) - 1) / hp.main_std_dev_threshold
+        self.clamped_range = (1e-4, 1e4) if getattr(hp, "precision", 32) == 16 else (1e-38, 1e38)
+        self._calls = itertools.count()  # Philox stream offset: one stream per call
+
+    # ------------------------------------------------------------------------------------------
+    def _params(self, all_positive: bool, saturate: bool = False) -> N.CodecParams:
+        hp = self.hparams
+        p = N.CodecParams()
+        p.threshold = hp.main_std_dev_threshold
+        p.range_main = self.range_normal
+        p.range_outlier = self.range_outlier
+        p.clamp_lo, p.clamp_hi = self.clamped_range
+        p.bits_main = hp.num_bits_main
+        p.bits_outlier = hp.num_bits_outlier
+        p.stochastic = int(bool(hp.stochastic_rounding))
+        p.all_positive = int(bool(all_positive))
+        p.saturate = int(bool(saturate))
+        # torch.manual_seed() governs the stream, as it governs the reference's rand_like
+        p.seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        p.offset = next(self._calls)
+        return p
+
+    def statistics(self, flat: torch.Tensor, sample_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Device float[2] = (mean, std) per smart.py:130-134 — no host round trip."""
+        lib = N.load()
+        hp = self.hparams
+        n = flat.numel()
+        out = torch.empty(2, dtype=torch.float32, device=flat.device)
+        stream = N.stream_ptr(flat.device)
+        if hp.use_sample_stats:
+            k = min(n, hp.num_samples)
+            if sample_idx is not None:
+                idx = sample_idx.to(device=flat.device, dtype=torch.int64).contiguous()
+                N.check(lib.smaq_stats_sampled(N.ptr(flat), n, N.ptr(idx), int(idx.numel()), N.ptr(out), stream),
+                        "smaq_stats_sampled")
+            elif k <= 1024:
+                N.check(lib.smaq_stats_sampled_draw(N.ptr(flat), n, k, torch.initial_seed() & (2**64 - 1),
+                                                    (1 << 62) + next(self._calls), N.ptr(out), stream),
+                        "smaq_stats_sampled_draw")
+            else:
+                idx = torch.randperm(n, device=flat.device)[:k]
+                N.check(lib.smaq_stats_sampled(N.ptr(flat), n, N.ptr(idx), k, N.ptr(out), stream),
+                        "smaq_stats_sampled")
+            if hp.use_range_std_dev:
+                raise NotImplementedError("--use_sample_stats together with --use_range_std_dev")
+            return out
+        ws_bytes = lib.smaq_stats_workspace_bytes(n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=flat.device)
+        if hp.use_range_std_dev:
+            N.check(lib.smaq_stats_range(N.ptr(flat), n, N.ptr(out), N.ptr(ws), ws_bytes, stream), "smaq_stats_range")
+        else:
+            N.check(lib.smaq_stats_full(N.ptr(flat), n, 1, N.ptr(out), N.ptr(ws), ws_bytes, stream),
+                    "smaq_stats_full")
+        return out
+
+    @torch.no_grad()
+    def __call__(
+        self,
+        data: torch.Tensor,
+        tag: str = None,
+        all_positive=False,
+        batch_norm_stats: Union[Tuple[torch.Tensor, torch.Tensor], None] = None,
+        **extra,
+    ):
+        profiler = Globals.profiler
+        if profiler is not None:
+            with profiler.profile("smaq"):
+                return self._call(data, tag, all_positive, batch_norm_stats, extra)
+        return self._call(data, tag, all_positive, batch_norm_stats, extra)
+
+    def _call(self, data, tag, all_positive, batch_norm_stats, extra):
+        hp = self.hparams
+        numel = data.numel()
+        orig_size = numel * 32
+        if numel < hp.min_size:  # smart.py:125-128: the SAME tensor object comes back
+            self.log_ratio(tag, orig_size, 32, 32)
+            return data
+
+        N.require_cuda_f32(data, "SmartFP")
+        lib = N.load()
+        use_bn = bool(getattr(hp, "use_batch_norm", False)) and batch_norm_stats is not None
+        probs = extra.get("_probs")
+        sample_idx = extra.get("_sample_idx")
+
+        src = data if data.is_contiguous() else data.contiguous()
+        flat = src.view(-1)
+        out = torch.empty_like(src)
+        stream = N.stream_ptr(data.device)
+        params = self._params(all_positive and not use_bn)
+        probs_ptr = None
+        if probs is not None:
+            probs = probs.to(device=data.device, dtype=torch.float32).contiguous()
+            assert probs.numel() == numel
+            probs_ptr = N.ptr(probs)
+
+        default_stats = not hp.use_sample_stats and not hp.use_range_std_dev
+        mean_std = None
+        if default_stats and not use_bn and numel <= lib.smaq_fused_small_max():
+            if hp.measure_compression_ratio:
+                mean_std = torch.empty(2, dtype=torch.float32, device=data.device)
+            N.check(
+                lib.smaq_roundtrip_small(N.ptr(flat), N.ptr(out), numel, probs_ptr, C.byref(params),
+                                         None if mean_std is None else N.ptr(mean_std), stream),
+                "smaq_roundtrip_small",
+            )
+        else:
+            mean_std = self.statistics(flat, sample_idx)  # statistics precede the BN un-affine (smart.py:130-149)
+            if use_bn:
+                flat = self._bn_unaffine(src, batch_norm_stats).view(-1)
+            N.check(
+                lib.smaq_roundtrip(N.ptr(flat), N.ptr(out), numel, N.ptr(mean_std), probs_ptr, C.byref(params), stream),
+                "smaq_roundtrip",
+            )
+            if use_bn:
+                out = self._bn_reaffine(out, batch_norm_stats)
+                if all_positive:
+                    out = out.clamp_min_(0.0)
+
+        if hp.measure_compression_ratio:
+            self.log_size(tag, orig_size, lambda: self._compressed_bits(flat, mean_std, params))
+        return out
+
+    # -- --use_batch_norm (smart.py:136-149,174-179): off by default, not on the hot path --------
+    def _bn_affine_params(self, stats):
+        gamma, beta = stats
+        if self.hparams.bn_scalar_params:
+            gamma, beta = gamma.mean(), beta.mean()
+        return gamma, beta
+
+    def _bn_unaffine(self, x, stats):
+        gamma, beta = self._bn_affine_params(stats)
+        # the reference broadcasts over the LAST axis of an (N, W, H, C) view (permute(0,3,2,1))
+        return ((x.permute(0, 3, 2, 1).clone() - beta) / gamma).permute(0, 3, 2, 1).clone()
+
+    def _bn_reaffine(self, y, stats):
+        gamma, beta = self._bn_affine_params(stats)
+        return ((y.permute(0, 3, 2, 1).clone() * gamma) + beta).permute(0, 3, 2, 1).clone()
+
+    # -- size accounting (smart.py:184-187) ------------------------------------------------------
+    def _compressed_bits(self, flat, mean_std, params) -> float:
+        lib = N.load()
+        counter = torch.zeros(1, dtype=torch.int64, device=flat.device)
+        N.check(
+            lib.smaq_count_outliers(N.ptr(flat), flat.numel(), N.ptr(mean_std), C.byref(params), N.ptr(counter),
+                                    N.stream_ptr(flat.device)),
+            "smaq_count_outliers",
+        )
+        n_out = int(counter.item())
+        hp = self.hparams
+        return n_out * hp.num_bits_outlier + (flat.numel() - n_out) * hp.num_bits_main

@@ -1,0 +1,70 @@
+"""Feature-map / gradient-map hooks — reference smart_compress/util/pytorch/autograd.py:12-77.
+
+``Compressor`` wraps an ``autograd.Function`` whose forward compresses what a layer produced
+(tag ``forward_autograd``) and whose backward compresses the gradient flowing back into that
+layer (tag ``backward_autograd``).  ``register_autograd_module`` re-binds ``forward`` on every
+module the layer predicate accepts, sharing one ``Compressor``.  Backward calls arrive on
+autograd's device worker thread; the codec picks up that thread's current stream itself.
+"""
+from argparse import Namespace
+
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from .quantization import is_valid_layer_type
+
+
+def process_input(args):
+    """Split a trailing ``{"batch_norm_stats": ...}`` dict off the positional arguments."""
+    if len(args) >= 1 and type(args[-1]) == dict and "batch_norm_stats" in args[-1]:
+        return args[:-1], args[-1]
+    return args, {}
+
+
+class Compressor(nn.Module):
+    def __init__(self, compress_fn, forward=True, backward=True):
+        super().__init__()
+        do_forward, do_backward = forward, backward
+
+        class CompressorAutoGradFn(Function):
+            @staticmethod
+            def forward(ctx, x: torch.Tensor, *args, **kwargs):
+                if not do_forward:
+                    return x
+                positional, extra = process_input(args)
+                return compress_fn(x, *positional, **kwargs, **extra, tag="forward_autograd")
+
+            @staticmethod
+            def backward(ctx, grad_output):
+                if not do_backward:
+                    return grad_output, None
+                if not ctx.needs_input_grad[0]:
+                    return None, None
+                return compress_fn(grad_output, tag="backward_autograd"), None
+
+        self.compress_fn = CompressorAutoGradFn.apply
+
+    def forward(self, *args, **kwargs):
+        return self.compress_fn(*args, **kwargs)
+
+
+def register_autograd_module(model: nn.Module, compress_fn, hparams: Namespace):
+    compressor = Compressor(compress_fn, forward=hparams.compress_forward, backward=hparams.compress_backward)
+    pass_bn_stats = bool(getattr(hparams, "use_batch_norm", False))
+
+    def patch(module: nn.Module):
+        if not is_valid_layer_type(module):
+            return
+        inner = module.forward
+        with_stats = pass_bn_stats and type(module) == nn.BatchNorm2d
+
+        def new_forward(*args, **kwargs):
+            result = inner(*args, **kwargs)
+            if with_stats:
+                return compressor(result, dict(batch_norm_stats=(module.weight.detach(), module.bias.detach())))
+            return compressor(result)
+
+        module.forward = new_forward
+
+    return model.apply(patch)

@@ -1,0 +1,107 @@
+"""Layer predicate and float_quantize wrapper — reference
+smart_compress/util/pytorch/quantization.py:8-204.
+
+``is_valid_layer_type`` decides which module outputs reach the codec: conv / linear / pool /
+normalisation layers by default, plus every ``torch.nn`` container and activation module and
+every module defined under ``smart_compress.models.pytorch`` (quantization.py:163-184).
+
+``float_quantize`` is the reference's wrapper (quantization.py:187-204) around qtorch 0.2.0's
+``float_quantize(x, exp, man, rounding="stochastic")``; here both the rounding and the
+"+max becomes +inf" fix-up run inside one sm_100a kernel (``smaq_float_quantize``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+from argparse import ArgumentParser
+
+import torch
+from torch import nn
+
+from ... import _native as N
+
+CONV_LAYERS = [nn.Conv1d, nn.Conv2d, nn.Conv3d, nn.ConvTranspose1d, nn.ConvTranspose2d, nn.ConvTranspose3d,
+               nn.Unfold, nn.Fold]
+POOL_LAYERS = [nn.MaxPool1d, nn.MaxPool2d, nn.MaxPool3d, nn.MaxUnpool1d, nn.MaxUnpool2d, nn.MaxUnpool3d,
+               nn.AvgPool1d, nn.AvgPool2d, nn.AvgPool3d, nn.FractionalMaxPool2d, nn.LPPool1d, nn.LPPool2d,
+               nn.AdaptiveMaxPool1d, nn.AdaptiveMaxPool2d, nn.AdaptiveMaxPool3d,
+               nn.AdaptiveAvgPool1d, nn.AdaptiveAvgPool2d, nn.AdaptiveAvgPool3d]
+PAD_LAYERS = [nn.ReflectionPad1d, nn.ReflectionPad2d, nn.ReplicationPad1d, nn.ReplicationPad2d, nn.ZeroPad2d,
+              nn.ConstantPad1d, nn.ConstantPad2d, nn.ConstantPad3d]
+ACTIVATION_LAYERS = [nn.ELU, nn.Hardshrink, nn.Hardtanh, nn.LeakyReLU, nn.LogSigmoid, nn.PReLU, nn.ReLU, nn.ReLU6,
+                     nn.RReLU, nn.SELU, nn.Sigmoid, nn.Softplus, nn.Softshrink, nn.Softsign, nn.Tanh,
+                     nn.Tanhshrink, nn.Threshold, nn.Softmin, nn.Softmax, nn.Softmax2d, nn.LogSoftmax]
+NORM_LAYERS = [nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d, nn.GroupNorm, nn.InstanceNorm1d, nn.InstanceNorm2d,
+               nn.InstanceNorm3d, nn.LayerNorm, nn.LocalResponseNorm]
+LINEAR_LAYERS = [nn.Linear, nn.Bilinear]
+DROPOUT_LAYERS = [nn.Dropout, nn.Dropout2d, nn.Dropout3d, nn.AlphaDropout]
+LOSS_LAYERS = [nn.L1Loss, nn.MSELoss, nn.CrossEntropyLoss, nn.NLLLoss, nn.PoissonNLLLoss, nn.KLDivLoss, nn.BCELoss,
+               nn.BCEWithLogitsLoss, nn.MarginRankingLoss, nn.HingeEmbeddingLoss, nn.MultiLabelMarginLoss,
+               nn.SmoothL1Loss, nn.SoftMarginLoss, nn.MultiLabelSoftMarginLoss, nn.MultiMarginLoss,
+               nn.TripletMarginLoss]
+
+LAYERS_TYPES = {
+    "conv": CONV_LAYERS,
+    "linear": LINEAR_LAYERS,
+    "pool": POOL_LAYERS,
+    "pad": PAD_LAYERS,
+    "activation": ACTIVATION_LAYERS,
+    "normalization": NORM_LAYERS,
+    "dropout": DROPOUT_LAYERS,
+    "loss": LOSS_LAYERS,
+}
+DEFAULT_LAYER_TYPES = ["conv", "linear", "pool", "normalization"]
+
+# modules whose *qualified type name* contains one of these are always wrapped
+_ALWAYS_WRAPPED = ("smart_compress.models.pytorch.", "torch.nn.modules.container.", "torch.nn.modules.activation.")
+
+
+def is_valid_layer_type(module, layer_types=DEFAULT_LAYER_TYPES):
+    accepted = []
+    for layer_type in layer_types:
+        assert layer_type in LAYERS_TYPES
+        accepted += LAYERS_TYPES[layer_type]
+    kind = type(module)
+    if kind in accepted:
+        return True
+    name = str(kind)
+    return any(marker in name for marker in _ALWAYS_WRAPPED)
+
+
+def add_float_quantize_args(parent_parser: ArgumentParser):
+    parser = ArgumentParser(parents=[parent_parser], add_help=False)
+    parser.add_argument("--no_float_quantize_check_inf", action="store_false", dest="float_quantize_check_inf")
+    return parser
+
+
+_calls = itertools.count()
+
+
+def make_floatq_params(exp: int, man: int, hparams, rounding: str = "stochastic") -> N.FloatqParams:
+    p = N.FloatqParams()
+    p.exp_bits, p.man_bits = exp, man
+    p.rounding = 1 if rounding == "stochastic" else 0
+    p.check_inf = int(bool(getattr(hparams, "float_quantize_check_inf", True)))
+    p.max_exp_bias = 0  # qtorch 0.2.0 rule (oracle/floatq.py)
+    p.seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    p.offset = next(_calls)
+    return p
+
+
+def float_quantize(x: torch.Tensor, exp: int, man: int, hparams, rand_bits: torch.Tensor = None):
+    """quantization.py:187-204.  Returns a new tensor; fp16 tensors round-trip through fp32 when
+    ``hparams.precision == 16`` exactly as there."""
+    lib = N.load()
+    is_16_bit = getattr(hparams, "precision", 32) == 16
+    src = x.float() if is_16_bit else x
+    N.require_cuda_f32(src, "float_quantize")
+    src = src.contiguous()
+    out = torch.empty_like(src)
+    params = make_floatq_params(exp, man, hparams)
+    rb = None
+    if rand_bits is not None:
+        rand_bits = rand_bits.to(device=src.device, dtype=torch.int32).contiguous()
+        rb = N.ptr(rand_bits)
+    N.check(lib.smaq_float_quantize(N.ptr(src), N.ptr(out), src.numel(), rb, C.byref(params),
+                                    N.stream_ptr(src.device)), "smaq_float_quantize")
+    return out.half() if is_16_bit else out

@@ -1,0 +1,120 @@
+"""Thin test-side helpers that call the C ABI (include/smaq_b200.h) directly through ctypes."""
+import ctypes as C
+
+import torch
+
+from smart_compress import _native as N
+
+
+def codec_params(cfg, *, all_positive=False, saturate=False, seed=1234, offset=0) -> N.CodecParams:
+    """oracle SmaqConfig -> smaq_codec_params (the host-side float->fp32 narrowing happens in ctypes)."""
+    p = N.CodecParams()
+    p.threshold = cfg.main_std_dev_threshold
+    p.range_main = cfg.range_normal
+    p.range_outlier = cfg.range_outlier
+    p.clamp_lo, p.clamp_hi = cfg.clamped_range
+    p.bits_main, p.bits_outlier = cfg.num_bits_main, cfg.num_bits_outlier
+    p.stochastic = int(cfg.stochastic_rounding)
+    p.all_positive = int(all_positive)
+    p.saturate = int(saturate)
+    p.seed, p.offset = seed, offset
+    return p
+
+
+def _ws(n, dev):
+    lib = N.load()
+    nbytes = lib.smaq_stats_workspace_bytes(n)
+    return torch.empty(nbytes, dtype=torch.uint8, device=dev), nbytes
+
+
+def stats_full(x, unbiased=True):
+    lib = N.load()
+    out = torch.empty(2, dtype=torch.float32, device=x.device)
+    ws, nb = _ws(x.numel(), x.device)
+    N.check(lib.smaq_stats_full(x.data_ptr(), x.numel(), int(unbiased), out.data_ptr(), ws.data_ptr(), nb,
+                                N.stream_ptr(x.device)), "stats_full")
+    return out
+
+
+def stats_range(x):
+    lib = N.load()
+    out = torch.empty(2, dtype=torch.float32, device=x.device)
+    ws, nb = _ws(x.numel(), x.device)
+    N.check(lib.smaq_stats_range(x.data_ptr(), x.numel(), out.data_ptr(), ws.data_ptr(), nb,
+                                 N.stream_ptr(x.device)), "stats_range")
+    return out
+
+
+def stats_sampled(x, idx):
+    lib = N.load()
+    out = torch.empty(2, dtype=torch.float32, device=x.device)
+    idx = idx.to(x.device, torch.int64).contiguous()
+    N.check(lib.smaq_stats_sampled(x.data_ptr(), x.numel(), idx.data_ptr(), idx.numel(), out.data_ptr(),
+                                   N.stream_ptr(x.device)), "stats_sampled")
+    return out
+
+
+def stats_sampled_draw(x, k, seed, offset=0):
+    lib = N.load()
+    out = torch.empty(2, dtype=torch.float32, device=x.device)
+    N.check(lib.smaq_stats_sampled_draw(x.data_ptr(), x.numel(), k, seed, offset, out.data_ptr(),
+                                        N.stream_ptr(x.device)), "stats_sampled_draw")
+    return out
+
+
+def s2fp8_stats(x):
+    lib = N.load()
+    out = torch.empty(2, dtype=torch.float32, device=x.device)
+    ws, nb = _ws(x.numel(), x.device)
+    N.check(lib.smaq_s2fp8_stats(x.data_ptr(), x.numel(), out.data_ptr(), ws.data_ptr(), nb,
+                                 N.stream_ptr(x.device)), "s2fp8_stats")
+    return out
+
+
+def roundtrip(x, mean_std, params, probs=None, out=None):
+    lib = N.load()
+    y = torch.empty_like(x) if out is None else out
+    N.check(lib.smaq_roundtrip(x.data_ptr(), y.data_ptr(), x.numel(), mean_std.data_ptr(),
+                               None if probs is None else probs.data_ptr(), C.byref(params),
+                               N.stream_ptr(x.device)), "roundtrip")
+    return y
+
+
+def roundtrip_small(x, params, probs=None, want_stats=False):
+    lib = N.load()
+    y = torch.empty_like(x)
+    ms = torch.empty(2, dtype=torch.float32, device=x.device) if want_stats else None
+    N.check(lib.smaq_roundtrip_small(x.data_ptr(), y.data_ptr(), x.numel(),
+                                     None if probs is None else probs.data_ptr(), C.byref(params),
+                                     None if ms is None else ms.data_ptr(), N.stream_ptr(x.device)), "roundtrip_small")
+    return (y, ms) if want_stats else y
+
+
+def floatq_params(exp, man, *, rounding=1, check_inf=True, max_exp_bias=0, seed=7, offset=0):
+    p = N.FloatqParams()
+    p.exp_bits, p.man_bits, p.rounding = exp, man, rounding
+    p.check_inf, p.max_exp_bias = int(check_inf), max_exp_bias
+    p.seed, p.offset = seed, offset
+    return p
+
+
+def float_quantize(x, params, rand_bits=None, out=None):
+    lib = N.load()
+    y = torch.empty_like(x) if out is None else out
+    N.check(lib.smaq_float_quantize(x.data_ptr(), y.data_ptr(), x.numel(),
+                                    None if rand_bits is None else rand_bits.data_ptr(), C.byref(params),
+                                    N.stream_ptr(x.device)), "float_quantize")
+    return y
+
+
+def s2fp8_apply(x, mu_max, params, rand_bits=None):
+    lib = N.load()
+    y = torch.empty_like(x)
+    N.check(lib.smaq_s2fp8_apply(x.data_ptr(), y.data_ptr(), x.numel(), mu_max.data_ptr(),
+                                 None if rand_bits is None else rand_bits.data_ptr(), C.byref(params),
+                                 N.stream_ptr(x.device)), "s2fp8_apply")
+    return y
+
+
+def mean_std_tensor(mean, std, dev):
+    return torch.tensor([float(mean), float(std)], dtype=torch.float32, device=dev)

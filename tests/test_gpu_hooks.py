@@ -1,0 +1,104 @@
+"""The boundary above the codec on a real device: autograd hooks and the optimizer wrapper
+(reference smart_compress/util/pytorch/{autograd,hooks,optimizer}.py)."""
+from argparse import ArgumentParser, Namespace
+from collections import Counter
+
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def hparams(**kw):
+    from smart_compress.compress.smart import SmartFP
+
+    args = SmartFP.add_argparse_args(ArgumentParser()).parse_args([])
+    args.precision = 32
+    for k in ("compress_forward", "compress_backward", "compress_weights", "compress_gradients",
+              "compress_momentum_vectors"):
+        setattr(args, k, True)
+    for k, v in kw.items():
+        setattr(args, k, v)
+    return args
+
+
+class Recorder:
+    """Wraps a plugin and records (tag, numel, kwargs) of each call."""
+
+    def __init__(self, inner):
+        self.inner, self.calls = inner, []
+
+    def __call__(self, t, tag=None, **kw):
+        self.calls.append((tag, t.numel(), {k: v for k, v in kw.items() if k == "all_positive"}))
+        return self.inner(t, tag=tag, **kw)
+
+
+def small_net():
+    return nn.Sequential(nn.Conv2d(3, 8, 3, padding=1), nn.BatchNorm2d(8), nn.ReLU(), nn.AdaptiveAvgPool2d(1),
+                         nn.Flatten(), nn.Linear(8, 10)).to(DEV)
+
+
+@pytest.mark.parametrize("optim_name", ["sgd", "adamw"])
+def test_training_step_through_hooks(optim_name):
+    from smart_compress.compress.smart import SmartFP
+    from smart_compress.util.pytorch.autograd import register_autograd_module
+    from smart_compress.util.pytorch.hooks import wrap_optimizer
+
+    torch.manual_seed(0)
+    hp = hparams()
+    codec = Recorder(SmartFP(hp))
+    model = register_autograd_module(small_net(), codec, hp)
+    bn = [p for m in model.modules() if type(m) == nn.BatchNorm2d for p in m.parameters(recurse=False)]
+    rest = [p for m in model.modules() if type(m) != nn.BatchNorm2d for p in m.parameters(recurse=False)]
+    groups = [dict(params=bn, no_weight_compression=True), dict(params=rest)]
+    inner = (torch.optim.SGD(groups, lr=0.1, momentum=0.9) if optim_name == "sgd"
+             else torch.optim.AdamW(groups, lr=1e-3))
+    opt = wrap_optimizer(inner, codec, hp)
+    x = torch.randn(16, 3, 8, 8, device=DEV)
+    target = torch.randint(0, 10, (16,), device=DEV)
+    losses = []
+    for _ in range(3):
+        def closure():
+            opt.zero_grad()
+            loss = nn.functional.cross_entropy(model(x), target)
+            loss.backward()
+            return loss
+
+        losses.append(float(opt.step(closure)))
+    assert all(torch.isfinite(torch.tensor(losses)))
+    tags = Counter(t for t, _, _ in codec.calls)
+    n_params = len(bn) + len(rest)
+    # wrapped: Sequential itself, Conv2d, BatchNorm2d, ReLU, AdaptiveAvgPool2d, Linear (Flatten is not
+    # in the predicate, quantization.py:166-184); every wrapped output needs a gradient
+    assert tags["forward_autograd"] == 3 * 6
+    assert tags["backward_autograd"] == 3 * 6
+    assert tags["optimizer_grad"] == 3 * 2 * n_params           # before and after the update
+    assert tags["optimizer_weight"] == 3 * len(rest)            # BN group opts out
+    per_param_state = 1 if optim_name == "sgd" else 2
+    assert tags["optimizer_momentum"] == 3 * per_param_state * n_params
+    if optim_name == "adamw":
+        assert sum(1 for t, _, kw in codec.calls if kw.get("all_positive")) == 3 * n_params
+        for p in bn + rest:
+            assert bool((inner.state[p]["exp_avg_sq"] >= 0).all())
+
+
+def test_backward_runs_on_autograd_thread_and_matches_forward_stream():
+    """Gradient maps are compressed on autograd's worker thread; results must be finite and the
+    hook must not touch leaves that need no grad."""
+    from smart_compress.compress.smart import SmartFP
+    from smart_compress.util.pytorch.autograd import Compressor
+
+    hp = hparams(stochastic_rounding=False)
+    comp = Compressor(SmartFP(hp))
+    x = torch.randn(64, 64, device=DEV, requires_grad=True)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        y = comp(x * 2.0)
+        y.sum().backward()
+    s.synchronize()
+    assert x.grad is not None and bool(torch.isfinite(x.grad).all())
+    leaf = torch.randn(64, device=DEV)  # no grad needed: backward returns (None, None)
+    out = comp(leaf)
+    assert not out.requires_grad

@@ -1,0 +1,317 @@
+"""GPU parity tests for the SmaQ round trip and its statistics, through the C ABI and the plugin.
+
+Contract (BASELINE.json north_star):
+  * given the reference's mean/std and the same uniform numbers, the decoded fp32 values are
+    BIT-EXACT against the oracle / the reference-generated golden vectors (target; the stated
+    tolerance is 1 ulp);
+  * mean/std within 1e-6 relative (of the std scale for a near-zero mean).
+"""
+import math
+
+import pytest
+import torch
+
+from oracle.smaq import SmaqConfig, full_mean_std, sample_mean_std, smaq_roundtrip, std_of
+from tests import cabi
+from tests.golden_util import assert_bit_equal, load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+CASES = load_golden()
+
+
+def make_outlier_tensor(n, seed=1234):
+    """BASELINE.md §4 input recipe (generated on CPU so the oracle sees identical bits)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, generator=g)
+    idx = torch.randperm(n, generator=g)[: max(1, n // 100)]
+    x[idx] *= 10
+    return x, g
+
+
+# ---- round trip, explicit statistics and probs: bit-exact ------------------------------------------
+@pytest.mark.parametrize("name", sorted(n for n, c in CASES.items() if not c["same_object"]))
+def test_roundtrip_matches_reference_golden(name):
+    c = CASES[name]
+    cfg = c["cfg"]
+    x = c["x"]
+    ref = smaq_roundtrip(x.clone(), cfg, probs=c["probs"], idx=c["idx"], **c["kwargs"])
+    assert_bit_equal(ref.y, c["y"], "oracle drifted from golden")
+    ms = cabi.mean_std_tensor(ref.mean, ref.std, DEV)
+    params = cabi.codec_params(cfg, all_positive=c["kwargs"].get("all_positive", False))
+    xd = x.to(DEV).contiguous().view(-1)
+    pd = None if c["probs"] is None else c["probs"].to(DEV).contiguous().view(-1)
+    y = cabi.roundtrip(xd, ms, params, probs=pd)
+    assert_bit_equal(y.cpu().view(x.shape), c["y"], name)
+
+
+@pytest.mark.parametrize("n", [8, 9, 1000, (1 << 20) + 3, 1 << 24])
+@pytest.mark.parametrize("stochastic", [True, False])
+def test_roundtrip_random_sizes_bit_exact(n, stochastic):
+    x, g = make_outlier_tensor(n, seed=n)
+    probs = torch.rand(n, generator=g)
+    cfg = SmaqConfig(stochastic_rounding=stochastic)
+    ref = smaq_roundtrip(x, cfg, probs=probs)
+    ms = cabi.mean_std_tensor(ref.mean, ref.std, DEV)
+    y = cabi.roundtrip(x.to(DEV), ms, cabi.codec_params(cfg), probs=probs.to(DEV))
+    assert_bit_equal(y.cpu(), ref.y, f"n={n}")
+
+
+def test_roundtrip_saturate_matches_oracle():
+    x, g = make_outlier_tensor(1 << 18, seed=5)
+    probs = torch.rand(x.numel(), generator=g)
+    cfg = SmaqConfig()
+    ref = smaq_roundtrip(x, cfg, probs=probs, saturate=True)
+    assert ref.code.abs().max() <= 63
+    ms = cabi.mean_std_tensor(ref.mean, ref.std, DEV)
+    y = cabi.roundtrip(x.to(DEV), ms, cabi.codec_params(cfg, saturate=True), probs=probs.to(DEV))
+    assert_bit_equal(y.cpu(), ref.y, "saturate")
+
+
+@pytest.mark.parametrize("kind", ["zero_mean_neg", "huge_std", "tiny_std", "inf_input", "zeros"])
+def test_roundtrip_degenerate_statistics(kind):
+    """Tensors for which the three-instruction division is not valid take the IEEE-divide branch."""
+    g = torch.Generator().manual_seed(3)
+    n = 5000
+    x = torch.randn(n, generator=g)
+    probs = torch.rand(n, generator=g)
+    cfg = SmaqConfig()
+    mean, std = None, None
+    if kind == "zero_mean_neg":
+        mean, std = torch.tensor(-0.0), torch.tensor(1.0)
+        cfg = SmaqConfig(stochastic_rounding=False)
+    elif kind == "huge_std":
+        x = x * 1e30
+    elif kind == "tiny_std":
+        x = x * 1e-32
+    elif kind == "inf_input":
+        x[17] = float("inf")
+        mean, std = torch.tensor(0.1), torch.tensor(1.3)
+    elif kind == "zeros":
+        x = torch.zeros(n)
+    ref = smaq_roundtrip(x, cfg, probs=probs, mean=mean, std=std)
+    ms = cabi.mean_std_tensor(ref.mean, ref.std, DEV)
+    y = cabi.roundtrip(x.to(DEV), ms, cabi.codec_params(cfg), probs=probs.to(DEV))
+    assert_bit_equal(y.cpu(), ref.y, kind)
+
+
+def test_roundtrip_in_place_and_unaligned():
+    x, g = make_outlier_tensor(100003, seed=9)
+    probs = torch.rand(x.numel(), generator=g)
+    cfg = SmaqConfig()
+    ref = smaq_roundtrip(x, cfg, probs=probs)
+    ms = cabi.mean_std_tensor(ref.mean, ref.std, DEV)
+    params = cabi.codec_params(cfg)
+    # in place
+    xd = x.to(DEV)
+    y = cabi.roundtrip(xd, ms, params, probs=probs.to(DEV), out=xd)
+    assert y.data_ptr() == xd.data_ptr()
+    assert_bit_equal(xd.cpu(), ref.y, "in place")
+    # 4-byte-aligned (not 16) views of x, probs and y
+    buf_x = torch.empty(x.numel() + 1, device=DEV)
+    buf_p = torch.empty(x.numel() + 3, device=DEV)
+    buf_y = torch.empty(x.numel() + 2, device=DEV)
+    vx, vp, vy = buf_x[1:], buf_p[3:], buf_y[2:]
+    vx.copy_(x)
+    vp.copy_(probs)
+    cabi.roundtrip(vx, ms, params, probs=vp, out=vy)
+    assert_bit_equal(vy.cpu(), ref.y, "unaligned")
+
+
+# ---- statistics --------------------------------------------------------------------------------
+def rel(a, b, scale=None):
+    scale = abs(b) if scale is None else scale
+    return abs(a - b) / scale
+
+
+@pytest.mark.parametrize("n", [8, 1000, 4099, (1 << 20) + 3, 1 << 24, (1 << 26) + 5])
+@pytest.mark.parametrize("kind", ["outliers", "shifted"])
+def test_full_statistics_within_1e6(n, kind):
+    x, _ = make_outlier_tensor(n, seed=n + 1)
+    if kind == "shifted":
+        x = x * 0.02 + 3.0
+    xd = x.to(DEV)
+    got = cabi.stats_full(xd).cpu()
+    xd64 = x.double()
+    true_mean, true_std = xd64.mean().item(), xd64.std().item()
+    ref_mean, ref_std = full_mean_std(x, SmaqConfig())
+    # vs fp64 ground truth, and vs what the reference's fp32 torch ops return
+    assert rel(got[0].item(), true_mean, max(abs(true_mean), true_std)) < 1e-6
+    assert rel(got[1].item(), true_std) < 1e-6
+    assert rel(got[0].item(), ref_mean.item(), max(abs(ref_mean.item()), ref_std.item())) < 1e-6
+    assert rel(got[1].item(), ref_std.item()) < 1e-6
+    # run-to-run reproducible (fixed combination order)
+    again = cabi.stats_full(xd).cpu()
+    assert torch.equal(got.view(torch.int32), again.view(torch.int32))
+
+
+def test_statistics_edge_cases():
+    xd = torch.full((1000,), 0.75, device=DEV)
+    got = cabi.stats_full(xd).cpu()
+    assert got[0].item() == 0.75 and got[1].item() == 0.0
+    x = torch.randn(100)
+    x[50] = float("nan")
+    got = cabi.stats_full(x.to(DEV)).cpu()
+    assert math.isnan(got[0].item()) and math.isnan(got[1].item())
+    # unaligned view
+    buf = torch.randn(1001, device=DEV)
+    got = cabi.stats_full(buf[1:]).cpu()
+    ref = buf[1:].double()
+    assert rel(got[1].item(), ref.std().item()) < 1e-6
+    # biased variant
+    got = cabi.stats_full(buf[1:], unbiased=False).cpu()
+    assert rel(got[1].item(), ref.std(unbiased=False).item()) < 1e-6
+
+
+def test_sampled_statistics_explicit_indices():
+    x, g = make_outlier_tensor(1 << 20, seed=77)
+    for k in (16, 64, 1024):
+        idx = torch.randperm(x.numel(), generator=g)[:k]
+        cfg = SmaqConfig(use_sample_stats=True, num_samples=k)
+        ref_mean, ref_std = sample_mean_std(x, idx, cfg)
+        got = cabi.stats_sampled(x.to(DEV), idx).cpu()
+        assert rel(got[0].item(), ref_mean.item(), max(abs(ref_mean.item()), ref_std.item())) < 1e-6
+        assert rel(got[1].item(), ref_std.item()) < 1e-6
+
+
+def test_sampled_statistics_device_draw():
+    """Device-drawn indices: a uniform k-subset (the law of randperm(n)[:k]); deterministic per seed."""
+    n, k = 1 << 16, 16
+    x = torch.arange(n, dtype=torch.float32)  # value == index: statistics reveal the draw
+    xd = x.to(DEV)
+    a = cabi.stats_sampled_draw(xd, k, seed=1).cpu()
+    b = cabi.stats_sampled_draw(xd, k, seed=1).cpu()
+    c = cabi.stats_sampled_draw(xd, k, seed=2).cpu()
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    means = torch.stack([cabi.stats_sampled_draw(xd, k, seed=s, offset=3) for s in range(400)]).cpu()[:, 0]
+    # E[mean] = (n-1)/2, sd of the mean of 16 uniform draws = n/sqrt(12*16); 400 repetitions
+    assert abs(means.mean().item() - (n - 1) / 2) < 4 * n / math.sqrt(12 * 16 * 400)
+    # k == n must select every index exactly once
+    small = torch.arange(16, dtype=torch.float32, device=DEV)
+    got = cabi.stats_sampled_draw(small, 16, seed=5).cpu()
+    assert abs(got[0].item() - 7.5) < 1e-6 and rel(got[1].item(), small.double().std(unbiased=False).item()) < 1e-6
+
+
+def test_range_statistics():
+    x, _ = make_outlier_tensor(300001, seed=4)
+    cfg = SmaqConfig(use_range_std_dev=True)
+    ref_std = std_of(x, cfg)
+    got = cabi.stats_range(x.to(DEV)).cpu()
+    assert rel(got[0].item(), x.double().mean().item(), 1.0) < 1e-6
+    assert rel(got[1].item(), ref_std.item()) < 1e-6
+
+
+# ---- small-tensor fused kernel --------------------------------------------------------------------
+@pytest.mark.parametrize("n", [8, 10, 512, 4099, 32768])
+def test_small_fused_matches_oracle_given_its_own_stats(n):
+    x, g = make_outlier_tensor(n, seed=n + 3)
+    probs = torch.rand(n, generator=g)
+    cfg = SmaqConfig()
+    y, ms = cabi.roundtrip_small(x.to(DEV), cabi.codec_params(cfg), probs=probs.to(DEV), want_stats=True)
+    ms = ms.cpu()
+    ref_mean, ref_std = full_mean_std(x, cfg)
+    assert rel(ms[0].item(), ref_mean.item(), max(abs(ref_mean.item()), ref_std.item())) < 1e-6
+    assert rel(ms[1].item(), ref_std.item()) < 1e-6
+    ref = smaq_roundtrip(x, cfg, probs=probs, mean=ms[0], std=ms[1])
+    assert_bit_equal(y.cpu(), ref.y, f"small n={n}")
+
+
+# ---- plugin end to end ---------------------------------------------------------------------------
+def make_plugin(argv=(), precision=32):
+    from argparse import ArgumentParser
+
+    from smart_compress.compress.smart import SmartFP
+
+    args = SmartFP.add_argparse_args(ArgumentParser()).parse_args(list(argv))
+    args.precision = precision
+    return SmartFP(args)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_plugin_golden_cases(name):
+    """Through SmartFP.__call__: the kernel's own statistics, the golden's probs / indices.
+    Bit-exact against the oracle fed the kernel's statistics; the statistics within 1e-6."""
+    c = CASES[name]
+    fp = make_plugin(c["argv"].split(), c["precision"])
+    xd = c["x"].to(DEV)
+    y = fp(xd, tag="t", _probs=c["probs"], _sample_idx=c["idx"], **c["kwargs"])
+    if c["same_object"]:
+        assert y is xd
+        return
+    assert y is not xd and y.shape == xd.shape and y.dtype == xd.dtype and y.device == xd.device
+    cfg = c["cfg"]
+    flat = xd.contiguous().view(-1)
+    ms = (fp.statistics(flat, c["idx"]) if (cfg.use_sample_stats or cfg.use_range_std_dev or
+                                              flat.numel() > 32768) else None)
+    if ms is None:
+        _, ms = cabi.roundtrip_small(flat, cabi.codec_params(cfg), probs=None if c["probs"] is None
+                                     else c["probs"].to(DEV).view(-1), want_stats=True)
+    ms = ms.cpu()
+    ref = smaq_roundtrip(c["x"].clone(), cfg, probs=c["probs"], idx=c["idx"], mean=ms[0], std=ms[1], **c["kwargs"])
+    assert_bit_equal(y.cpu(), ref.y, name)
+    if not torch.isnan(c["y"]).any():
+        # and close to the reference's own output (statistics may differ in the last bits)
+        ref_stats = smaq_roundtrip(c["x"].clone(), cfg, probs=c["probs"], idx=c["idx"], **c["kwargs"])
+        scale = max(abs(ref_stats.mean.item()), ref_stats.std.item(), 1e-30)
+        assert rel(ms[0].item(), ref_stats.mean.item(), scale) < 1e-6
+        if ref_stats.std.item() != 0:
+            assert rel(ms[1].item(), ref_stats.std.item()) < 1e-6
+
+
+def test_plugin_philox_path_properties():
+    """Performance path (in-kernel Philox): seeded, unbiased, codes on the reference's grid."""
+    fp = make_plugin()
+    x, _ = make_outlier_tensor(1 << 22, seed=11)
+    xd = x.to(DEV)
+    torch.manual_seed(123)
+    fp1 = make_plugin()
+    y1 = fp1(xd)
+    torch.manual_seed(123)
+    fp2 = make_plugin()
+    y2 = fp2(xd)
+    assert torch.equal(y1, y2)          # same seed, same call index -> same stream
+    y3 = fp2(xd)
+    assert not torch.equal(y1, y3)      # next call -> next stream
+    # every output must be one of the two values the oracle can produce (probs = 0+ and probs -> 1)
+    ms = fp.statistics(xd).cpu()
+    cfg = SmaqConfig()
+    lo = smaq_roundtrip(x, cfg, probs=torch.full_like(x, 1.0 - 2 ** -24), mean=ms[0], std=ms[1]).y
+    hi = smaq_roundtrip(x, cfg, probs=torch.zeros_like(x), mean=ms[0], std=ms[1]).y
+    y = y1.cpu()
+    assert bool(((y == lo) | (y == hi)).all())
+    # stochastic rounding is unbiased: mean error is ~N(0, step^2/ (6 n))
+    err = (y.double() - x.double()).mean().item()
+    assert abs(err) < 5 * ms[1].item() / 15 / math.sqrt(x.numel())
+
+
+def test_plugin_noncontiguous_and_shapes():
+    fp = make_plugin(["--no_stochastic_rounding"])
+    x = torch.randn(6, 5, 7, 3, device=DEV)
+    xt = x.permute(0, 3, 1, 2)  # non-contiguous view, as cuDNN channels-last outputs can be
+    y = fp(xt)
+    assert y.shape == xt.shape
+    ref = fp(xt.contiguous())
+    assert torch.equal(y, ref)
+
+
+def test_plugin_refuses_cpu_tensors():
+    from smart_compress._native import NativeLibraryError
+
+    fp = make_plugin()
+    with pytest.raises(NativeLibraryError):
+        fp(torch.randn(100))
+
+
+def test_compression_ratio_logging():
+    fp = make_plugin(["--measure_compression_ratio", "--no_stochastic_rounding"])
+    seen = {}
+    fp.log = lambda k, v, **kw: seen.__setitem__(k, v)
+    x, _ = make_outlier_tensor(1 << 16, seed=21)
+    fp(x.to(DEV), tag="forward_autograd")
+    cfg = SmaqConfig(stochastic_rounding=False)
+    ref = smaq_roundtrip(x, cfg)
+    n_out = int((ref.hi | ref.lo).sum())
+    want = n_out * 8 + (x.numel() - n_out) * 6
+    assert abs(seen["new_size_forward_autograd"] - want) <= 8 * 4  # stats differ in the last bit at most
+    assert seen["orig_size"] == x.numel() * 32
+    assert 4.0 < seen["compression_ratio"] < 5.4
