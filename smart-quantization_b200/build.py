@@ -24,9 +24,10 @@ SOURCES = ["capi.cu", "smaq_stats.cu", "smaq_roundtrip.cu", "smaq_pack.cu", "flo
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    # parity: every fp32 step of the reference is a separate rounding -> no FMA contraction,
-    # IEEE division and square root, denormals kept.
-    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    # parity: IEEE division and square root, denormals kept.  -fmad stays at its default (true):
+    # parity-critical steps use the never-contracted _rn intrinsics (csrc/smaq_math.cuh), and
+    # libdevice's powf/log2f must be compiled the way torch compiles them (S2FP8 bit-exactness).
+    "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC",
 ]
 
