@@ -27,8 +27,8 @@ lane packs its own 32 values in registers):
                 LSB-first, padded to a whole uint32; table[t] = first word of CTA tile t in the
                 extras section, table[n_cta_tiles] = total words.
 Elements past n (padding of the last tile) are main elements with payload 0.
-Non-finite codes (NaN input statistics, infinite inputs) are stored as code 0 and counted in
-n_saturated together with the clamped ones.
+Infinite codes saturate like any other over-range code; NaN codes (NaN statistics or inputs) are
+stored as code 0; both are counted in n_saturated together with the clamped ones.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this.
 """
@@ -86,7 +86,7 @@ def codes_from_result(res: SmaqResult, cfg: SmaqConfig):
     lo = res.lo.reshape(-1).numpy()
     outlier = hi | lo
     lim = np.where(outlier, cfg.max_code_outlier, cfg.max_code_main).astype(np.float32)
-    finite = np.isfinite(code)
+    finite = ~np.isnan(code)  # +-inf saturates to +-lim, NaN becomes 0
     clipped = finite & (np.abs(code) > lim)
     sat = np.clip(np.where(finite, code, 0.0), -lim, lim)
     mag = np.abs(sat).astype(np.uint32)

@@ -1,0 +1,45 @@
+// Per-call parameters as the kernels see them (by value in the launch), shared by the round-trip
+// and the packed encode/decode kernels.
+#pragma once
+#include "common.cuh"
+#include "smaq_math.cuh"
+
+namespace smaq {
+
+struct KernelParams {
+  float thr, range_main, range_out, clamp_lo, clamp_hi;
+  int bits_main, bits_outlier;
+  int all_positive, saturate;
+  uint64_t seed, offset;
+};
+
+inline KernelParams to_kernel_params(const smaq_codec_params& p) {
+  KernelParams k;
+  k.thr = p.threshold;
+  k.range_main = p.range_main;
+  k.range_out = p.range_outlier;
+  k.clamp_lo = p.clamp_lo;
+  k.clamp_hi = p.clamp_hi;
+  k.bits_main = p.bits_main;
+  k.bits_outlier = p.bits_outlier;
+  k.all_positive = p.all_positive;
+  k.saturate = p.saturate;
+  k.seed = p.seed;
+  k.offset = p.offset;
+  return k;
+}
+
+__device__ __forceinline__ Scalars scalars_from(float mean, float std_raw, const KernelParams& kp) {
+  return make_scalars(mean, std_raw, kp.thr, kp.range_main, kp.range_out, kp.clamp_lo, kp.clamp_hi, kp.bits_main,
+                      kp.bits_outlier);
+}
+
+inline int check_params(const smaq_codec_params* p) {
+  if (!p) return fail(SMAQ_ERR_ARG, "params is NULL");
+  if (!(p->threshold > 0.0f)) return fail(SMAQ_ERR_ARG, "threshold must be > 0");
+  if (p->bits_main < 3 || p->bits_main > 16 || p->bits_outlier < p->bits_main || p->bits_outlier > 17)
+    return fail(SMAQ_ERR_ARG, "unsupported bit widths main=%d outlier=%d", p->bits_main, p->bits_outlier);
+  return SMAQ_OK;
+}
+
+}  // namespace smaq

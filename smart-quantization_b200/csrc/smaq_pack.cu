@@ -1,14 +1,522 @@
-// placeholder until the packed encode/decode kernels land (next commit)
-#include "common.cuh"
+// Kernels (2) and (3): the SmaQ quantizer that MATERIALISES its codes as a dense bit stream,
+// and the matching dequantizer.
+//
+// The reference only ever holds the code as an fp32 value (smart_compress/compress/smart.py:164-169)
+// and accounts for 6 bits per main element and 8 per outlier (smart.py:184-187).  The stream
+// written here has exactly that size (plus a 4-byte entry per 8192 elements and word alignment);
+// its layout ("SQB1") is specified in DESIGN.md and restated executable in oracle/pack.py.
+//
+// Mapping to the hardware
+//   * one warp owns 1024 consecutive elements and reads them with eight coalesced 128-bit loads
+//     (lane l takes elements 128k + 4l + j): no shared-memory staging is needed for the input;
+//   * every lane packs its own 32 codes in registers: one tag word, PM words of base fields —
+//     the fixed-position part of the stream (PM+1 bits per element), stored with coalesced
+//     32-bit row writes; no __ballot_sync transposition (6 votes per element were measured in
+//     SASS to cost more issue slots than the whole quantiser);
+//   * the variable part — XB extra bits per OUTLIER — is compacted per lane in registers, placed
+//     inside the CTA tile by a shuffle/shared-memory prefix scan of the per-lane outlier counts
+//     (popc of the tag word), and placed in the tensor by a single-pass decoupled look-back over
+//     CTA tiles (tiles are numbered by an atomic ticket, so a tile only ever waits for tiles
+//     that are already running); the result is deterministic: byte-identical run to run;
+//   * the decoder needs no scan across tiles: the per-tile word offset is in the table.
+//
+// HBM roofline (6/8 bits, fraction f of outliers): encode reads 4 B and writes (6 + 2f)/8 B per
+// element; decode the reverse.  f = 0.165 on the benchmark input -> 4.79 B per element each way.
+#include "params.cuh"
+
+namespace smaq {
+
+constexpr int kWarpTile = 1024;
+constexpr int kWarpsPerCta = 8;
+constexpr int kCtaTile = kWarpTile * kWarpsPerCta;
+constexpr int kPackThreads = 32 * kWarpsPerCta;
+constexpr int kCountSlots = 64;
+constexpr uint32_t kMagic = 0x31425153u;  // 'SQB1'
+
+struct EncodeWs {
+  unsigned int ticket;
+  unsigned int status;
+  unsigned int pad[2];
+  unsigned long long n_out[kCountSlots];
+  unsigned long long n_sat[kCountSlots];
+  unsigned long long state[1];  // [n_cta_tiles]: flag (2 bits) | exclusive/inclusive word count
+};
+
+constexpr unsigned long long kFlagA = 1ull << 62;  // tile aggregate available
+constexpr unsigned long long kFlagP = 2ull << 62;  // inclusive prefix available
+constexpr unsigned long long kValMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// groups of lane-local elements that share one 32-bit extras accumulator: XB * (32 / G) <= 32
+__host__ __device__ constexpr int ext_groups(int xb) { return xb <= 1 ? 1 : xb <= 2 ? 2 : xb <= 4 ? 4 : 8; }
+
+// Exclusive prefix over the CTA of a per-thread bit count; returns the thread's offset and the total.
+__device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t& total) {
+  uint32_t inc = warp_inclusive_scan(v);
+  if (lane_id() == 31) s_warp[warp_id()] = inc;
+  __syncthreads();
+  uint32_t before = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < kWarpsPerCta; ++w) {
+    uint32_t t = s_warp[w];
+    before += (w < warp_id()) ? t : 0u;
+    all += t;
+  }
+  total = all;
+  return before + inc - v;
+}
+
+// Decoupled look-back (Merrill & Garland) over CTA tiles, run by warp 0.  Returns the number of
+// extras words that precede this tile.  Tiles are numbered by ticket, so every predecessor is
+// resident or finished; the watchdog only exists so that a logic error cannot hang the GPU.
+__device__ __forceinline__ unsigned long long lookback_exclusive(EncodeWs* ws, long long tile,
+                                                                  unsigned long long aggregate) {
+  const int lane = lane_id();
+  if (tile == 0) {
+    if (lane == 0) st_state(&ws->state[0], kFlagP | aggregate);
+    return 0;
+  }
+  if (lane == 0) st_state(&ws->state[tile], kFlagA | aggregate);
+  unsigned long long excl = 0;
+  long long window_end = tile - 1;
+  unsigned int spins = 0;
+  bool timed_out = false;
+  while (true) {
+    const long long idx = window_end - lane;
+    unsigned long long sv = (idx >= 0) ? ld_state(&ws->state[idx]) : kFlagP;  // virtual tiles before 0: P(0)
+    while (__any_sync(0xffffffffu, (sv >> 62) == 0)) {
+      if ((sv >> 62) == 0) sv = ld_state(&ws->state[idx]);
+      if (++spins > (1u << 22)) {  // watchdog (~1 s): record the failure, unblock the successors
+        timed_out = true;
+        break;
+      }
+      __nanosleep(40);
+    }
+    if (timed_out) {
+      if (lane == 0) atomicExch(&ws->status, 1u);
+      excl = 0;
+      break;
+    }
+    const unsigned int has_p = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+    unsigned long long val = sv & kValMask;
+    if (has_p) {
+      const int first = __ffs(has_p) - 1;  // nearest predecessor holding an inclusive prefix
+      val = (lane <= first) ? val : 0ull;
+      excl += warp_sum(val);
+      break;
+    }
+    excl += warp_sum(val);
+    window_end -= 32;
+  }
+  if (lane == 0) st_state(&ws->state[tile], kFlagP | (excl + aggregate));
+  return excl;
+}
+
+template <int PM>
+__device__ __forceinline__ void put_field(uint32_t (&bw)[PM], int i, uint32_t field) {
+  const int pos = PM * i, w = pos >> 5, sh = pos & 31;  // compile-time after unrolling
+  bw[w] |= field << sh;
+  if (sh + PM > 32) bw[w + 1] |= field >> (32 - sh);
+}
+template <int PM>
+__device__ __forceinline__ uint32_t get_field(const uint32_t (&bw)[PM], int i) {
+  const int pos = PM * i, w = pos >> 5, sh = pos & 31;
+  uint32_t v = bw[w] >> sh;
+  if (sh + PM > 32) v |= bw[w + 1] << (32 - sh);
+  return v & ((1u << PM) - 1u);
+}
+
+template <int PM, int XB, bool kStochastic, bool kHasProbs, bool kFast>
+__device__ __forceinline__ void encode_tile(const float* __restrict__ x, int64_t n, const float* __restrict__ probs,
+                                            const KernelParams& kp, const Scalars& s, bool aligned, long long tile,
+                                            uint32_t* __restrict__ planes, uint32_t& tagw_out, uint32_t (&ea)[8],
+                                            uint32_t (&ecnt)[8], uint32_t& n_sat_out) {
+  constexpr int G = ext_groups(XB);
+  constexpr int EPG = 32 / G;
+  const int lane = lane_id();
+  const int64_t wt = (int64_t)tile * kWarpsPerCta + warp_id();
+  const int64_t base = wt * kWarpTile;
+  const Philox rng(kp.seed);
+
+  uint32_t tagw = 0, n_sat = 0;
+  uint32_t bw[PM];
+#pragma unroll
+  for (int w = 0; w < PM; ++w) bw[w] = 0;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) { ea[g] = 0; ecnt[g] = 0; }
+
+  if (base < n) {
+    const bool full = aligned && (base + kWarpTile <= n);
+    float v[32], pr[32];
+    if (full) {
+      const float4* xv = reinterpret_cast<const float4*>(x + base) + lane;
+      const float4* pv = reinterpret_cast<const float4*>(probs + base) + lane;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float4 t = ldg_stream(xv + 32 * k);
+        v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+      }
+      if (kStochastic && kHasProbs) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float4 t = ldg_stream(pv + 32 * k);
+          pr[4 * k] = t.x; pr[4 * k + 1] = t.y; pr[4 * k + 2] = t.z; pr[4 * k + 3] = t.w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int64_t e = base + 128 * (i >> 2) + 4 * lane + (i & 3);
+        v[i] = (e < n) ? x[e] : 0.0f;
+        if (kStochastic && kHasProbs) pr[i] = (e < n) ? probs[e] : 0.0f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      uint4 r = make_uint4(0, 0, 0, 0);
+      if (kStochastic && !kHasProbs) r = rng.for_group((uint64_t)((base >> 2) + 32 * k + lane), kp.offset);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = 4 * k + j;
+        float p = 0.0f;
+        if (kStochastic) p = kHasProbs ? pr[i] : uniform24(j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w);
+        Classified c;
+        const float code = encode_value<kStochastic, kFast>(v[i], s, p, c);
+        bool outl = c.hi || c.lo;
+        float sat = saturate_code(code, s, outl);
+        bool bad = !(sat == code);  // clipped at the field width, or not a number
+        sat = (sat != sat) ? 0.0f : sat;
+        bool valid = true;
+        if (!full) {
+          valid = (base + 128 * k + 4 * lane + j) < n;
+          outl = outl && valid;
+          bad = bad && valid;
+        }
+        const uint32_t mag = (uint32_t)abs(__float2int_rz(sat));
+        const uint32_t sbit = outl ? (c.lo ? 1u : 0u) : (__float_as_uint(sat) >> 31);
+        uint32_t payload = (mag << 1) | sbit;
+        if (!full) payload = valid ? payload : 0u;
+        n_sat += bad ? 1u : 0u;
+        tagw |= (outl ? 1u : 0u) << i;
+        put_field<PM>(bw, i, payload & ((1u << PM) - 1u));
+        if (XB > 0) {
+          const int g = i / EPG;
+          ea[g] |= (payload >> PM) << ecnt[g];  // payload >> PM is 0 for a main element
+          ecnt[g] += outl ? (uint32_t)XB : 0u;
+        }
+      }
+    }
+    // fixed-position part of the stream: (1 + PM) rows of 32 words per warp tile, coalesced
+    uint32_t* rec = planes + wt * (int64_t)((1 + PM) * 32) + lane;
+    rec[0] = tagw;
+#pragma unroll
+    for (int w = 0; w < PM; ++w) rec[32 * (w + 1)] = bw[w];
+  }
+  tagw_out = tagw;
+  n_sat_out = n_sat;
+}
+
+template <int PM, int XB, bool kStochastic, bool kHasProbs>
+__global__ void __launch_bounds__(kPackThreads, 2)
+    encode_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ mean_std,
+                  const float* __restrict__ probs, KernelParams kp, smaq_packed_header* __restrict__ hdr,
+                  uint32_t* __restrict__ table, uint32_t* __restrict__ planes, uint32_t* __restrict__ extras,
+                  EncodeWs* ws, long long n_cta_tiles, int aligned) {
+  constexpr int G = ext_groups(XB);
+  constexpr int kExtWords = kCtaTile * XB / 32 + 2;
+  __shared__ uint32_t s_ext[kExtWords];
+  __shared__ uint32_t s_warp[kWarpsPerCta];
+  __shared__ unsigned long long s_off;
+  __shared__ unsigned int s_tile;
+
+  if (threadIdx.x == 0) s_tile = atomicAdd(&ws->ticket, 1u);
+  for (int i = threadIdx.x; i < kExtWords; i += kPackThreads) s_ext[i] = 0;
+  __syncthreads();
+  const long long tile = s_tile;
+
+  const Scalars s = scalars_from(mean_std[0], mean_std[1], kp);
+  uint32_t tagw, n_sat, ea[8], ecnt[8];
+  if (s.fast)
+    encode_tile<PM, XB, kStochastic, kHasProbs, true>(x, n, probs, kp, s, aligned != 0, tile, planes, tagw, ea, ecnt, n_sat);
+  else
+    encode_tile<PM, XB, kStochastic, kHasProbs, false>(x, n, probs, kp, s, aligned != 0, tile, planes, tagw, ea, ecnt, n_sat);
+
+  // place the lane's extras inside the CTA tile
+  const uint32_t n_out = __popc(tagw);
+  uint32_t total_bits;
+  uint32_t pos = cta_exclusive_scan(n_out * XB, s_warp, total_bits);
+  if (XB > 0) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      if (ecnt[g]) {
+        const uint32_t w = pos >> 5, sh = pos & 31;
+        atomicOr(&s_ext[w], ea[g] << sh);
+        if (sh + ecnt[g] > 32) atomicOr(&s_ext[w + 1], ea[g] >> (32 - sh));
+        pos += ecnt[g];
+      }
+    }
+  }
+  const uint32_t words = (total_bits + 31) >> 5;
+
+  // counts, spread over slots (the last tile sums them): before this tile publishes anything
+  const uint32_t w_out = warp_sum(n_out), w_sat = warp_sum(n_sat);
+  if (lane_id() == 0) {
+    const int slot = (int)((tile * kWarpsPerCta + warp_id()) % kCountSlots);
+    if (w_out) atomicAdd(&ws->n_out[slot], (unsigned long long)w_out);
+    if (w_sat) atomicAdd(&ws->n_sat[slot], (unsigned long long)w_sat);
+    __threadfence();
+  }
+  __syncthreads();
+
+  if (warp_id() == 0) {
+    unsigned long long excl = lookback_exclusive(ws, tile, words);
+    if (lane_id() == 0) s_off = excl;
+  }
+  __syncthreads();
+  const unsigned long long off = s_off;
+  for (uint32_t i = threadIdx.x; i < words; i += kPackThreads) extras[off + i] = s_ext[i];
+
+  if (threadIdx.x == 0) {
+    table[tile] = (uint32_t)off;
+    if (tile == 0) {
+      hdr->magic = kMagic;
+      hdr->bits_main = kp.bits_main;
+      hdr->bits_outlier = kp.bits_outlier;
+      hdr->stochastic = kStochastic ? 1 : 0;
+      hdr->n = n;
+      hdr->mean = mean_std[0];
+      hdr->std_raw = mean_std[1];
+      hdr->threshold = kp.thr;
+      hdr->range_main = kp.range_main;
+      hdr->range_outlier = kp.range_out;
+      hdr->clamp_lo = kp.clamp_lo;
+      hdr->clamp_hi = kp.clamp_hi;
+      hdr->pad0 = 0.0f;
+    }
+    if (tile == n_cta_tiles - 1) {
+      // every other tile added its counts (and fenced) before publishing the state this tile waited on
+      __threadfence();
+      unsigned long long a = 0, b = 0;
+      for (int i = 0; i < kCountSlots; ++i) {
+        a += ld_state(&ws->n_out[i]);
+        b += ld_state(&ws->n_sat[i]);
+      }
+      hdr->n_outlier = a;
+      hdr->n_saturated = b;
+      hdr->extras_words = off + words;
+      hdr->status = atomicAdd(&ws->status, 0u);
+      table[n_cta_tiles] = (uint32_t)(off + words);
+    }
+  }
+}
+
+template <int PM, int XB, bool kFast>
+__device__ __forceinline__ void decode_tile(const uint32_t* __restrict__ s_ext, uint32_t pos, uint32_t tagw,
+                                            const uint32_t (&bw)[PM], const Scalars& s, bool all_positive,
+                                            float* __restrict__ y, int64_t n, int64_t base, bool aligned) {
+  constexpr int G = ext_groups(XB);
+  constexpr int EPG = 32 / G;
+  const int lane = lane_id();
+  uint32_t win[G];
+  if (XB > 0) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const uint32_t gmask = (EPG == 32) ? 0xffffffffu : (((1u << EPG) - 1u) << (g * EPG));
+      const uint32_t cnt = __popc(tagw & gmask) * XB;
+      const uint32_t w = pos >> 5, sh = pos & 31;
+      win[g] = __funnelshift_r(s_ext[w], s_ext[w + 1], sh);
+      pos += cnt;
+    }
+  }
+  const bool full = aligned && (base + kWarpTile <= n);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = 4 * k + j;
+      const bool outl = (tagw >> i) & 1u;
+      uint32_t payload = get_field<PM>(bw, i);
+      if (XB > 0) {
+        const int g = i / EPG;
+        const uint32_t e = win[g] & ((1u << XB) - 1u);
+        if (outl) {
+          payload |= e << PM;
+          win[g] >>= XB;
+        }
+      }
+      const uint32_t sbit = payload & 1u;
+      const float mag = (float)(payload >> 1);
+      const float code = __uint_as_float(__float_as_uint(mag) | (sbit << 31));  // -0.0 when sbit and mag == 0
+      const float shift = outl ? (sbit ? s.shift_lo : s.shift_hi) : s.shift_mid;
+      Divisor range;
+      range.b = outl ? s.range_out.b : s.range_main.b;
+      range.r = outl ? s.range_out.r : s.range_main.r;
+      o[j] = decode_value<kFast>(code, shift, range, s, all_positive);
+    }
+    if (full) {
+      stg_stream(reinterpret_cast<float4*>(y + base) + 32 * k + lane, make_float4(o[0], o[1], o[2], o[3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t e = base + 128 * k + 4 * lane + j;
+        if (e < n) y[e] = o[j];
+      }
+    }
+  }
+}
+
+template <int PM, int XB>
+__global__ void __launch_bounds__(kPackThreads, 2)
+    decode_kernel(const smaq_packed_header* __restrict__ hdr, const uint32_t* __restrict__ table,
+                  const uint32_t* __restrict__ planes, const uint32_t* __restrict__ extras, float* __restrict__ y,
+                  int64_t n, int all_positive, int aligned) {
+  constexpr int kExtWords = kCtaTile * XB / 32 + 2;
+  __shared__ uint32_t s_ext[kExtWords];
+  __shared__ uint32_t s_warp[kWarpsPerCta];
+  const long long tile = blockIdx.x;
+  const int lane = lane_id();
+  const int64_t wt = (int64_t)tile * kWarpsPerCta + warp_id();
+  const int64_t base = wt * kWarpTile;
+
+  const Scalars s = make_scalars(hdr->mean, hdr->std_raw, hdr->threshold, hdr->range_main, hdr->range_outlier,
+                                 hdr->clamp_lo, hdr->clamp_hi, hdr->bits_main, hdr->bits_outlier);
+  uint32_t tagw = 0, bw[PM];
+#pragma unroll
+  for (int w = 0; w < PM; ++w) bw[w] = 0;
+  if (base < n) {
+    const uint32_t* rec = planes + wt * (int64_t)((1 + PM) * 32) + lane;
+    tagw = rec[0];
+#pragma unroll
+    for (int w = 0; w < PM; ++w) bw[w] = rec[32 * (w + 1)];
+  }
+  uint32_t total_bits;
+  const uint32_t pos = cta_exclusive_scan(__popc(tagw) * XB, s_warp, total_bits);
+  const uint32_t words = (total_bits + 31) >> 5;
+  const uint32_t off = table[tile];
+  for (uint32_t i = threadIdx.x; i < words; i += kPackThreads) s_ext[i] = extras[(size_t)off + i];
+  if (threadIdx.x < 2) s_ext[words + threadIdx.x] = 0;
+  __syncthreads();
+  if (base >= n) return;
+  if (s.fast) decode_tile<PM, XB, true>(s_ext, pos, tagw, bw, s, all_positive != 0, y, n, base, aligned != 0);
+  else decode_tile<PM, XB, false>(s_ext, pos, tagw, bw, s, all_positive != 0, y, n, base, aligned != 0);
+}
+
+static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+static bool width_supported(int bits_main, int bits_outlier) {
+  const int pm = bits_main - 1, xb = bits_outlier - bits_main;
+  return pm >= 3 && pm <= 7 && xb >= 0 && xb <= 4;
+}
+
+}  // namespace smaq
+
 extern "C" {
-int smaq_packed_layout_for(int64_t, int32_t, int32_t, smaq_packed_layout*) {
-  return smaq::fail(SMAQ_ERR_UNSUPPORTED, "packed stream: not built yet");
+
+int smaq_packed_layout_for(int64_t n, int32_t bits_main, int32_t bits_outlier, smaq_packed_layout* out) {
+  using namespace smaq;
+  if (!out || n < 0) return fail(SMAQ_ERR_ARG, "packed_layout: bad argument");
+  if (!width_supported(bits_main, bits_outlier))
+    return fail(SMAQ_ERR_UNSUPPORTED,
+                "packed stream supports num_bits_main 4..8 and num_bits_outlier - num_bits_main 0..4 (got %d/%d); "
+                "the fake-quantisation round trip has no such limit",
+                bits_main, bits_outlier);
+  const int pm = bits_main - 1, xb = bits_outlier - bits_main;
+  smaq_packed_layout l;
+  l.n = n;
+  l.bits_main = bits_main;
+  l.bits_outlier = bits_outlier;
+  l.n_warp_tiles = (n + kWarpTile - 1) / kWarpTile;
+  l.n_cta_tiles = (l.n_warp_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
+  l.header_off = 0;
+  l.header_bytes = 128;
+  l.table_off = l.header_off + l.header_bytes;
+  l.table_bytes = align_up((l.n_cta_tiles + 1) * 4, 128);
+  l.planes_off = l.table_off + l.table_bytes;
+  l.planes_bytes = l.n_warp_tiles * (int64_t)(1 + pm) * 128;
+  l.extras_off = l.planes_off + l.planes_bytes;
+  l.extras_capacity_bytes = align_up(l.n_cta_tiles * (int64_t)(kCtaTile * xb / 32) * 4 + 4, 128);
+  l.total_capacity_bytes = l.extras_off + l.extras_capacity_bytes;
+  l.workspace_bytes = align_up((int64_t)sizeof(EncodeWs) + l.n_cta_tiles * 8, 128);
+  *out = l;
+  return SMAQ_OK;
 }
-int smaq_encode(const float*, int64_t, const float*, const float*, const smaq_codec_params*, void*, size_t, void*,
-                size_t, smaq_stream_t) {
-  return smaq::fail(SMAQ_ERR_UNSUPPORTED, "packed stream: not built yet");
+
+int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* probs, const smaq_codec_params* params,
+                void* packed, size_t packed_bytes, void* ws, size_t ws_bytes, smaq_stream_t stream_) {
+  using namespace smaq;
+  static_assert(sizeof(smaq_packed_header) <= 128, "header must fit its slot");
+  if (int rc = check_params(params)) return rc;
+  if (!x || !mean_std || !packed || !ws || n <= 0) return fail(SMAQ_ERR_ARG, "encode: null pointer or n <= 0");
+  smaq_packed_layout l;
+  if (int rc = smaq_packed_layout_for(n, params->bits_main, params->bits_outlier, &l)) return rc;
+  if (packed_bytes < (size_t)l.total_capacity_bytes) return fail(SMAQ_ERR_WORKSPACE, "encode: packed buffer too small");
+  if (ws_bytes < (size_t)l.workspace_bytes) return fail(SMAQ_ERR_WORKSPACE, "encode: workspace too small");
+  if (!aligned16(packed)) return fail(SMAQ_ERR_ARG, "encode: packed buffer must be 16-byte aligned");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SMAQ_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)l.workspace_bytes, stream));
+  char* pb = (char*)packed;
+  auto* hdr = (smaq_packed_header*)(pb + l.header_off);
+  auto* table = (uint32_t*)(pb + l.table_off);
+  auto* planes = (uint32_t*)(pb + l.planes_off);
+  auto* extras = (uint32_t*)(pb + l.extras_off);
+  KernelParams kp = to_kernel_params(*params);
+  const int aligned = aligned16(x) && (!probs || aligned16(probs));
+  const int pm = params->bits_main - 1, xb = params->bits_outlier - params->bits_main;
+  const unsigned grid = (unsigned)l.n_cta_tiles;
+  const bool st = params->stochastic != 0;
+  const bool hp = st && probs != nullptr;
+
+#define SMAQ_ENC(PM_, XB_)                                                                                         \
+  if (pm == PM_ && xb == XB_) {                                                                                    \
+    if (!st) encode_kernel<PM_, XB_, false, false><<<grid, kPackThreads, 0, stream>>>(                             \
+          x, n, mean_std, probs, kp, hdr, table, planes, extras, (EncodeWs*)ws, l.n_cta_tiles, aligned);           \
+    else if (hp) encode_kernel<PM_, XB_, true, true><<<grid, kPackThreads, 0, stream>>>(                           \
+          x, n, mean_std, probs, kp, hdr, table, planes, extras, (EncodeWs*)ws, l.n_cta_tiles, aligned);           \
+    else encode_kernel<PM_, XB_, true, false><<<grid, kPackThreads, 0, stream>>>(                                  \
+          x, n, mean_std, probs, kp, hdr, table, planes, extras, (EncodeWs*)ws, l.n_cta_tiles, aligned);           \
+  }
+#define SMAQ_ENC_ROW(PM_) SMAQ_ENC(PM_, 0) SMAQ_ENC(PM_, 1) SMAQ_ENC(PM_, 2) SMAQ_ENC(PM_, 3) SMAQ_ENC(PM_, 4)
+  SMAQ_ENC_ROW(3) SMAQ_ENC_ROW(4) SMAQ_ENC_ROW(5) SMAQ_ENC_ROW(6) SMAQ_ENC_ROW(7)
+#undef SMAQ_ENC_ROW
+#undef SMAQ_ENC
+  SMAQ_LAUNCH_OK();
+  return SMAQ_OK;
 }
-int smaq_decode(const void*, size_t, int64_t, int32_t, int32_t, int32_t, float*, smaq_stream_t) {
-  return smaq::fail(SMAQ_ERR_UNSUPPORTED, "packed stream: not built yet");
+
+int smaq_decode(const void* packed, size_t packed_bytes, int64_t n, int32_t bits_main, int32_t bits_outlier,
+                int32_t all_positive, float* y, smaq_stream_t stream_) {
+  using namespace smaq;
+  if (!packed || !y || n <= 0) return fail(SMAQ_ERR_ARG, "decode: null pointer or n <= 0");
+  smaq_packed_layout l;
+  if (int rc = smaq_packed_layout_for(n, bits_main, bits_outlier, &l)) return rc;
+  if (packed_bytes < (size_t)l.extras_off) return fail(SMAQ_ERR_WORKSPACE, "decode: packed buffer too small");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const char* pb = (const char*)packed;
+  auto* hdr = (const smaq_packed_header*)(pb + l.header_off);
+  auto* table = (const uint32_t*)(pb + l.table_off);
+  auto* planes = (const uint32_t*)(pb + l.planes_off);
+  auto* extras = (const uint32_t*)(pb + l.extras_off);
+  const int aligned = aligned16(y);
+  const int pm = bits_main - 1, xb = bits_outlier - bits_main;
+  const unsigned grid = (unsigned)l.n_cta_tiles;
+#define SMAQ_DEC(PM_, XB_)                                                                                         \
+  if (pm == PM_ && xb == XB_)                                                                                      \
+    decode_kernel<PM_, XB_><<<grid, kPackThreads, 0, stream>>>(hdr, table, planes, extras, y, n, all_positive, aligned);
+#define SMAQ_DEC_ROW(PM_) SMAQ_DEC(PM_, 0) SMAQ_DEC(PM_, 1) SMAQ_DEC(PM_, 2) SMAQ_DEC(PM_, 3) SMAQ_DEC(PM_, 4)
+  SMAQ_DEC_ROW(3) SMAQ_DEC_ROW(4) SMAQ_DEC_ROW(5) SMAQ_DEC_ROW(6) SMAQ_DEC_ROW(7)
+#undef SMAQ_DEC_ROW
+#undef SMAQ_DEC
+  SMAQ_LAUNCH_OK();
+  return SMAQ_OK;
 }
-}
+
+}  // extern "C"

@@ -9,37 +9,10 @@
 // passed (parity mode only; the performance path draws Philox numbers in-kernel).
 #include "common.cuh"
 #include "moments.cuh"
+#include "params.cuh"
 #include "smaq_math.cuh"
 
 namespace smaq {
-
-struct KernelParams {
-  float thr, range_main, range_out, clamp_lo, clamp_hi;
-  int bits_main, bits_outlier;
-  int all_positive, saturate;
-  uint64_t seed, offset;
-};
-
-static KernelParams to_kernel_params(const smaq_codec_params& p) {
-  KernelParams k;
-  k.thr = p.threshold;
-  k.range_main = p.range_main;
-  k.range_out = p.range_outlier;
-  k.clamp_lo = p.clamp_lo;
-  k.clamp_hi = p.clamp_hi;
-  k.bits_main = p.bits_main;
-  k.bits_outlier = p.bits_outlier;
-  k.all_positive = p.all_positive;
-  k.saturate = p.saturate;
-  k.seed = p.seed;
-  k.offset = p.offset;
-  return k;
-}
-
-__device__ __forceinline__ Scalars scalars_from(float mean, float std_raw, const KernelParams& kp) {
-  return make_scalars(mean, std_raw, kp.thr, kp.range_main, kp.range_out, kp.clamp_lo, kp.clamp_hi, kp.bits_main,
-                      kp.bits_outlier);
-}
 
 template <bool kStochastic, bool kFast>
 __device__ __forceinline__ float roundtrip_one(float x, float p, const Scalars& s, bool saturate, bool all_positive) {
@@ -222,14 +195,6 @@ static int rt_grid(int64_t n) {
   int64_t cap = (int64_t)sms * 8;
   if (want < 1) want = 1;
   return (int)(want < cap ? want : cap);
-}
-
-static int check_params(const smaq_codec_params* p) {
-  if (!p) return fail(SMAQ_ERR_ARG, "params is NULL");
-  if (!(p->threshold > 0.0f)) return fail(SMAQ_ERR_ARG, "threshold must be > 0");
-  if (p->bits_main < 3 || p->bits_main > 16 || p->bits_outlier < p->bits_main || p->bits_outlier > 17)
-    return fail(SMAQ_ERR_ARG, "unsupported bit widths main=%d outlier=%d", p->bits_main, p->bits_outlier);
-  return SMAQ_OK;
 }
 
 }  // namespace smaq

@@ -1,0 +1,54 @@
+"""The materialised SmaQ stream ("SQB1"): what ``SmartFP.encode`` returns and ``SmartFP.decode`` reads.
+
+Not in the reference (which only fake-quantises, smart.py:154-172); named by the build's north
+star.  The buffer lives in device memory; ``header()`` is the only call that synchronises."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from .. import _native as N
+
+
+def packed_layout(n: int, bits_main: int, bits_outlier: int) -> N.PackedLayout:
+    lay = N.PackedLayout()
+    N.check(N.load().smaq_packed_layout_for(n, bits_main, bits_outlier, C.byref(lay)), "smaq_packed_layout_for")
+    return lay
+
+
+@dataclass
+class PackedSmaq:
+    buffer: torch.Tensor          # uint8, device; capacity-sized (see used_bytes)
+    layout: N.PackedLayout
+    shape: torch.Size
+
+    @property
+    def numel(self) -> int:
+        return int(self.layout.n)
+
+    def header(self) -> N.PackedHeader:
+        """Copies the 128-byte header to the host (synchronises the stream)."""
+        raw = bytes(self.buffer[: C.sizeof(N.PackedHeader)].cpu().numpy())
+        return N.PackedHeader.from_buffer_copy(raw)
+
+    def section(self, name: str) -> torch.Tensor:
+        """uint32 view of 'table', 'planes' or 'extras' (device tensor, capacity-sized)."""
+        lay = self.layout
+        off, nbytes = {
+            "table": (lay.table_off, (lay.n_cta_tiles + 1) * 4),
+            "planes": (lay.planes_off, lay.planes_bytes),
+            "extras": (lay.extras_off, lay.extras_capacity_bytes),
+        }[name]
+        return self.buffer[off: off + nbytes].view(torch.int32)
+
+    def used_bytes(self) -> int:
+        """Bytes a consumer must keep: header + table + planes + the extras words actually written."""
+        lay = self.layout
+        return int(lay.extras_off + 4 * self.header().extras_words)
+
+    def payload_bits(self) -> int:
+        """The reference's own size accounting (smart.py:184-187)."""
+        h = self.header()
+        return int(h.bits_outlier * h.n_outlier + h.bits_main * (h.n - h.n_outlier))

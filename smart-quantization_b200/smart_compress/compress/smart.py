@@ -179,6 +179,49 @@ class SmartFP(CompressionAlgorithmBase):
             self.log_size(tag, orig_size, lambda: self._compressed_bits(flat, mean_std, params))
         return out
 
+    # -- materialised stream: encode / decode ---------------------------------------------------
+    @torch.no_grad()
+    def encode(self, data: torch.Tensor, mean_std: Optional[torch.Tensor] = None, **extra):
+        """Quantise and PACK ``data`` (6-bit main / 8-bit outlier codes with the default flags) into a
+        device buffer; statistics as in ``__call__`` unless ``mean_std`` (device float[2]) is given."""
+        from .packed import PackedSmaq, packed_layout
+
+        N.require_cuda_f32(data, "SmartFP.encode")
+        lib = N.load()
+        hp = self.hparams
+        src = data if data.is_contiguous() else data.contiguous()
+        flat = src.view(-1)
+        n = flat.numel()
+        lay = packed_layout(n, hp.num_bits_main, hp.num_bits_outlier)
+        if mean_std is None:
+            mean_std = self.statistics(flat, extra.get("_sample_idx"))
+        buf = torch.empty(lay.total_capacity_bytes, dtype=torch.uint8, device=data.device)
+        ws = torch.empty(lay.workspace_bytes, dtype=torch.uint8, device=data.device)
+        params = self._params(all_positive=False)
+        probs = extra.get("_probs")
+        probs_ptr = None
+        if probs is not None:
+            probs = probs.to(device=data.device, dtype=torch.float32).contiguous()
+            probs_ptr = N.ptr(probs)
+        N.check(
+            lib.smaq_encode(N.ptr(flat), n, N.ptr(mean_std), probs_ptr, C.byref(params), N.ptr(buf), buf.numel(),
+                            N.ptr(ws), ws.numel(), N.stream_ptr(data.device)),
+            "smaq_encode",
+        )
+        return PackedSmaq(buffer=buf, layout=lay, shape=data.shape)
+
+    @torch.no_grad()
+    def decode(self, packed, all_positive: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        lib = N.load()
+        lay = packed.layout
+        y = out if out is not None else torch.empty(packed.shape, dtype=torch.float32, device=packed.buffer.device)
+        N.check(
+            lib.smaq_decode(N.ptr(packed.buffer), packed.buffer.numel(), lay.n, lay.bits_main, lay.bits_outlier,
+                            int(bool(all_positive)), N.ptr(y), N.stream_ptr(y.device)),
+            "smaq_decode",
+        )
+        return y
+
     # -- --use_batch_norm (smart.py:136-149,174-179): off by default, not on the hot path --------
     def _bn_affine_params(self, stats):
         gamma, beta = stats

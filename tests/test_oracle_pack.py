@@ -49,15 +49,17 @@ def test_negative_zero_code_survives_truncation():
                      std=torch.tensor(1.0), saturate=True).y, "-0 mean")
 
 
-def test_non_finite_codes_become_zero_and_are_counted():
+def test_non_finite_codes_are_saturated_or_zeroed_and_counted():
     cfg = SmaqConfig(stochastic_rounding=False)
-    x = torch.randn(64)
-    x[3] = float("inf")
+    x = torch.randn(64).clamp(-2, 2)
+    x[3], x[4], x[5] = float("inf"), float("-inf"), float("nan")
     res = smaq_roundtrip(x, cfg, mean=torch.tensor(0.0), std=torch.tensor(1.0))
     p = opack.pack(res, cfg)
-    assert p.n_saturated >= 1
+    assert p.n_saturated == 3
     tag, s, mag = opack.unpack_codes(p)
-    assert tag[3] and mag[3] == 0
+    assert tag[3] and mag[3] == 63 and s[3] == 0
+    assert tag[4] and mag[4] == 63 and s[4] == 1
+    assert not tag[5] and mag[5] == 0 and s[5] == 0
 
 
 def test_lane_order_is_a_permutation():
