@@ -24,12 +24,27 @@ SOURCES = ["capi.cu", "smaq_stats.cu", "smaq_roundtrip.cu", "smaq_pack.cu", "flo
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    # parity: IEEE division and square root, denormals kept.  -fmad stays at its default (true):
-    # parity-critical steps use the never-contracted _rn intrinsics (csrc/smaq_math.cuh), and
-    # libdevice's powf/log2f must be compiled the way torch compiles them (S2FP8 bit-exactness).
+    # parity: IEEE division and square root, denormals kept
     "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC",
 ]
+
+
+# Per-file FMA contraction.  The SmaQ element arithmetic must round after every operation, and
+# ptxas was observed to fuse mul.rn.f32x2 + add.rn.f32x2 into FFMA2 under the default -fmad=true,
+# so those translation units are built with -fmad=false (explicit fma.rn is unaffected).  The
+# float-emulation / statistics units keep the default: libdevice's powf / log2f must be compiled
+# the way torch compiles them for S2FP8 to agree bit for bit with torch's CUDA operators.
+NO_FMAD = {"smaq_roundtrip.cu", "smaq_pack.cu"}
+
+
+def extra_flags(source: str):
+    flags = []
+    if os.path.basename(source) in NO_FMAD:
+        flags.append("-fmad=false")
+    if os.environ.get("SMAQ_DEV") == "1":  # development builds: only the default 6/8-bit packed kernels
+        flags.append("-DSMAQ_PACK_MINIMAL")
+    return flags
 
 
 def nvcc_path() -> str:
@@ -42,6 +57,7 @@ def nvcc_path() -> str:
 def _digest(paths) -> str:
     h = hashlib.sha256()
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(os.environ.get("SMAQ_DEV", "0").encode())
     for p in sorted(paths):
         with open(p, "rb") as f:
             h.update(p.encode())
@@ -61,7 +77,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for s in srcs:
         o = os.path.join(OUT_DIR, os.path.basename(s)[:-3] + ".o")
-        cmd = [nvcc_path(), *NVCC_FLAGS, "-c", s, "-o", o]
+        cmd = [nvcc_path(), *NVCC_FLAGS, *extra_flags(s), "-c", s, "-o", o]
         if verbose:
             cmd[1:1] = ["-Xptxas", "-v"]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -62,42 +62,56 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
 }
 
 // ---- Philox4x32-10 (Salmon et al., SC'11): counter-based, so the random number of element i
-// depends only on (seed, offset, i) and never on the launch geometry. ---------------------------
-struct Philox {
-  uint32_t k0, k1;
-  __host__ __device__ __forceinline__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
-
-  __host__ __device__ __forceinline__ static void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
-#if defined(__CUDA_ARCH__)
-    lo = a * b;
-    hi = __umulhi(a, b);
-#else
-    uint64_t p = (uint64_t)a * b;
-    lo = (uint32_t)p;
-    hi = (uint32_t)(p >> 32);
-#endif
-  }
-
-  // counter = (c0,c1,c2,c3); returns 4 x 32 random bits
-  __host__ __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
-    uint32_t ka = k0, kb = k1;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      uint32_t h0, l0, h1, l1;
-      mulhilo(0xD2511F53u, c0, h0, l0);
-      mulhilo(0xCD9E8D57u, c2, h1, l1);
-      uint32_t n0 = h1 ^ c1 ^ ka, n2 = h0 ^ c3 ^ kb;
-      c0 = n0; c1 = l1; c2 = n2; c3 = l0;
-      ka += 0x9E3779B9u; kb += 0xBB67AE85u;
-    }
-    uint4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
-    return o;
-  }
-  // the 4 random words for elements [4*g, 4*g+4) of a tensor
-  __host__ __device__ __forceinline__ uint4 for_group(uint64_t g, uint64_t offset) const {
-    return (*this)((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)offset, (uint32_t)(offset >> 32));
-  }
+// depends only on (seed, offset, i) and never on the launch geometry.  The ten round keys are
+// derived from the seed on the host and travel in the kernel parameters: in SASS they are
+// constant-bank operands of the LOP3s, not per-round additions. -------------------------------
+constexpr int kPhiloxRounds = 10;
+struct PhiloxKeys {
+  uint32_t k0[kPhiloxRounds], k1[kPhiloxRounds];
 };
+__host__ __device__ __forceinline__ PhiloxKeys make_philox_keys(uint64_t seed) {
+  PhiloxKeys K;
+  uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < kPhiloxRounds; ++r) {
+    K.k0[r] = a;
+    K.k1[r] = b;
+    a += 0x9E3779B9u;
+    b += 0xBB67AE85u;
+  }
+  return K;
+}
+__host__ __device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+  lo = a * b;
+  hi = __umulhi(a, b);
+#else
+  uint64_t p = (uint64_t)a * b;
+  lo = (uint32_t)p;
+  hi = (uint32_t)(p >> 32);
+#endif
+}
+// counter = (c0,c1,c2,c3); returns 4 x 32 random bits
+__host__ __device__ __forceinline__ uint4 philox4x32(const PhiloxKeys& K, uint32_t c0, uint32_t c1, uint32_t c2,
+                                                     uint32_t c3) {
+#pragma unroll
+  for (int r = 0; r < kPhiloxRounds; ++r) {
+    uint32_t h0, l0, h1, l1;
+    mulhilo32(0xD2511F53u, c0, h0, l0);
+    mulhilo32(0xCD9E8D57u, c2, h1, l1);
+    const uint32_t n0 = h1 ^ c1 ^ K.k0[r], n2 = h0 ^ c3 ^ K.k1[r];
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+  }
+  uint4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+  return o;
+}
+// the 4 random words for elements [4*g, 4*g+4) of a tensor, stream `offset`
+__host__ __device__ __forceinline__ uint4 philox_group(const PhiloxKeys& K, uint64_t g, uint64_t offset) {
+  return philox4x32(K, (uint32_t)g, (uint32_t)(g >> 32), (uint32_t)offset, (uint32_t)(offset >> 32));
+}
+__host__ __device__ __forceinline__ uint32_t philox_word(const uint4& q, int j) {
+  return j == 0 ? q.x : j == 1 ? q.y : j == 2 ? q.z : q.w;
+}
 
 // ---- warp helpers --------------------------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

@@ -10,7 +10,8 @@ struct KernelParams {
   float thr, range_main, range_out, clamp_lo, clamp_hi;
   int bits_main, bits_outlier;
   int all_positive, saturate;
-  uint64_t seed, offset;
+  uint64_t offset;
+  PhiloxKeys keys;
 };
 
 inline KernelParams to_kernel_params(const smaq_codec_params& p) {
@@ -24,8 +25,8 @@ inline KernelParams to_kernel_params(const smaq_codec_params& p) {
   k.bits_outlier = p.bits_outlier;
   k.all_positive = p.all_positive;
   k.saturate = p.saturate;
-  k.seed = p.seed;
   k.offset = p.offset;
+  k.keys = make_philox_keys(p.seed);
   return k;
 }
 

@@ -134,17 +134,53 @@ __device__ __forceinline__ uint32_t get_field(const uint32_t (&bw)[PM], int i) {
   return v & ((1u << PM) - 1u);
 }
 
+// Integer side of one element: rounded code (fp32) -> stored payload; updates the lane's words.
+//   payload = (min(|code|, limit) << 1) | s,  s = sign bit of the code (main) / lower side (outlier)
+// F2I saturates +-inf to INT_MAX/INT_MIN and maps NaN to 0, which is exactly the format's rule.
+template <int PM, int XB>
+__device__ __forceinline__ void pack_element(int i, float code, bool outl, bool lo, bool valid, const int lim_main,
+                                             const int lim_out, uint32_t& tagw, uint32_t (&bw)[PM], uint32_t (&ea)[8],
+                                             uint32_t (&ecnt)[8], uint32_t& n_sat) {
+  constexpr int EPG = 32 / ext_groups(XB);
+  const int ci = __float2int_rz(code);
+  const uint32_t a = (uint32_t)abs(ci);
+  const uint32_t lim = (uint32_t)(outl ? lim_out : lim_main);
+  const uint32_t mag = min(a, lim);
+  const bool bad = valid && ((a > lim) || (code != code));
+  const uint32_t sbit = outl ? (lo ? 1u : 0u) : ((code != code) ? 0u : (bits_of(code) >> 31));
+  uint32_t payload = (mag << 1) | sbit;
+  if (!valid) payload = 0u;
+  n_sat += bad ? 1u : 0u;
+  if (outl) tagw |= 1u << i;
+  put_field<PM>(bw, i, payload & ((1u << PM) - 1u));
+  if (XB > 0) {
+    const int g = i / EPG;
+    ea[g] |= (payload >> PM) << ecnt[g];  // payload >> PM is 0 for a main element
+    if (outl) ecnt[g] += (uint32_t)XB;
+  }
+}
+
+// Exact (IEEE-divide) re-computation of one 4-element chunk: degenerate statistics or a flagged chunk.
+template <bool kStochastic>
+__device__ __noinline__ void encode_chunk_exact(float4 v, float4 pr, const Scalars& s, float4& code, uint32_t& cls) {
+  PairClass k0, k1;
+  bool unused = false;
+  const f32x2 c01 = encode_pair<kStochastic, false>(pair(v.x, v.y), pair(pr.x, pr.y), s, k0, unused);
+  const f32x2 c23 = encode_pair<kStochastic, false>(pair(v.z, v.w), pair(pr.z, pr.w), s, k1, unused);
+  code = make_float4(c01.x, c01.y, c23.x, c23.y);
+  cls = (k0.outl0 ? 1u : 0u) | (k0.outl1 ? 2u : 0u) | (k1.outl0 ? 4u : 0u) | (k1.outl1 ? 8u : 0u) |
+        (k0.lo0 ? 16u : 0u) | (k0.lo1 ? 32u : 0u) | (k1.lo0 ? 64u : 0u) | (k1.lo1 ? 128u : 0u);
+}
+
 template <int PM, int XB, bool kStochastic, bool kHasProbs, bool kFast>
 __device__ __forceinline__ void encode_tile(const float* __restrict__ x, int64_t n, const float* __restrict__ probs,
                                             const KernelParams& kp, const Scalars& s, bool aligned, long long tile,
                                             uint32_t* __restrict__ planes, uint32_t& tagw_out, uint32_t (&ea)[8],
                                             uint32_t (&ecnt)[8], uint32_t& n_sat_out) {
-  constexpr int G = ext_groups(XB);
-  constexpr int EPG = 32 / G;
   const int lane = lane_id();
   const int64_t wt = (int64_t)tile * kWarpsPerCta + warp_id();
   const int64_t base = wt * kWarpTile;
-  const Philox rng(kp.seed);
+  const int lim_main = (int)s.lim_main, lim_out = (int)s.lim_out;
 
   uint32_t tagw = 0, n_sat = 0;
   uint32_t bw[PM];
@@ -155,63 +191,57 @@ __device__ __forceinline__ void encode_tile(const float* __restrict__ x, int64_t
 
   if (base < n) {
     const bool full = aligned && (base + kWarpTile <= n);
-    float v[32], pr[32];
+    float4 v[8], pr[8];
     if (full) {
       const float4* xv = reinterpret_cast<const float4*>(x + base) + lane;
       const float4* pv = reinterpret_cast<const float4*>(probs + base) + lane;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float4 t = ldg_stream(xv + 32 * k);
-        v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
-      }
+      for (int k = 0; k < 8; ++k) v[k] = ldg_stream(xv + 32 * k);
       if (kStochastic && kHasProbs) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float4 t = ldg_stream(pv + 32 * k);
-          pr[4 * k] = t.x; pr[4 * k + 1] = t.y; pr[4 * k + 2] = t.z; pr[4 * k + 3] = t.w;
-        }
+        for (int k = 0; k < 8; ++k) pr[k] = ldg_stream(pv + 32 * k);
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int64_t e = base + 128 * (i >> 2) + 4 * lane + (i & 3);
-        v[i] = (e < n) ? x[e] : 0.0f;
-        if (kStochastic && kHasProbs) pr[i] = (e < n) ? probs[e] : 0.0f;
+      for (int k = 0; k < 8; ++k) {
+        const int64_t e = base + 128 * k + 4 * lane;
+        v[k] = make_float4(e < n ? x[e] : 0.f, e + 1 < n ? x[e + 1] : 0.f, e + 2 < n ? x[e + 2] : 0.f,
+                           e + 3 < n ? x[e + 3] : 0.f);
+        if (kStochastic && kHasProbs)
+          pr[k] = make_float4(e < n ? probs[e] : 0.f, e + 1 < n ? probs[e + 1] : 0.f, e + 2 < n ? probs[e + 2] : 0.f,
+                              e + 3 < n ? probs[e + 3] : 0.f);
       }
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      uint4 r = make_uint4(0, 0, 0, 0);
-      if (kStochastic && !kHasProbs) r = rng.for_group((uint64_t)((base >> 2) + 32 * k + lane), kp.offset);
+      float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kStochastic) {
+        if (kHasProbs) p4 = pr[k];
+        else {
+          const uint4 r = philox_group(kp.keys, (uint64_t)((base >> 2) + 32 * k + lane), kp.offset);
+          const f32x2 a = uniform24_pair(r.x, r.y), b = uniform24_pair(r.z, r.w);
+          p4 = make_float4(a.x, a.y, b.x, b.y);
+        }
+      }
+      float4 code;
+      uint32_t cls;
+      bool suspect = !kFast;
+      if (kFast) {
+        PairClass k0, k1;
+        const f32x2 c01 = encode_pair<kStochastic, true>(pair(v[k].x, v[k].y), pair(p4.x, p4.y), s, k0, suspect);
+        const f32x2 c23 = encode_pair<kStochastic, true>(pair(v[k].z, v[k].w), pair(p4.z, p4.w), s, k1, suspect);
+        code = make_float4(c01.x, c01.y, c23.x, c23.y);
+        cls = (k0.outl0 ? 1u : 0u) | (k0.outl1 ? 2u : 0u) | (k1.outl0 ? 4u : 0u) | (k1.outl1 ? 8u : 0u) |
+              (k0.lo0 ? 16u : 0u) | (k0.lo1 ? 32u : 0u) | (k1.lo0 ? 64u : 0u) | (k1.lo1 ? 128u : 0u);
+      }
+      if (suspect) encode_chunk_exact<kStochastic>(v[k], p4, s, code, cls);
+      const float cj[4] = {code.x, code.y, code.z, code.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int i = 4 * k + j;
-        float p = 0.0f;
-        if (kStochastic) p = kHasProbs ? pr[i] : uniform24(j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w);
-        Classified c;
-        const float code = encode_value<kStochastic, kFast>(v[i], s, p, c);
-        bool outl = c.hi || c.lo;
-        float sat = saturate_code(code, s, outl);
-        bool bad = !(sat == code);  // clipped at the field width, or not a number
-        sat = (sat != sat) ? 0.0f : sat;
-        bool valid = true;
-        if (!full) {
-          valid = (base + 128 * k + 4 * lane + j) < n;
-          outl = outl && valid;
-          bad = bad && valid;
-        }
-        const uint32_t mag = (uint32_t)abs(__float2int_rz(sat));
-        const uint32_t sbit = outl ? (c.lo ? 1u : 0u) : (__float_as_uint(sat) >> 31);
-        uint32_t payload = (mag << 1) | sbit;
-        if (!full) payload = valid ? payload : 0u;
-        n_sat += bad ? 1u : 0u;
-        tagw |= (outl ? 1u : 0u) << i;
-        put_field<PM>(bw, i, payload & ((1u << PM) - 1u));
-        if (XB > 0) {
-          const int g = i / EPG;
-          ea[g] |= (payload >> PM) << ecnt[g];  // payload >> PM is 0 for a main element
-          ecnt[g] += outl ? (uint32_t)XB : 0u;
-        }
+        const bool valid = full || (base + 128 * k + 4 * lane + j) < n;
+        const bool outl = ((cls >> j) & 1u) && valid;
+        pack_element<PM, XB>(4 * k + j, cj[j], outl, (cls >> (4 + j)) & 1u, valid, lim_main, lim_out, tagw, bw, ea,
+                             ecnt, n_sat);
       }
     }
     // fixed-position part of the stream: (1 + PM) rows of 32 words per warp tile, coalesced
@@ -227,7 +257,8 @@ __device__ __forceinline__ void encode_tile(const float* __restrict__ x, int64_t
 template <int PM, int XB, bool kStochastic, bool kHasProbs>
 __global__ void __launch_bounds__(kPackThreads, 2)
     encode_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ mean_std,
-                  const float* __restrict__ probs, KernelParams kp, smaq_packed_header* __restrict__ hdr,
+                  const float* __restrict__ probs, const __grid_constant__ KernelParams kp,
+                  smaq_packed_header* __restrict__ hdr,
                   uint32_t* __restrict__ table, uint32_t* __restrict__ planes, uint32_t* __restrict__ extras,
                   EncodeWs* ws, long long n_cta_tiles, int aligned) {
   constexpr int G = ext_groups(XB);
@@ -318,10 +349,10 @@ __global__ void __launch_bounds__(kPackThreads, 2)
   }
 }
 
-template <int PM, int XB, bool kFast>
+template <int PM, int XB, bool kFast, bool kAllPos>
 __device__ __forceinline__ void decode_tile(const uint32_t* __restrict__ s_ext, uint32_t pos, uint32_t tagw,
-                                            const uint32_t (&bw)[PM], const Scalars& s, bool all_positive,
-                                            float* __restrict__ y, int64_t n, int64_t base, bool aligned) {
+                                            const uint32_t (&bw)[PM], const Scalars& s, float* __restrict__ y,
+                                            int64_t n, int64_t base, bool aligned) {
   constexpr int G = ext_groups(XB);
   constexpr int EPG = 32 / G;
   const int lane = lane_id();
@@ -339,7 +370,7 @@ __device__ __forceinline__ void decode_tile(const uint32_t* __restrict__ s_ext, 
   const bool full = aligned && (base + kWarpTile <= n);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    float o[4];
+    float code[4], shift[4], rb[4], rr[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int i = 4 * k + j;
@@ -355,16 +386,20 @@ __device__ __forceinline__ void decode_tile(const uint32_t* __restrict__ s_ext, 
       }
       const uint32_t sbit = payload & 1u;
       const float mag = (float)(payload >> 1);
-      const float code = __uint_as_float(__float_as_uint(mag) | (sbit << 31));  // -0.0 when sbit and mag == 0
-      const float shift = outl ? (sbit ? s.shift_lo : s.shift_hi) : s.shift_mid;
-      Divisor range;
-      range.b = outl ? s.range_out.b : s.range_main.b;
-      range.r = outl ? s.range_out.r : s.range_main.r;
-      o[j] = decode_value<kFast>(code, shift, range, s, all_positive);
+      code[j] = __uint_as_float(__float_as_uint(mag) | (sbit << 31));  // -0.0 when s and mag == 0
+      shift[j] = outl ? (sbit ? s.shift_lo : s.shift_hi) : s.shift_mid;
+      rb[j] = outl ? s.range_out.b : s.range_main.b;
+      rr[j] = outl ? s.range_out.r : s.range_main.r;
     }
+    bool unused = false;
+    const f32x2 y01 = decode_pair<kFast, false>(pair(code[0], code[1]), pair(shift[0], shift[1]), pair(rb[0], rb[1]),
+                                                pair(rr[0], rr[1]), s, kAllPos, unused);
+    const f32x2 y23 = decode_pair<kFast, false>(pair(code[2], code[3]), pair(shift[2], shift[3]), pair(rb[2], rb[3]),
+                                                pair(rr[2], rr[3]), s, kAllPos, unused);
     if (full) {
-      stg_stream(reinterpret_cast<float4*>(y + base) + 32 * k + lane, make_float4(o[0], o[1], o[2], o[3]));
+      stg_stream(reinterpret_cast<float4*>(y + base) + 32 * k + lane, make_float4(y01.x, y01.y, y23.x, y23.y));
     } else {
+      const float o[4] = {y01.x, y01.y, y23.x, y23.y};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int64_t e = base + 128 * k + 4 * lane + j;
@@ -406,14 +441,22 @@ __global__ void __launch_bounds__(kPackThreads, 2)
   if (threadIdx.x < 2) s_ext[words + threadIdx.x] = 0;
   __syncthreads();
   if (base >= n) return;
-  if (s.fast) decode_tile<PM, XB, true>(s_ext, pos, tagw, bw, s, all_positive != 0, y, n, base, aligned != 0);
-  else decode_tile<PM, XB, false>(s_ext, pos, tagw, bw, s, all_positive != 0, y, n, base, aligned != 0);
+  if (s.fast) {
+    if (all_positive) decode_tile<PM, XB, true, true>(s_ext, pos, tagw, bw, s, y, n, base, aligned != 0);
+    else decode_tile<PM, XB, true, false>(s_ext, pos, tagw, bw, s, y, n, base, aligned != 0);
+  } else {
+    if (all_positive) decode_tile<PM, XB, false, true>(s_ext, pos, tagw, bw, s, y, n, base, aligned != 0);
+    else decode_tile<PM, XB, false, false>(s_ext, pos, tagw, bw, s, y, n, base, aligned != 0);
+  }
 }
 
 static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 static bool width_supported(int bits_main, int bits_outlier) {
   const int pm = bits_main - 1, xb = bits_outlier - bits_main;
+#ifdef SMAQ_PACK_MINIMAL
+  return pm == 5 && xb == 2;
+#endif
   return pm >= 3 && pm <= 7 && xb >= 0 && xb <= 4;
 }
 
@@ -485,7 +528,11 @@ int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* p
           x, n, mean_std, probs, kp, hdr, table, planes, extras, (EncodeWs*)ws, l.n_cta_tiles, aligned);           \
   }
 #define SMAQ_ENC_ROW(PM_) SMAQ_ENC(PM_, 0) SMAQ_ENC(PM_, 1) SMAQ_ENC(PM_, 2) SMAQ_ENC(PM_, 3) SMAQ_ENC(PM_, 4)
+#ifdef SMAQ_PACK_MINIMAL
+  SMAQ_ENC(5, 2)
+#else
   SMAQ_ENC_ROW(3) SMAQ_ENC_ROW(4) SMAQ_ENC_ROW(5) SMAQ_ENC_ROW(6) SMAQ_ENC_ROW(7)
+#endif
 #undef SMAQ_ENC_ROW
 #undef SMAQ_ENC
   SMAQ_LAUNCH_OK();
@@ -512,7 +559,11 @@ int smaq_decode(const void* packed, size_t packed_bytes, int64_t n, int32_t bits
   if (pm == PM_ && xb == XB_)                                                                                      \
     decode_kernel<PM_, XB_><<<grid, kPackThreads, 0, stream>>>(hdr, table, planes, extras, y, n, all_positive, aligned);
 #define SMAQ_DEC_ROW(PM_) SMAQ_DEC(PM_, 0) SMAQ_DEC(PM_, 1) SMAQ_DEC(PM_, 2) SMAQ_DEC(PM_, 3) SMAQ_DEC(PM_, 4)
+#ifdef SMAQ_PACK_MINIMAL
+  SMAQ_DEC(5, 2)
+#else
   SMAQ_DEC_ROW(3) SMAQ_DEC_ROW(4) SMAQ_DEC_ROW(5) SMAQ_DEC_ROW(6) SMAQ_DEC_ROW(7)
+#endif
 #undef SMAQ_DEC_ROW
 #undef SMAQ_DEC
   SMAQ_LAUNCH_OK();

@@ -6,7 +6,10 @@
 // std==0 fix-up and the clamp are evaluated on the device, so the call never synchronises.
 //
 // HBM roofline: 8 bytes per element (4 read + 4 written); +4 when an explicit probs tensor is
-// passed (parity mode only; the performance path draws Philox numbers in-kernel).
+// passed (parity mode only; the performance path draws Philox numbers in-kernel).  Measured
+// (profiles/): the kernel is bound by instruction issue, so the element loop is written to
+// minimise issue slots — packed FADD2/FMUL2/FFMA2 arithmetic, three-instruction divisions
+// checked once per four elements, Philox round keys as constant-bank operands.
 #include "common.cuh"
 #include "moments.cuh"
 #include "params.cuh"
@@ -14,91 +17,117 @@
 
 namespace smaq {
 
-template <bool kStochastic, bool kFast>
-__device__ __forceinline__ float roundtrip_one(float x, float p, const Scalars& s, bool saturate, bool all_positive) {
-  Classified k;
-  float code = encode_value<kStochastic, kFast>(x, s, p, k);
-  if (saturate) code = saturate_code(code, s, k.hi || k.lo);
-  return decode_value<kFast>(code, k.shift, k.range, s, all_positive);
+// Four elements with the IEEE divide everywhere: degenerate statistics, or a group the fast
+// path flagged.  Out of line so the hot loop stays small.
+template <bool kStochastic>
+__device__ __noinline__ float4 roundtrip_group_exact(float4 v, float4 pr, const Scalars& s, bool saturate,
+                                                     bool all_positive) {
+  PairClass k0, k1;
+  bool unused = false;
+  f32x2 c01 = encode_pair<kStochastic, false>(pair(v.x, v.y), pair(pr.x, pr.y), s, k0, unused);
+  f32x2 c23 = encode_pair<kStochastic, false>(pair(v.z, v.w), pair(pr.z, pr.w), s, k1, unused);
+  if (saturate) {
+    c01 = pair(saturate_code(c01.x, s, k0.outl0), saturate_code(c01.y, s, k0.outl1));
+    c23 = pair(saturate_code(c23.x, s, k1.outl0), saturate_code(c23.y, s, k1.outl1));
+  }
+  f32x2 y01 = decode_pair<false, false>(c01, k0.shift, k0.range_b, k0.range_r, s, all_positive, unused);
+  f32x2 y23 = decode_pair<false, false>(c23, k1.shift, k1.range_b, k1.range_r, s, all_positive, unused);
+  return make_float4(y01.x, y01.y, y23.x, y23.y);
 }
 
-// Processes the 4-element group g (elements 4g..4g+3) of a tensor whose base pointers are 16-byte aligned.
-template <bool kStochastic, bool kHasProbs, bool kFast>
+// Processes the 4-element group g (elements 4g..4g+3).
+template <bool kStochastic, bool kHasProbs, bool kAllPos, bool kSaturate, bool kFast>
 __device__ __forceinline__ float4 roundtrip_group(float4 v, float4 pr, uint64_t g, const Scalars& s,
-                                                  const KernelParams& kp, const Philox& rng) {
-  float p0 = pr.x, p1 = pr.y, p2 = pr.z, p3 = pr.w;
+                                                  const KernelParams& kp) {
   if (kStochastic && !kHasProbs) {
-    uint4 r = rng.for_group(g, kp.offset);
-    p0 = uniform24(r.x); p1 = uniform24(r.y); p2 = uniform24(r.z); p3 = uniform24(r.w);
+    const uint4 r = philox_group(kp.keys, g, kp.offset);
+    const f32x2 a = uniform24_pair(r.x, r.y), b = uniform24_pair(r.z, r.w);
+    pr = make_float4(a.x, a.y, b.x, b.y);
   }
-  float4 o;
-  o.x = roundtrip_one<kStochastic, kFast>(v.x, p0, s, kp.saturate, kp.all_positive);
-  o.y = roundtrip_one<kStochastic, kFast>(v.y, p1, s, kp.saturate, kp.all_positive);
-  o.z = roundtrip_one<kStochastic, kFast>(v.z, p2, s, kp.saturate, kp.all_positive);
-  o.w = roundtrip_one<kStochastic, kFast>(v.w, p3, s, kp.saturate, kp.all_positive);
+  if (!kFast) return roundtrip_group_exact<kStochastic>(v, pr, s, kSaturate, kAllPos);
+  PairClass k0, k1;
+  bool suspect = false;
+  f32x2 c01 = encode_pair<kStochastic, true>(pair(v.x, v.y), pair(pr.x, pr.y), s, k0, suspect);
+  f32x2 c23 = encode_pair<kStochastic, true>(pair(v.z, v.w), pair(pr.z, pr.w), s, k1, suspect);
+  if (kSaturate) {
+    c01 = pair(saturate_code(c01.x, s, k0.outl0), saturate_code(c01.y, s, k0.outl1));
+    c23 = pair(saturate_code(c23.x, s, k1.outl0), saturate_code(c23.y, s, k1.outl1));
+  }
+  const f32x2 y01 = decode_pair<true, true>(c01, k0.shift, k0.range_b, k0.range_r, s, kAllPos, suspect);
+  const f32x2 y23 = decode_pair<true, true>(c23, k1.shift, k1.range_b, k1.range_r, s, kAllPos, suspect);
+  float4 o = make_float4(y01.x, y01.y, y23.x, y23.y);
+  if (suspect) o = roundtrip_group_exact<kStochastic>(v, pr, s, kSaturate, kAllPos);  // rare
   return o;
 }
 
 constexpr int kRtThreads = 256;
 constexpr int kRtUnroll = 4;  // independent 128-bit loads in flight per thread
 
-template <bool kStochastic, bool kHasProbs, bool kAligned, bool kFast>
+template <bool kStochastic, bool kHasProbs, bool kAllPos, bool kSaturate, bool kFast>
 __device__ __forceinline__ void roundtrip_body(const float* x, float* y, int64_t n, const float* __restrict__ probs,
                                                const KernelParams& kp, const Scalars& s) {
-  const Philox rng(kp.seed);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   const int64_t ngroups = n >> 2;
-
-  if (kAligned) {
-    const float4* xv = reinterpret_cast<const float4*>(x);
-    const float4* pv = reinterpret_cast<const float4*>(probs);
-    float4* yv = reinterpret_cast<float4*>(y);
-    int64_t g = tid;
-    for (; g + (kRtUnroll - 1) * nthreads < ngroups; g += kRtUnroll * nthreads) {
-      float4 v[kRtUnroll], pr[kRtUnroll];
+  const float4* xv = reinterpret_cast<const float4*>(x);
+  const float4* pv = reinterpret_cast<const float4*>(probs);
+  float4* yv = reinterpret_cast<float4*>(y);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  int64_t g = tid;
+  for (; g + (kRtUnroll - 1) * nthreads < ngroups; g += kRtUnroll * nthreads) {
+    float4 v[kRtUnroll], pr[kRtUnroll];
 #pragma unroll
-      for (int u = 0; u < kRtUnroll; ++u) {
-        v[u] = ldg_stream(xv + g + u * nthreads);
-        if (kStochastic && kHasProbs) pr[u] = ldg_stream(pv + g + u * nthreads);
-        else pr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+    for (int u = 0; u < kRtUnroll; ++u) {
+      v[u] = ldg_stream(xv + g + u * nthreads);
+      pr[u] = (kStochastic && kHasProbs) ? ldg_stream(pv + g + u * nthreads) : zero4;
+    }
 #pragma unroll
-      for (int u = 0; u < kRtUnroll; ++u)
-        stg_stream(yv + g + u * nthreads,
-                   roundtrip_group<kStochastic, kHasProbs, kFast>(v[u], pr[u], (uint64_t)(g + u * nthreads), s, kp, rng));
-    }
-    for (; g < ngroups; g += nthreads) {
-      float4 v = ldg_stream(xv + g);
-      float4 pr = (kStochastic && kHasProbs) ? ldg_stream(pv + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-      stg_stream(yv + g, roundtrip_group<kStochastic, kHasProbs, kFast>(v, pr, (uint64_t)g, s, kp, rng));
-    }
+    for (int u = 0; u < kRtUnroll; ++u)
+      stg_stream(yv + g + u * nthreads, roundtrip_group<kStochastic, kHasProbs, kAllPos, kSaturate, kFast>(
+                                            v[u], pr[u], (uint64_t)(g + u * nthreads), s, kp));
   }
-  // elements not covered by whole aligned groups: the last n%4 (aligned) or everything (unaligned)
-  const int64_t first = kAligned ? (ngroups << 2) : 0;
-  for (int64_t i = first + tid; i < n; i += nthreads) {
-    float p = 0.f;
-    if (kStochastic) {
-      if (kHasProbs) p = probs[i];
-      else {
-        uint4 r = rng.for_group((uint64_t)(i >> 2), kp.offset);
-        uint32_t w = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
-        p = uniform24(w);
-      }
-    }
-    y[i] = roundtrip_one<kStochastic, kFast>(x[i], p, s, kp.saturate, kp.all_positive);
+  for (; g < ngroups; g += nthreads) {
+    const float4 v = ldg_stream(xv + g);
+    const float4 pr = (kStochastic && kHasProbs) ? ldg_stream(pv + g) : zero4;
+    stg_stream(yv + g, roundtrip_group<kStochastic, kHasProbs, kAllPos, kSaturate, kFast>(v, pr, (uint64_t)g, s, kp));
   }
 }
 
-template <bool kStochastic, bool kHasProbs, bool kAligned>
+// One element at a time: tails, unaligned tensors, small tensors.
+template <bool kStochastic, bool kHasProbs>
+__device__ __forceinline__ float roundtrip_element(const float* x, const float* probs, int64_t i, const Scalars& s,
+                                                   const KernelParams& kp) {
+  float p = 0.f;
+  if (kStochastic)
+    p = kHasProbs ? probs[i] : uniform24(philox_word(philox_group(kp.keys, (uint64_t)(i >> 2), kp.offset), (int)(i & 3)));
+  return roundtrip_scalar<kStochastic>(x[i], p, s, kp.saturate != 0, kp.all_positive != 0);
+}
+
+// Aligned tensors: 128-bit path for whole groups, element path for the last n % 4.
+template <bool kStochastic, bool kHasProbs, bool kAllPos, bool kSaturate>
 __global__ void __launch_bounds__(kRtThreads) roundtrip_kernel(const float* x, float* y, int64_t n,
                                                                const float* __restrict__ mean_std,
-                                                               const float* __restrict__ probs, KernelParams kp) {
+                                                               const float* __restrict__ probs,
+                                                               const __grid_constant__ KernelParams kp) {
   const Scalars s = scalars_from(mean_std[0], mean_std[1], kp);
   // uniform branch: the three-instruction division is valid for this tensor, or every division
   // is the IEEE one (degenerate statistics: huge/tiny/NaN std, mean == -0)
-  if (s.fast) roundtrip_body<kStochastic, kHasProbs, kAligned, true>(x, y, n, probs, kp, s);
-  else roundtrip_body<kStochastic, kHasProbs, kAligned, false>(x, y, n, probs, kp, s);
+  if (s.fast) roundtrip_body<kStochastic, kHasProbs, kAllPos, kSaturate, true>(x, y, n, probs, kp, s);
+  else roundtrip_body<kStochastic, kHasProbs, kAllPos, kSaturate, false>(x, y, n, probs, kp, s);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = ((n >> 2) << 2) + tid;
+  if (i < n) y[i] = roundtrip_element<kStochastic, kHasProbs>(x, probs, i, s, kp);
+}
+
+// Tensors whose pointers are only 4-byte aligned (views into larger buffers).
+template <bool kStochastic, bool kHasProbs>
+__global__ void __launch_bounds__(kRtThreads) roundtrip_unaligned_kernel(const float* x, float* y, int64_t n,
+                                                                         const float* __restrict__ mean_std,
+                                                                         const float* __restrict__ probs,
+                                                                         const __grid_constant__ KernelParams kp) {
+  const Scalars s = scalars_from(mean_std[0], mean_std[1], kp);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = roundtrip_element<kStochastic, kHasProbs>(x, probs, i, s, kp);
 }
 
 // ---- small tensors: statistics + round trip in one block, one launch ---------------------------
@@ -121,42 +150,25 @@ __device__ __forceinline__ void small_body(const float* x, float* y, int64_t n, 
   }
   __syncthreads();
   const Scalars s = scalars_from(bcast[0], bcast[1], kp);
-  const Philox rng(kp.seed);
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    float p = 0.f;
-    if (kStochastic) {
-      if (kHasProbs) p = probs[i];
-      else {
-        uint4 r = rng.for_group((uint64_t)(i >> 2), kp.offset);
-        uint32_t w = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
-        p = uniform24(w);
-      }
-    }
-    y[i] = s.fast ? roundtrip_one<kStochastic, true>(x[i], p, s, kp.saturate, kp.all_positive)
-                  : roundtrip_one<kStochastic, false>(x[i], p, s, kp.saturate, kp.all_positive);
-  }
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) y[i] = roundtrip_element<kStochastic, kHasProbs>(x, probs, i, s, kp);
   __syncthreads();
 }
 
 template <bool kStochastic, bool kHasProbs>
 __global__ void __launch_bounds__(kStatsThreads) roundtrip_small_kernel(const float* x, float* y, int64_t n,
-                                                                        const float* probs, KernelParams kp,
+                                                                        const float* probs,
+                                                                        const __grid_constant__ KernelParams kp,
                                                                         float* mean_std_out) {
   __shared__ Acc smem[kStatsThreads / 32];
   __shared__ float bcast[2];
   small_body<kStochastic, kHasProbs>(x, y, n, probs, kp, mean_std_out, smem, bcast);
 }
 
-// ---- many tensors, one launch -------------------------------------------------------------------
-// Small tensors (n <= kSmallMax) are handled whole by one block each.  Large tensors run the
-// same grid-wide two-phase scheme as the single-tensor path, phase 1 here, phase 2 below.
-struct MultiWs {
-  float mean_std[2];
-};
-
+// ---- many small tensors, one launch ----------------------------------------------------------------
 template <bool kStochastic>
 __global__ void __launch_bounds__(kStatsThreads) multi_small_kernel(const smaq_tensor_desc* __restrict__ descs,
-                                                                    int count, int64_t min_size, KernelParams kp) {
+                                                                    int count, int64_t min_size,
+                                                                    const __grid_constant__ KernelParams kp) {
   __shared__ Acc smem[kStatsThreads / 32];
   __shared__ float bcast[2];
   for (int t = blockIdx.x; t < count; t += gridDim.x) {
@@ -177,11 +189,12 @@ __global__ void __launch_bounds__(kStatsThreads) multi_small_kernel(const smaq_t
 // --measure_compression_ratio only: how many elements classify as outliers.
 __global__ void __launch_bounds__(kRtThreads) count_outliers_kernel(const float* __restrict__ x, int64_t n,
                                                                     const float* __restrict__ mean_std,
-                                                                    KernelParams kp, unsigned long long* counter) {
+                                                                    const __grid_constant__ KernelParams kp,
+                                                                    unsigned long long* counter) {
   const Scalars s = scalars_from(mean_std[0], mean_std[1], kp);
   unsigned int local = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float z = true_div(x[i] - s.mean, s.div.b);
+    float z = true_div(__fsub_rn(x[i], s.mean), s.div.b);
     local += (z > s.thr || z < s.neg_thr) ? 1u : 0u;
   }
   local = warp_sum(local);
@@ -197,6 +210,17 @@ static int rt_grid(int64_t n) {
   return (int)(want < cap ? want : cap);
 }
 
+template <bool kStochastic, bool kHasProbs>
+static void launch_aligned(int grid, cudaStream_t stream, const float* x, float* y, int64_t n, const float* mean_std,
+                           const float* probs, const KernelParams& kp) {
+  const bool ap = kp.all_positive != 0, sat = kp.saturate != 0;
+#define SMAQ_RT(AP, SAT) \
+  roundtrip_kernel<kStochastic, kHasProbs, AP, SAT><<<grid, kRtThreads, 0, stream>>>(x, y, n, mean_std, probs, kp)
+  if (ap) { if (sat) SMAQ_RT(true, true); else SMAQ_RT(true, false); }
+  else    { if (sat) SMAQ_RT(false, true); else SMAQ_RT(false, false); }
+#undef SMAQ_RT
+}
+
 }  // namespace smaq
 
 extern "C" {
@@ -208,17 +232,19 @@ int smaq_roundtrip(const float* x, float* y, int64_t n, const float* mean_std, c
   if (!x || !y || !mean_std || n < 0) return fail(SMAQ_ERR_ARG, "roundtrip: null pointer or n < 0");
   if (n == 0) return SMAQ_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
-  KernelParams kp = to_kernel_params(*params);
+  const KernelParams kp = to_kernel_params(*params);
   const bool al = aligned16(x) && aligned16(y) && (!probs || aligned16(probs));
   const int grid = rt_grid(n);
-#define SMAQ_RT(S, P, A) roundtrip_kernel<S, P, A><<<grid, kRtThreads, 0, stream>>>(x, y, n, mean_std, probs, kp)
-  if (params->stochastic) {
-    if (probs) { if (al) SMAQ_RT(true, true, true); else SMAQ_RT(true, true, false); }
-    else       { if (al) SMAQ_RT(true, false, true); else SMAQ_RT(true, false, false); }
+  const bool st = params->stochastic != 0;
+  if (al) {
+    if (!st) launch_aligned<false, false>(grid, stream, x, y, n, mean_std, probs, kp);
+    else if (probs) launch_aligned<true, true>(grid, stream, x, y, n, mean_std, probs, kp);
+    else launch_aligned<true, false>(grid, stream, x, y, n, mean_std, probs, kp);
   } else {
-    if (al) SMAQ_RT(false, false, true); else SMAQ_RT(false, false, false);
+    if (!st) roundtrip_unaligned_kernel<false, false><<<grid, kRtThreads, 0, stream>>>(x, y, n, mean_std, probs, kp);
+    else if (probs) roundtrip_unaligned_kernel<true, true><<<grid, kRtThreads, 0, stream>>>(x, y, n, mean_std, probs, kp);
+    else roundtrip_unaligned_kernel<true, false><<<grid, kRtThreads, 0, stream>>>(x, y, n, mean_std, probs, kp);
   }
-#undef SMAQ_RT
   SMAQ_LAUNCH_OK();
   return SMAQ_OK;
 }
@@ -229,7 +255,7 @@ int smaq_count_outliers(const float* x, int64_t n, const float* mean_std, const 
   if (int rc = check_params(params)) return rc;
   if (!x || !mean_std || !counter || n < 0) return fail(SMAQ_ERR_ARG, "count_outliers: bad argument");
   if (n == 0) return SMAQ_OK;
-  KernelParams kp = to_kernel_params(*params);
+  const KernelParams kp = to_kernel_params(*params);
   count_outliers_kernel<<<rt_grid(n), kRtThreads, 0, (cudaStream_t)stream_>>>(x, n, mean_std, kp, counter);
   SMAQ_LAUNCH_OK();
   return SMAQ_OK;
@@ -244,7 +270,7 @@ int smaq_roundtrip_small(const float* x, float* y, int64_t n, const float* probs
   if (!x || !y || n <= 0) return fail(SMAQ_ERR_ARG, "roundtrip_small: null pointer or n <= 0");
   if (n > kSmallMax) return fail(SMAQ_ERR_ARG, "roundtrip_small: n > %lld", (long long)kSmallMax);
   cudaStream_t stream = (cudaStream_t)stream_;
-  KernelParams kp = to_kernel_params(*params);
+  const KernelParams kp = to_kernel_params(*params);
   if (params->stochastic) {
     if (probs) roundtrip_small_kernel<true, true><<<1, kStatsThreads, 0, stream>>>(x, y, n, probs, kp, mean_std_out);
     else roundtrip_small_kernel<true, false><<<1, kStatsThreads, 0, stream>>>(x, y, n, probs, kp, mean_std_out);
@@ -272,7 +298,7 @@ int smaq_roundtrip_multi(const smaq_tensor_desc* descs, int32_t count, int64_t m
     return fail(SMAQ_ERR_UNSUPPORTED, "roundtrip_multi: tensors above %lld elements go through smaq_roundtrip",
                 (long long)kSmallMax);
   cudaStream_t stream = (cudaStream_t)stream_;
-  KernelParams kp = to_kernel_params(*params);
+  const KernelParams kp = to_kernel_params(*params);
   int sms = sm_count();
   if (sms <= 0) sms = 148;
   int grid = count < sms * 8 ? count : sms * 8;

@@ -115,10 +115,10 @@ __global__ void __launch_bounds__(32) sampled_draw_stats_kernel(const float* __r
                                                                 float* __restrict__ out) {
   __shared__ int64_t chosen[1024];
   const int lane = lane_id();
-  Philox rng(seed);
+  const PhiloxKeys keys = make_philox_keys(seed);
   for (int i = 0; i < k; ++i) {
     const int64_t j = n - k + i;  // Floyd: t ~ U{0..j}; take t unless already chosen, else j
-    uint4 r = rng.for_group((uint64_t)i, offset);
+    uint4 r = philox_group(keys, (uint64_t)i, offset);
     uint64_t r64 = ((uint64_t)r.x << 32) | r.y;
     int64_t t = (int64_t)__umul64hi(r64, (uint64_t)j + 1);
     bool hit = false;

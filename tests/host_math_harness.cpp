@@ -11,25 +11,42 @@ using namespace smaq;
 
 extern "C" {
 
-// Round trip of n values with explicit probs; variant: 0 = IEEE divide everywhere, 1 = as the kernel decides.
+// Round trip of n values with explicit probs, processed in pairs exactly as the kernels do;
+// variant: 0 = IEEE divide everywhere, 1 = as the kernel decides (fast path + exact redo of flagged pairs).
 void harness_roundtrip(const float* x, const float* probs, float* y, float* codes, int64_t n, float mean,
                        float std_raw, float thr, float range_main, float range_out, float clamp_lo, float clamp_hi,
                        int bits_main, int bits_outlier, int stochastic, int all_positive, int saturate, int variant,
                        int* used_fast) {
   Scalars s = make_scalars(mean, std_raw, thr, range_main, range_out, clamp_lo, clamp_hi, bits_main, bits_outlier);
   bool fast = variant == 1 && s.fast;
-  if (used_fast) *used_fast = fast;
-  for (int64_t i = 0; i < n; ++i) {
-    Classified k;
-    float p = probs ? probs[i] : 0.0f;
-    float code;
-    if (fast) code = stochastic ? encode_value<true, true>(x[i], s, p, k) : encode_value<false, true>(x[i], s, p, k);
-    else code = stochastic ? encode_value<true, false>(x[i], s, p, k) : encode_value<false, false>(x[i], s, p, k);
-    if (saturate) code = saturate_code(code, s, k.hi || k.lo);
-    if (codes) codes[i] = code;
-    y[i] = fast ? decode_value<true>(code, k.shift, k.range, s, all_positive)
-                : decode_value<false>(code, k.shift, k.range, s, all_positive);
+  int64_t redone = 0;
+  for (int64_t i = 0; i < n; i += 2) {
+    const bool has2 = i + 1 < n;
+    f32x2 xv = pair(x[i], has2 ? x[i + 1] : x[i]);
+    f32x2 pv = pair(probs ? probs[i] : 0.0f, probs ? (has2 ? probs[i + 1] : probs[i]) : 0.0f);
+    PairClass k;
+    bool suspect = !fast;
+    f32x2 code = pair(0.f, 0.f), out = pair(0.f, 0.f);
+    if (fast) {
+      code = stochastic ? encode_pair<true, true>(xv, pv, s, k, suspect) : encode_pair<false, true>(xv, pv, s, k, suspect);
+      if (saturate) code = pair(saturate_code(code.x, s, k.outl0), saturate_code(code.y, s, k.outl1));
+      out = decode_pair<true, true>(code, k.shift, k.range_b, k.range_r, s, all_positive != 0, suspect);
+    }
+    if (suspect) {
+      bool unused = false;
+      redone += fast;
+      code = stochastic ? encode_pair<true, false>(xv, pv, s, k, unused) : encode_pair<false, false>(xv, pv, s, k, unused);
+      if (saturate) code = pair(saturate_code(code.x, s, k.outl0), saturate_code(code.y, s, k.outl1));
+      out = decode_pair<false, false>(code, k.shift, k.range_b, k.range_r, s, all_positive != 0, unused);
+    }
+    y[i] = out.x;
+    if (codes) codes[i] = code.x;
+    if (has2) {
+      y[i + 1] = out.y;
+      if (codes) codes[i + 1] = code.y;
+    }
   }
+  if (used_fast) *used_fast = fast ? (int)(1 + (redone > n / 4)) : 0;  // 2: mostly redone (degenerate input)
 }
 
 // Exhaustive-style check of the three-instruction division against the IEEE divide.
@@ -38,13 +55,17 @@ int64_t harness_div_check(const float* a, int64_t n, float b, int tiny_guard) {
   Divisor d = make_divisor(b);
   int64_t bad = 0;
   for (int64_t i = 0; i < n; ++i) {
-    float q = tiny_guard ? div_rn<true>(a[i], d) : div_rn<false>(a[i], d);
+    // the kernels' contract: div3 unless the guard fires, then the IEEE divide
+    f32x2 q2 = div3(splat(a[i]), splat(d.b), splat(d.r));
+    float q = q2.x;
+    const bool redo = tiny_guard ? not_at_least(q, 9.094947017729282e-13f) : not_at_most(a[i], 1.2676506e30f);
+    if (redo) q = true_div(a[i], d.b);
     float t = a[i] / b;
     uint32_t qb, tb;
     memcpy(&qb, &q, 4);
     memcpy(&tb, &t, 4);
     bool both_nan = (q != q) && (t != t);
-    bool both_zero = (q == 0.0f) && (t == 0.0f);  // sign of zero is handled by the caller's contract
+    bool both_zero = (q == 0.0f) && (t == 0.0f);  // the sign of a zero quotient never reaches the output (Scalars::fast)
     if (qb != tb && !both_nan && !both_zero) ++bad;
   }
   return bad;

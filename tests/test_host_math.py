@@ -45,7 +45,7 @@ def run_roundtrip(lib, x, probs, cfg, mean, std, *, all_positive=False, saturate
         f(float(mean)), f(float(std)), f(cfg.main_std_dev_threshold), f(cfg.range_normal), f(cfg.range_outlier),
         f(cfg.clamped_range[0]), f(cfg.clamped_range[1]), cfg.num_bits_main, cfg.num_bits_outlier,
         int(cfg.stochastic_rounding), int(all_positive), int(saturate), variant, C.byref(used_fast))
-    return torch.from_numpy(y), torch.from_numpy(codes), bool(used_fast.value)
+    return torch.from_numpy(y), torch.from_numpy(codes), used_fast.value == 1
 
 
 @pytest.mark.parametrize("variant", [0, 1])

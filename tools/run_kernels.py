@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Launch each kernel of the hot path a few times (for ncu): stats, fused round trip, encode, decode, FP8, S2FP8.
+
+    python tools/run_kernels.py [--log2n 28] [--reps 3] [--only encode,decode]
+"""
+import argparse
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "smart-quantization_b200")]
+import torch  # noqa: E402
+
+from bench import make_input, make_plugin  # noqa: E402
+from smart_compress import _native as N  # noqa: E402
+from smart_compress.compress.packed import packed_layout  # noqa: E402
+from smart_compress.util.pytorch.quantization import make_floatq_params  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--log2n", type=int, default=28)
+ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--only", default="stats,roundtrip,encode,decode,fp8,s2fp8")
+a = ap.parse_args()
+only = set(a.only.split(","))
+dev = torch.device("cuda:0")
+lib = N.load()
+n = 1 << a.log2n
+x = make_input(n, dev)
+y = torch.empty_like(x)
+fp = make_plugin()
+ms = fp.statistics(x)
+lay = packed_layout(n, 6, 8)
+packed = torch.empty(lay.total_capacity_bytes, dtype=torch.uint8, device=dev)
+ws = torch.empty(lay.workspace_bytes, dtype=torch.uint8, device=dev)
+sws_b = lib.smaq_stats_workspace_bytes(n)
+sws = torch.empty(sws_b, dtype=torch.uint8, device=dev)
+st = N.stream_ptr(dev)
+params = fp._params(all_positive=False)
+p8 = make_floatq_params(5, 2, fp.hparams)
+mm = torch.empty(2, dtype=torch.float32, device=dev)
+# the decoder needs a valid stream even when encode is not profiled
+lib.smaq_encode(x.data_ptr(), n, ms.data_ptr(), None, C.byref(params), packed.data_ptr(), packed.numel(), ws.data_ptr(), ws.numel(), st)
+torch.cuda.synchronize()
+for _ in range(a.reps):
+    if "stats" in only:
+        lib.smaq_stats_full(x.data_ptr(), n, 1, ms.data_ptr(), sws.data_ptr(), sws_b, st)
+    if "roundtrip" in only:
+        lib.smaq_roundtrip(x.data_ptr(), y.data_ptr(), n, ms.data_ptr(), None, C.byref(params), st)
+    if "encode" in only:
+        lib.smaq_encode(x.data_ptr(), n, ms.data_ptr(), None, C.byref(params), packed.data_ptr(), packed.numel(), ws.data_ptr(), ws.numel(), st)
+    if "decode" in only:
+        lib.smaq_decode(packed.data_ptr(), packed.numel(), n, 6, 8, 0, y.data_ptr(), st)
+    if "fp8" in only:
+        lib.smaq_float_quantize(x.data_ptr(), y.data_ptr(), n, None, C.byref(p8), st)
+    if "s2fp8" in only:
+        lib.smaq_s2fp8_stats(x.data_ptr(), n, mm.data_ptr(), sws.data_ptr(), sws_b, st)
+        lib.smaq_s2fp8_apply(x.data_ptr(), y.data_ptr(), n, mm.data_ptr(), None, C.byref(p8), st)
+torch.cuda.synchronize()
+print("ok", float(y[:16].sum()))
