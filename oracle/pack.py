@@ -18,14 +18,17 @@ so the stream holds exactly  n + pm*n + xb*n_out = bits_main*n_main + bits_outli
 
 Geometry (chosen so one warp reads its 1024 values with eight coalesced 128-bit loads and every
 lane packs its own 32 values in registers):
-    warp tile = 1024 consecutive elements; lane l (0..31) owns local element i = 4k + j
-                (k = 0..7, j = 0..3)  <->  tile element 128*k + 4*l + j
+    warp tile = 1024 consecutive elements; lane l (0..31) owns local element i = 8k + j
+                (k = 0..3, j = 0..7)  <->  tile element 256*k + 8*l + j
     planes    : per warp tile (1+pm) rows of 32 uint32, row-major [row][lane]:
                 row 0 = tag word (bit i = element i is an outlier),
                 rows 1..pm = the lane's 32 base fields concatenated LSB-first (field i at bit pm*i)
-    CTA tile  = 8 warp tiles; its outliers' ext fields are concatenated in (warp, lane, i) order,
-                LSB-first, padded to a whole uint32; table[t] = first word of CTA tile t in the
-                extras section, table[n_cta_tiles] = total words.
+    extras    : per warp tile, its outliers' ext fields concatenated in (lane, i) order, LSB-first,
+                padded to a whole uint32 (so a warp places them without a block barrier); warp-tile
+                segments follow each other in tile order.
+    CTA tile  = 8 warp tiles; table[t] = first word of CTA tile t's first segment in the extras
+                section, table[n_cta_tiles] = total words (a warp finds its own segment by adding
+                the word counts of the warps before it, which follow from the tag words).
 Elements past n (padding of the last tile) are main elements with payload 0.
 Infinite codes saturate like any other over-range code; NaN codes (NaN statistics or inputs) are
 stored as code 0; both are counted in n_saturated together with the clamped ones.
@@ -75,8 +78,8 @@ def lane_order_index(n_padded: int) -> np.ndarray:
     w = np.arange(n_padded // WARP_TILE)[:, None, None]
     l = np.arange(32)[None, :, None]
     i = np.arange(32)[None, None, :]
-    k, j = i // 4, i % 4
-    return w * WARP_TILE + 128 * k + 4 * l + j
+    k, j = i // 8, i % 8
+    return w * WARP_TILE + 256 * k + 8 * l + j
 
 
 def codes_from_result(res: SmaqResult, cfg: SmaqConfig):
@@ -124,22 +127,22 @@ def pack(res: SmaqResult, cfg: SmaqConfig) -> Packed:
     words = (bits.reshape(n_wt, 32, pm, 32).astype(np.uint64) * weights).sum(axis=3).astype(np.uint32)
     planes[:, 1:, :] = np.transpose(words, (0, 2, 1))
 
-    # extras: (cta tile, warp, lane, i) order == flattened [w, l, i] order, split per CTA tile
-    ext = (pay_l >> np.uint64(pm)).reshape(-1)
-    tflat = tag_l.reshape(-1)
-    per_cta = WARPS_PER_CTA * WARP_TILE
-    table = np.zeros(n_ct + 1, dtype=np.uint32)
+    # extras: one word-aligned segment per warp tile, fields in (lane, i) order == flattened [w, l, i]
+    ext = (pay_l >> np.uint64(pm)).reshape(n_wt, -1)
+    tflat = tag_l.reshape(n_wt, -1)
+    seg_words = np.zeros(n_ct * WARPS_PER_CTA, dtype=np.int64)
     chunks = []
-    for t in range(n_ct):
-        sl = slice(t * per_cta, min((t + 1) * per_cta, n_pad))
-        e = ext[sl][tflat[sl]]
+    for w in range(n_wt):
+        e = ext[w][tflat[w]]
         nbits = e.size * xb
         nwords = -(-nbits // 32)
+        seg_words[w] = nwords
         if nwords:
             b = ((e[:, None] >> np.arange(xb, dtype=np.uint64)) & np.uint64(1)).reshape(-1)
             b = np.concatenate([b, np.zeros(nwords * 32 - nbits, dtype=np.uint64)])
             chunks.append((b.reshape(nwords, 32) * weights).sum(axis=1).astype(np.uint32))
-        table[t + 1] = table[t] + nwords
+    table = np.zeros(n_ct + 1, dtype=np.uint32)
+    table[1:] = np.cumsum(seg_words.reshape(n_ct, WARPS_PER_CTA).sum(axis=1))
     extras = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.uint32)
     return Packed(n=n, cfg=cfg, mean=np.float32(res.mean), std_raw=np.float32(res.std), planes=planes,
                   table=table, extras=extras, n_outlier=int(outlier.sum()), n_saturated=n_sat)
@@ -160,17 +163,18 @@ def unpack_codes(p: Packed):
     base = (fields << np.arange(pm, dtype=np.uint64)).sum(axis=3)            # [w, l, i]
     ext = np.zeros(n_wt * 32 * 32, dtype=np.uint64)
     tflat = tag_l.reshape(-1)
-    per_cta = WARPS_PER_CTA * WARP_TILE
-    for t in range(len(p.table) - 1):
-        sl = slice(t * per_cta, min((t + 1) * per_cta, n_pad))
+    word = 0
+    for w in range(n_wt):
+        sl = slice(w * WARP_TILE, (w + 1) * WARP_TILE)
         k = int(tflat[sl].sum())
-        if k == 0 or xb == 0:
-            continue
-        w = p.extras[p.table[t]: p.table[t + 1]]
-        b = ((w[:, None] >> shifts) & 1).reshape(-1)[: k * xb].reshape(k, xb).astype(np.uint64)
-        vals = (b << np.arange(xb, dtype=np.uint64)).sum(axis=1)
-        idx = np.nonzero(tflat[sl])[0] + sl.start
-        ext[idx] = vals
+        nwords = -(-(k * xb) // 32)
+        if w % WARPS_PER_CTA == 0:
+            assert word == int(p.table[w // WARPS_PER_CTA]), "table does not match the tag words"
+        if k and xb:
+            seg = p.extras[word: word + nwords]
+            b = ((seg[:, None] >> shifts) & 1).reshape(-1)[: k * xb].reshape(k, xb).astype(np.uint64)
+            ext[np.nonzero(tflat[sl])[0] + sl.start] = (b << np.arange(xb, dtype=np.uint64)).sum(axis=1)
+        word += nwords
     pay_l = base.reshape(-1) | (ext << np.uint64(pm))
     perm = lane_order_index(n_pad).reshape(-1)
     pay = np.zeros(n_pad, dtype=np.uint64)

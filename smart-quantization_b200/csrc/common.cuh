@@ -31,7 +31,7 @@ int sm_count();  // cached per device, immutable once read
                           __FILE__, __LINE__);                                          \
   } while (0)
 
-inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+__host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- streaming 128-bit global accesses -------------------------------------------------------
 // Every tensor on this path is touched once per kernel: keep it out of L1.  Plain (coherent)
@@ -53,6 +53,25 @@ __device__ __forceinline__ void stg_stream(float4* p, float4 v) {
                "f"(v.z), "f"(v.w)
                : "memory");
 }
+// 256-bit accesses (sm_100): eight consecutive fp32 per lane in one instruction; needs 32-byte
+// alignment.  The load also marks the line evict-first in L2 (the qualifier exists for .v8 only).
+struct f32x8 {
+  float4 a, b;
+};
+__device__ __forceinline__ f32x8 ldg_stream8(const float* p) {
+  f32x8 v;
+  asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream8(float* p, const f32x8& v) {
+  asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v.a.x), "f"(v.a.y),
+               "f"(v.a.z), "f"(v.a.w), "f"(v.b.x), "f"(v.b.y), "f"(v.b.z), "f"(v.b.w)
+               : "memory");
+}
+__host__ __device__ inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
+
 __device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
   uint4 v;
   asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

@@ -3,21 +3,25 @@
 //
 // The reference only ever holds the code as an fp32 value (smart_compress/compress/smart.py:164-169)
 // and accounts for 6 bits per main element and 8 per outlier (smart.py:184-187).  The stream
-// written here has exactly that size (plus a 4-byte entry per 8192 elements and word alignment);
-// its layout ("SQB1") is specified in DESIGN.md and restated executable in oracle/pack.py.
+// written here has exactly that size plus a 4-byte table entry per 8192 elements and at most 31
+// padding bits per 1024 elements; its layout ("SQB1") is specified in DESIGN.md and restated
+// executable in oracle/pack.py.
 //
 // Mapping to the hardware
-//   * one warp owns 1024 consecutive elements and reads them with eight coalesced 128-bit loads
-//     (lane l takes elements 128k + 4l + j): no shared-memory staging is needed for the input;
-//   * every lane packs its own 32 codes in registers: one tag word, PM words of base fields —
-//     the fixed-position part of the stream (PM+1 bits per element), stored with coalesced
-//     32-bit row writes; no __ballot_sync transposition (6 votes per element were measured in
-//     SASS to cost more issue slots than the whole quantiser);
+//   * one warp owns 1024 consecutive elements; the tile is brought into shared memory by ONE TMA
+//     bulk copy (cp.async.bulk + mbarrier), double-buffered, so the next tile is in flight while
+//     this one is quantised — these kernels are bound by instruction issue, and without the
+//     prefetch too few bytes are in flight to keep HBM busy (profiles/);
+//   * lane l takes elements 256k + 8l + j (two 128-bit shared loads per chunk; eight elements share
+//     one Philox call) and packs its own
+//     32 codes in registers: one tag word and PM words of base fields — the fixed-position part
+//     of the stream (PM+1 bits per element), stored with coalesced 32-bit row writes.  No
+//     __ballot_sync transposition: 6 votes per element cost more issue slots than the quantiser;
 //   * the variable part — XB extra bits per OUTLIER — is compacted per lane in registers, placed
-//     inside the CTA tile by a shuffle/shared-memory prefix scan of the per-lane outlier counts
-//     (popc of the tag word), and placed in the tensor by a single-pass decoupled look-back over
-//     CTA tiles (tiles are numbered by an atomic ticket, so a tile only ever waits for tiles
-//     that are already running); the result is deterministic: byte-identical run to run;
+//     inside the warp tile by a shuffle prefix scan of the per-lane outlier counts (popc of the
+//     tag word), and placed in the tensor by a single-pass decoupled look-back over groups of CTA
+//     tiles (groups are numbered by an atomic ticket, so a group only ever waits for groups that
+//     are already running).  Placement is deterministic: the stream is byte-identical run to run;
 //   * the decoder needs no scan across tiles: the per-tile word offset is in the table.
 //
 // HBM roofline (6/8 bits, fraction f of outliers): encode reads 4 B and writes (6 + 2f)/8 B per
@@ -30,101 +34,18 @@ constexpr int kWarpTile = 1024;
 constexpr int kWarpsPerCta = 8;
 constexpr int kCtaTile = kWarpTile * kWarpsPerCta;
 constexpr int kPackThreads = 32 * kWarpsPerCta;
-constexpr int kCountSlots = 64;
 constexpr uint32_t kMagic = 0x31425153u;  // 'SQB1'
-
-struct EncodeWs {
-  unsigned int ticket;
-  unsigned int status;
-  unsigned int pad[2];
-  unsigned long long n_out[kCountSlots];
-  unsigned long long n_sat[kCountSlots];
-  unsigned long long state[1];  // [n_cta_tiles]: flag (2 bits) | exclusive/inclusive word count
-};
-
-constexpr unsigned long long kFlagA = 1ull << 62;  // tile aggregate available
-constexpr unsigned long long kFlagP = 2ull << 62;  // inclusive prefix available
-constexpr unsigned long long kValMask = (1ull << 62) - 1;
-
-__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 // groups of lane-local elements that share one 32-bit extras accumulator: XB * (32 / G) <= 32
 __host__ __device__ constexpr int ext_groups(int xb) { return xb <= 1 ? 1 : xb <= 2 ? 2 : xb <= 4 ? 4 : 8; }
-
-// Exclusive prefix over the CTA of a per-thread bit count; returns the thread's offset and the total.
-__device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t& total) {
-  uint32_t inc = warp_inclusive_scan(v);
-  if (lane_id() == 31) s_warp[warp_id()] = inc;
-  __syncthreads();
-  uint32_t before = 0, all = 0;
-#pragma unroll
-  for (int w = 0; w < kWarpsPerCta; ++w) {
-    uint32_t t = s_warp[w];
-    before += (w < warp_id()) ? t : 0u;
-    all += t;
-  }
-  total = all;
-  return before + inc - v;
-}
-
-// Decoupled look-back (Merrill & Garland) over CTA tiles, run by warp 0.  Returns the number of
-// extras words that precede this tile.  Tiles are numbered by ticket, so every predecessor is
-// resident or finished; the watchdog only exists so that a logic error cannot hang the GPU.
-__device__ __forceinline__ unsigned long long lookback_exclusive(EncodeWs* ws, long long tile,
-                                                                  unsigned long long aggregate) {
-  const int lane = lane_id();
-  if (tile == 0) {
-    if (lane == 0) st_state(&ws->state[0], kFlagP | aggregate);
-    return 0;
-  }
-  if (lane == 0) st_state(&ws->state[tile], kFlagA | aggregate);
-  unsigned long long excl = 0;
-  long long window_end = tile - 1;
-  unsigned int spins = 0;
-  bool timed_out = false;
-  while (true) {
-    const long long idx = window_end - lane;
-    unsigned long long sv = (idx >= 0) ? ld_state(&ws->state[idx]) : kFlagP;  // virtual tiles before 0: P(0)
-    while (__any_sync(0xffffffffu, (sv >> 62) == 0)) {
-      if ((sv >> 62) == 0) sv = ld_state(&ws->state[idx]);
-      if (++spins > (1u << 22)) {  // watchdog (~1 s): record the failure, unblock the successors
-        timed_out = true;
-        break;
-      }
-      __nanosleep(40);
-    }
-    if (timed_out) {
-      if (lane == 0) atomicExch(&ws->status, 1u);
-      excl = 0;
-      break;
-    }
-    const unsigned int has_p = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
-    unsigned long long val = sv & kValMask;
-    if (has_p) {
-      const int first = __ffs(has_p) - 1;  // nearest predecessor holding an inclusive prefix
-      val = (lane <= first) ? val : 0ull;
-      excl += warp_sum(val);
-      break;
-    }
-    excl += warp_sum(val);
-    window_end -= 32;
-  }
-  if (lane == 0) st_state(&ws->state[tile], kFlagP | (excl + aggregate));
-  return excl;
-}
+// 32-bit words of extras a warp tile can need
+__host__ __device__ constexpr int seg_words(int xb) { return xb == 0 ? 1 : kWarpTile * xb / 32; }
 
 template <int PM>
 __device__ __forceinline__ void put_field(uint32_t (&bw)[PM], int i, uint32_t field) {
   const int pos = PM * i, w = pos >> 5, sh = pos & 31;  // compile-time after unrolling
-  bw[w] |= field << sh;
-  if (sh + PM > 32) bw[w + 1] |= field >> (32 - sh);
+  bw[w] += field << sh;                                  // fields never overlap: add == or (one LEA)
+  if (sh + PM > 32) bw[w + 1] += field >> (32 - sh);
 }
 template <int PM>
 __device__ __forceinline__ uint32_t get_field(const uint32_t (&bw)[PM], int i) {
@@ -134,223 +55,402 @@ __device__ __forceinline__ uint32_t get_field(const uint32_t (&bw)[PM], int i) {
   return v & ((1u << PM) - 1u);
 }
 
+// What a lane accumulates for its 32 elements of one warp tile.
+template <int PM>
+struct LaneWords {
+  uint32_t tagw;      // bit i: element i is an outlier
+  uint32_t bw[PM];    // 32 base fields of PM bits
+  uint32_t ea[8];     // extras accumulators (ext_groups(XB) of them are used)
+  uint32_t ecnt[8];   // bits held by each
+  uint32_t n_sat;     // codes clipped at the field width / not a number
+};
+
 // Integer side of one element: rounded code (fp32) -> stored payload; updates the lane's words.
-//   payload = (min(|code|, limit) << 1) | s,  s = sign bit of the code (main) / lower side (outlier)
-// F2I saturates +-inf to INT_MAX/INT_MIN and maps NaN to 0, which is exactly the format's rule.
-template <int PM, int XB>
-__device__ __forceinline__ void pack_element(int i, float code, bool outl, bool lo, bool valid, const int lim_main,
-                                             const int lim_out, uint32_t& tagw, uint32_t (&bw)[PM], uint32_t (&ea)[8],
-                                             uint32_t (&ecnt)[8], uint32_t& n_sat) {
+//   payload = (min(|code|, limit) << 1) | s,  s = sign bit of the code (main) / of z (outlier: lower side)
+// Branch-free: `m` is the all-ones/zero outlier mask, `zb` the bits of z.  F2I saturates large
+// codes and maps NaN to 0, which is the format's rule; `vmask` is zero for padding elements.
+template <int PM, int XB, bool kCheckNan>
+__device__ __forceinline__ void pack_element(int i, float code, uint32_t m, uint32_t zb, uint32_t vmask,
+                                             const uint32_t lim_main, const uint32_t lim_out, LaneWords<PM>& L) {
   constexpr int EPG = 32 / ext_groups(XB);
-  const int ci = __float2int_rz(code);
-  const uint32_t a = (uint32_t)abs(ci);
-  const uint32_t lim = (uint32_t)(outl ? lim_out : lim_main);
+  const uint32_t a = (uint32_t)abs(__float2int_rz(code));
+  const uint32_t lim = (lim_out & m) | (lim_main & ~m);
   const uint32_t mag = min(a, lim);
-  const bool bad = valid && ((a > lim) || (code != code));
-  const uint32_t sbit = outl ? (lo ? 1u : 0u) : ((code != code) ? 0u : (bits_of(code) >> 31));
-  uint32_t payload = (mag << 1) | sbit;
-  if (!valid) payload = 0u;
-  n_sat += bad ? 1u : 0u;
-  if (outl) tagw |= 1u << i;
-  put_field<PM>(bw, i, payload & ((1u << PM) - 1u));
+  uint32_t cb = bits_of(code);
+  bool bad = a > lim;
+  if (kCheckNan) {  // exact path only: the fast path never sees a NaN code (it is flagged upstream)
+    const bool isnan_ = code != code;
+    bad = bad || isnan_;
+    cb = isnan_ ? 0u : cb;
+  }
+  const uint32_t sbit = ((zb & m) | (cb & ~m)) >> 31;
+  const uint32_t payload = ((mag << 1) | sbit) & vmask;
+  L.n_sat += (bad && vmask) ? 1u : 0u;
+  L.tagw |= m & vmask & (1u << i);
+  put_field<PM>(L.bw, i, payload & ((1u << PM) - 1u));
   if (XB > 0) {
     const int g = i / EPG;
-    ea[g] |= (payload >> PM) << ecnt[g];  // payload >> PM is 0 for a main element
-    if (outl) ecnt[g] += (uint32_t)XB;
+    L.ea[g] |= (payload >> PM) << L.ecnt[g];  // payload >> PM is 0 for a main element
+    L.ecnt[g] += m & vmask & (uint32_t)XB;
   }
 }
 
-// Exact (IEEE-divide) re-computation of one 4-element chunk: degenerate statistics or a flagged chunk.
+// Exact (IEEE-divide) re-computation of one 4-element chunk: degenerate statistics or a flagged
+// chunk.  Out of line; the result comes back in registers.
+struct ExactChunk {
+  float4 code;
+  uint32_t cls;  // bit j: outlier; bit 4+j: z negative
+};
 template <bool kStochastic>
-__device__ __noinline__ void encode_chunk_exact(float4 v, float4 pr, const Scalars& s, float4& code, uint32_t& cls) {
+__device__ __noinline__ ExactChunk encode_chunk_exact(float4 v, float4 pr, const Scalars& s) {
   PairClass k0, k1;
   bool unused = false;
   const f32x2 c01 = encode_pair<kStochastic, false>(pair(v.x, v.y), pair(pr.x, pr.y), s, k0, unused);
   const f32x2 c23 = encode_pair<kStochastic, false>(pair(v.z, v.w), pair(pr.z, pr.w), s, k1, unused);
-  code = make_float4(c01.x, c01.y, c23.x, c23.y);
-  cls = (k0.outl0 ? 1u : 0u) | (k0.outl1 ? 2u : 0u) | (k1.outl0 ? 4u : 0u) | (k1.outl1 ? 8u : 0u) |
-        (k0.lo0 ? 16u : 0u) | (k0.lo1 ? 32u : 0u) | (k1.lo0 ? 64u : 0u) | (k1.lo1 ? 128u : 0u);
+  ExactChunk r;
+  r.code = make_float4(c01.x, c01.y, c23.x, c23.y);
+  r.cls = (k0.m0 & 1u) | (k0.m1 & 2u) | (k1.m0 & 4u) | (k1.m1 & 8u) | ((k0.zb0 >> 31) << 4) | ((k0.zb1 >> 31) << 5) |
+          ((k1.zb0 >> 31) << 6) | ((k1.zb1 >> 31) << 7);
+  return r;
 }
 
+// One warp tile: quantise 1024 values and pack them into the lane's words.  `staged` points at the
+// tile in shared memory (TMA), or is null: direct global loads (unaligned tensors, the ragged
+// last tile).
 template <int PM, int XB, bool kStochastic, bool kHasProbs, bool kFast>
 __device__ __forceinline__ void encode_tile(const float* __restrict__ x, int64_t n, const float* __restrict__ probs,
-                                            const KernelParams& kp, const Scalars& s, bool aligned, long long tile,
-                                            uint32_t* __restrict__ planes, uint32_t& tagw_out, uint32_t (&ea)[8],
-                                            uint32_t (&ecnt)[8], uint32_t& n_sat_out) {
+                                            const KernelParams& kp, const Scalars& s, const float4* staged,
+                                            int64_t base, LaneWords<PM>& L) {
   const int lane = lane_id();
-  const int64_t wt = (int64_t)tile * kWarpsPerCta + warp_id();
-  const int64_t base = wt * kWarpTile;
-  const int lim_main = (int)s.lim_main, lim_out = (int)s.lim_out;
+  const uint32_t lim_main = (uint32_t)s.lim_main, lim_out = (uint32_t)s.lim_out;
+  L.tagw = 0;
+  L.n_sat = 0;
+#pragma unroll
+  for (int w = 0; w < PM; ++w) L.bw[w] = 0;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) { L.ea[g] = 0; L.ecnt[g] = 0; }
 
-  uint32_t tagw = 0, n_sat = 0;
-  uint32_t bw[PM];
+  const bool full = staged != nullptr;
+  const bool probs_vec = kStochastic && kHasProbs && full && aligned16(probs);
+  // lane l owns elements 256k + 8l + j of the tile (k = 0..3, j = 0..7): local index i = 8k + j
 #pragma unroll
-  for (int w = 0; w < PM; ++w) bw[w] = 0;
+  for (int k = 0; k < 4; ++k) {
+    const int64_t e = base + 256 * k + 8 * lane;
+    float4 v[2], p4[2];
 #pragma unroll
-  for (int g = 0; g < 8; ++g) { ea[g] = 0; ecnt[g] = 0; }
-
-  if (base < n) {
-    const bool full = aligned && (base + kWarpTile <= n);
-    float4 v[8], pr[8];
-    if (full) {
-      const float4* xv = reinterpret_cast<const float4*>(x + base) + lane;
-      const float4* pv = reinterpret_cast<const float4*>(probs + base) + lane;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = ldg_stream(xv + 32 * k);
+    for (int h = 0; h < 2; ++h) {
+      const int64_t eh = e + 4 * h;
+      p4[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (full) v[h] = staged[64 * k + 2 * lane + h];
+      else v[h] = make_float4(eh < n ? x[eh] : 0.f, eh + 1 < n ? x[eh + 1] : 0.f, eh + 2 < n ? x[eh + 2] : 0.f,
+                              eh + 3 < n ? x[eh + 3] : 0.f);
       if (kStochastic && kHasProbs) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) pr[k] = ldg_stream(pv + 32 * k);
+        if (probs_vec) p4[h] = ldg_stream(reinterpret_cast<const float4*>(probs + eh));
+        else p4[h] = make_float4(eh < n ? probs[eh] : 0.f, eh + 1 < n ? probs[eh + 1] : 0.f,
+                                 eh + 2 < n ? probs[eh + 2] : 0.f, eh + 3 < n ? probs[eh + 3] : 0.f);
+      }
+    }
+    if (kStochastic && !kHasProbs) {
+      const uint4 r = philox_group(kp.keys, (uint64_t)(e >> 3), kp.offset);
+      const f32x2 q0 = uniform16_pair(r.x), q1 = uniform16_pair(r.y), q2 = uniform16_pair(r.z), q3 = uniform16_pair(r.w);
+      p4[0] = make_float4(q0.x, q0.y, q1.x, q1.y);
+      p4[1] = make_float4(q2.x, q2.y, q3.x, q3.y);
+    }
+    bool suspect = false;
+    if (kFast && full) {
+      PairClass k0, k1, k2, k3;
+      const f32x2 c0 = encode_pair<kStochastic, true>(pair(v[0].x, v[0].y), pair(p4[0].x, p4[0].y), s, k0, suspect);
+      const f32x2 c1 = encode_pair<kStochastic, true>(pair(v[0].z, v[0].w), pair(p4[0].z, p4[0].w), s, k1, suspect);
+      const f32x2 c2 = encode_pair<kStochastic, true>(pair(v[1].x, v[1].y), pair(p4[1].x, p4[1].y), s, k2, suspect);
+      const f32x2 c3 = encode_pair<kStochastic, true>(pair(v[1].z, v[1].w), pair(p4[1].z, p4[1].w), s, k3, suspect);
+      if (!suspect) {  // the hot path: branch-free packing of eight elements
+        pack_element<PM, XB, false>(8 * k + 0, c0.x, k0.m0, k0.zb0, 0xFFFFFFFFu, lim_main, lim_out, L);
+        pack_element<PM, XB, false>(8 * k + 1, c0.y, k0.m1, k0.zb1, 0xFFFFFFFFu, lim_main, lim_out, L);
+        pack_element<PM, XB, false>(8 * k + 2, c1.x, k1.m0, k1.zb0, 0xFFFFFFFFu, lim_main, lim_out, L);
+        pack_element<PM, XB, false>(8 * k + 3, c1.y, k1.m1, k1.zb1, 0xFFFFFFFFu, lim_main, lim_out, L);
+        pack_element<PM, XB, false>(8 * k + 4, c2.x, k2.m0, k2.zb0, 0xFFFFFFFFu, lim_main, lim_out, L);
+        pack_element<PM, XB, false>(8 * k + 5, c2.y, k2.m1, k2.zb1, 0xFFFFFFFFu, lim_main, lim_out, L);
+        pack_element<PM, XB, false>(8 * k + 6, c3.x, k3.m0, k3.zb0, 0xFFFFFFFFu, lim_main, lim_out, L);
+        pack_element<PM, XB, false>(8 * k + 7, c3.y, k3.m1, k3.zb1, 0xFFFFFFFFu, lim_main, lim_out, L);
       }
     } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int64_t e = base + 128 * k + 4 * lane;
-        v[k] = make_float4(e < n ? x[e] : 0.f, e + 1 < n ? x[e + 1] : 0.f, e + 2 < n ? x[e + 2] : 0.f,
-                           e + 3 < n ? x[e + 3] : 0.f);
-        if (kStochastic && kHasProbs)
-          pr[k] = make_float4(e < n ? probs[e] : 0.f, e + 1 < n ? probs[e + 1] : 0.f, e + 2 < n ? probs[e + 2] : 0.f,
-                              e + 3 < n ? probs[e + 3] : 0.f);
-      }
+      suspect = true;
     }
+    if (suspect) {  // rare: flagged chunk, degenerate statistics, or the ragged last tile
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kStochastic) {
-        if (kHasProbs) p4 = pr[k];
-        else {
-          const uint4 r = philox_group(kp.keys, (uint64_t)((base >> 2) + 32 * k + lane), kp.offset);
-          const f32x2 a = uniform24_pair(r.x, r.y), b = uniform24_pair(r.z, r.w);
-          p4 = make_float4(a.x, a.y, b.x, b.y);
+      for (int h = 0; h < 2; ++h) {
+        const ExactChunk ex = encode_chunk_exact<kStochastic>(v[h], p4[h], s);
+        const float cj[4] = {ex.code.x, ex.code.y, ex.code.z, ex.code.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t vmask = (full || (e + 4 * h + j) < n) ? 0xFFFFFFFFu : 0u;
+          const uint32_t m = ((ex.cls >> j) & 1u) ? 0xFFFFFFFFu : 0u;
+          const uint32_t zb = ((ex.cls >> (4 + j)) & 1u) << 31;
+          pack_element<PM, XB, true>(8 * k + 4 * h + j, cj[j], m, zb, vmask, lim_main, lim_out, L);
         }
       }
-      float4 code;
-      uint32_t cls;
-      bool suspect = !kFast;
-      if (kFast) {
-        PairClass k0, k1;
-        const f32x2 c01 = encode_pair<kStochastic, true>(pair(v[k].x, v[k].y), pair(p4.x, p4.y), s, k0, suspect);
-        const f32x2 c23 = encode_pair<kStochastic, true>(pair(v[k].z, v[k].w), pair(p4.z, p4.w), s, k1, suspect);
-        code = make_float4(c01.x, c01.y, c23.x, c23.y);
-        cls = (k0.outl0 ? 1u : 0u) | (k0.outl1 ? 2u : 0u) | (k1.outl0 ? 4u : 0u) | (k1.outl1 ? 8u : 0u) |
-              (k0.lo0 ? 16u : 0u) | (k0.lo1 ? 32u : 0u) | (k1.lo0 ? 64u : 0u) | (k1.lo1 ? 128u : 0u);
-      }
-      if (suspect) encode_chunk_exact<kStochastic>(v[k], p4, s, code, cls);
-      const float cj[4] = {code.x, code.y, code.z, code.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool valid = full || (base + 128 * k + 4 * lane + j) < n;
-        const bool outl = ((cls >> j) & 1u) && valid;
-        pack_element<PM, XB>(4 * k + j, cj[j], outl, (cls >> (4 + j)) & 1u, valid, lim_main, lim_out, tagw, bw, ea,
-                             ecnt, n_sat);
-      }
     }
-    // fixed-position part of the stream: (1 + PM) rows of 32 words per warp tile, coalesced
-    uint32_t* rec = planes + wt * (int64_t)((1 + PM) * 32) + lane;
-    rec[0] = tagw;
-#pragma unroll
-    for (int w = 0; w < PM; ++w) rec[32 * (w + 1)] = bw[w];
   }
-  tagw_out = tagw;
-  n_sat_out = n_sat;
 }
 
+// ---- TMA bulk copy of one warp tile (4 KB, contiguous) into shared memory ----------------------
+// One lane issues cp.async.bulk; every lane of the warp waits on the warp's mbarrier.  The copy
+// is linear, so lane l finds its chunk k at float4 index 32k + l — the same coalesced mapping a
+// direct 128-bit load would use.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_tile(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+constexpr int kMaxRounds = 4;  // CTA tiles per CTA ("group")
+constexpr int kStages = 2;
+constexpr int kStageBytes = kWarpTile * 4;                                  // 4 KB per warp tile
+constexpr int kEncodeDynSmem = kWarpsPerCta * kStages * kStageBytes + 1024;  // + alignment slack
+
+// Scratch of one encode call (device).  Placement of the variable-length part is
+// reduce-then-scan: pass 1 (the expensive one, one read of x) quantises, writes the fixed part of
+// the stream and parks every warp tile's extras segment at a fixed stride; pass 2 scans the
+// per-group word counts (one small block); pass 3 moves the segments to their dense positions.
+// No kernel ever waits on another block, so nothing here can hang, and the placement is a pure
+// function of the input: the stream is byte-identical run to run.  (A single-pass decoupled
+// look-back was measured first: with ~450 groups resident, each group's look-back walk under full
+// HBM load cost ~10x its own compute time — profiles/r1_encode_lookback.txt.)
+struct EncodeScratch {
+  uint32_t* group_words;  // [n_groups] extras words of each group
+  uint32_t* group_nout;   // [n_groups] outliers
+  uint32_t* group_nsat;   // [n_groups] clipped / NaN codes
+  uint32_t* group_off;    // [n_groups] exclusive prefix of group_words (pass 2)
+  uint32_t* seg_words;    // [n_warp_tiles] words of each warp tile's segment
+  uint32_t* staging;      // [n_warp_tiles][seg_words(XB)] parked segments
+};
+
+// Pass 1.  One CTA = one group of `rounds` consecutive CTA tiles (8 warp tiles each); each warp
+// runs through its `rounds` warp tiles on its own: while it quantises tile r out of shared
+// memory, TMA is already filling the other stage with tile r+1.  No block barrier in the loop.
 template <int PM, int XB, bool kStochastic, bool kHasProbs>
-__global__ void __launch_bounds__(kPackThreads, 2)
+__global__ void __launch_bounds__(kPackThreads, 3)
     encode_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ mean_std,
                   const float* __restrict__ probs, const __grid_constant__ KernelParams kp,
-                  smaq_packed_header* __restrict__ hdr,
-                  uint32_t* __restrict__ table, uint32_t* __restrict__ planes, uint32_t* __restrict__ extras,
-                  EncodeWs* ws, long long n_cta_tiles, int aligned) {
+                  uint32_t* __restrict__ planes, EncodeScratch sc, long long n_cta_tiles, int rounds, int aligned) {
   constexpr int G = ext_groups(XB);
-  constexpr int kExtWords = kCtaTile * XB / 32 + 2;
-  __shared__ uint32_t s_ext[kExtWords];
-  __shared__ uint32_t s_warp[kWarpsPerCta];
-  __shared__ unsigned long long s_off;
-  __shared__ unsigned int s_tile;
+  constexpr int kSeg = seg_words(XB);
+  extern __shared__ unsigned char dyn_smem[];
+  __shared__ uint32_t s_seg[kWarpsPerCta][kSeg + 1];  // +1: spill word of the last atomicOr
+  __shared__ uint32_t s_tot[3][kWarpsPerCta];
+  __shared__ __align__(8) uint64_t s_bar[kWarpsPerCta][kStages];
 
-  if (threadIdx.x == 0) s_tile = atomicAdd(&ws->ticket, 1u);
-  for (int i = threadIdx.x; i < kExtWords; i += kPackThreads) s_ext[i] = 0;
-  __syncthreads();
-  const long long tile = s_tile;
+  const int lane = lane_id(), warp = warp_id();
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < kStages; ++st) mbar_init(&s_bar[warp][st], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  const long long group = blockIdx.x;
+  const long long first_tile = group * rounds;
+  const int nrounds = (int)min((long long)rounds, n_cta_tiles - first_tile);
+
+  // this warp's two 4 KB stages (1 KB aligned)
+  unsigned char* stage_base =
+      (unsigned char*)(((uintptr_t)dyn_smem + 1023) & ~(uintptr_t)1023) + (size_t)warp * kStages * kStageBytes;
 
   const Scalars s = scalars_from(mean_std[0], mean_std[1], kp);
-  uint32_t tagw, n_sat, ea[8], ecnt[8];
-  if (s.fast)
-    encode_tile<PM, XB, kStochastic, kHasProbs, true>(x, n, probs, kp, s, aligned != 0, tile, planes, tagw, ea, ecnt, n_sat);
-  else
-    encode_tile<PM, XB, kStochastic, kHasProbs, false>(x, n, probs, kp, s, aligned != 0, tile, planes, tagw, ea, ecnt, n_sat);
+  auto tile_base = [&](int r) { return ((int64_t)(first_tile + r) * kWarpsPerCta + warp) * kWarpTile; };
+  // a warp tile is staged through TMA when it lies wholly inside the tensor and x is 16-byte aligned
+  auto tile_is_full = [&](int r) { return aligned && (tile_base(r) + kWarpTile <= n); };
+  auto issue = [&](int r) {
+    if (lane == 0 && tile_is_full(r))
+      tma_load_tile(stage_base + (r % kStages) * kStageBytes, x + tile_base(r), kStageBytes, &s_bar[warp][r % kStages]);
+  };
 
-  // place the lane's extras inside the CTA tile
-  const uint32_t n_out = __popc(tagw);
-  uint32_t total_bits;
-  uint32_t pos = cta_exclusive_scan(n_out * XB, s_warp, total_bits);
-  if (XB > 0) {
+  issue(0);
+  uint32_t n_out_total = 0, n_sat_total = 0, words_total = 0;
+  uint32_t* seg = s_seg[warp];
+  for (int r = 0; r < nrounds; ++r) {
+    if (r + 1 < nrounds) issue(r + 1);  // stage (r+1)%2 was fully consumed in round r-1 (__syncwarp below)
+    const int64_t base = tile_base(r);
+    if (base >= n) break;  // warp tiles past the end of the tensor: nothing stored (uniform per warp)
+    const int64_t wt = base / kWarpTile;
+    const float4* staged = nullptr;
+    if (tile_is_full(r)) {
+      mbar_wait(&s_bar[warp][r % kStages], (uint32_t)((r / kStages) & 1));
+      staged = reinterpret_cast<const float4*>(stage_base + (r % kStages) * kStageBytes);
+    }
+    if (XB > 0) {
+      for (int j = lane; j < kSeg + 1; j += 32) seg[j] = 0;
+    }
+    LaneWords<PM> L;
+    if (s.fast) encode_tile<PM, XB, kStochastic, kHasProbs, true>(x, n, probs, kp, s, staged, base, L);
+    else encode_tile<PM, XB, kStochastic, kHasProbs, false>(x, n, probs, kp, s, staged, base, L);
+    __syncwarp();  // stage fully read (lane 0 may refill it); segment zeroing visible to the whole warp
+
+    // fixed-position part of the stream: (1 + PM) rows of 32 words per warp tile, coalesced
+    uint32_t* rec = planes + wt * (int64_t)((1 + PM) * 32) + lane;
+    rec[0] = L.tagw;
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      if (ecnt[g]) {
-        const uint32_t w = pos >> 5, sh = pos & 31;
-        atomicOr(&s_ext[w], ea[g] << sh);
-        if (sh + ecnt[g] > 32) atomicOr(&s_ext[w + 1], ea[g] >> (32 - sh));
-        pos += ecnt[g];
+    for (int w = 0; w < PM; ++w) rec[32 * (w + 1)] = L.bw[w];
+
+    // variable part: the lane's extras go into this warp tile's word-aligned segment
+    const uint32_t n_out = __popc(L.tagw);
+    n_out_total += n_out;
+    n_sat_total += L.n_sat;
+    if (XB > 0) {
+      const uint32_t inc = warp_inclusive_scan(n_out * XB);
+      uint32_t pos = inc - n_out * XB;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (L.ecnt[g]) {
+          const uint32_t w = pos >> 5, sh = pos & 31;
+          atomicOr(&seg[w], L.ea[g] << sh);
+          if (sh + L.ecnt[g] > 32) atomicOr(&seg[w + 1], L.ea[g] >> (32 - sh));
+          pos += L.ecnt[g];
+        }
       }
+      const uint32_t nwords = (__shfl_sync(0xffffffffu, inc, 31) + 31) >> 5;
+      __syncwarp();
+      uint32_t* park = sc.staging + wt * (int64_t)kSeg;
+      for (uint32_t j = lane; j < nwords; j += 32) park[j] = seg[j];
+      if (lane == 0) sc.seg_words[wt] = nwords;
+      words_total += nwords;
+      __syncwarp();  // the copy is done before the next round zeroes the segment
     }
   }
-  const uint32_t words = (total_bits + 31) >> 5;
 
-  // counts, spread over slots (the last tile sums them): before this tile publishes anything
-  const uint32_t w_out = warp_sum(n_out), w_sat = warp_sum(n_sat);
-  if (lane_id() == 0) {
-    const int slot = (int)((tile * kWarpsPerCta + warp_id()) % kCountSlots);
-    if (w_out) atomicAdd(&ws->n_out[slot], (unsigned long long)w_out);
-    if (w_sat) atomicAdd(&ws->n_sat[slot], (unsigned long long)w_sat);
-    __threadfence();
+  // per-group totals (plain stores: no atomics, no pre-zeroed memory)
+  const uint32_t w_out = warp_sum(n_out_total), w_sat = warp_sum(n_sat_total);
+  if (lane == 0) {
+    s_tot[0][warp] = words_total;
+    s_tot[1][warp] = w_out;
+    s_tot[2][warp] = w_sat;
   }
   __syncthreads();
-
-  if (warp_id() == 0) {
-    unsigned long long excl = lookback_exclusive(ws, tile, words);
-    if (lane_id() == 0) s_off = excl;
-  }
-  __syncthreads();
-  const unsigned long long off = s_off;
-  for (uint32_t i = threadIdx.x; i < words; i += kPackThreads) extras[off + i] = s_ext[i];
-
-  if (threadIdx.x == 0) {
-    table[tile] = (uint32_t)off;
-    if (tile == 0) {
-      hdr->magic = kMagic;
-      hdr->bits_main = kp.bits_main;
-      hdr->bits_outlier = kp.bits_outlier;
-      hdr->stochastic = kStochastic ? 1 : 0;
-      hdr->n = n;
-      hdr->mean = mean_std[0];
-      hdr->std_raw = mean_std[1];
-      hdr->threshold = kp.thr;
-      hdr->range_main = kp.range_main;
-      hdr->range_outlier = kp.range_out;
-      hdr->clamp_lo = kp.clamp_lo;
-      hdr->clamp_hi = kp.clamp_hi;
-      hdr->pad0 = 0.0f;
-    }
-    if (tile == n_cta_tiles - 1) {
-      // every other tile added its counts (and fenced) before publishing the state this tile waited on
-      __threadfence();
-      unsigned long long a = 0, b = 0;
-      for (int i = 0; i < kCountSlots; ++i) {
-        a += ld_state(&ws->n_out[i]);
-        b += ld_state(&ws->n_sat[i]);
-      }
-      hdr->n_outlier = a;
-      hdr->n_saturated = b;
-      hdr->extras_words = off + words;
-      hdr->status = atomicAdd(&ws->status, 0u);
-      table[n_cta_tiles] = (uint32_t)(off + words);
-    }
+  if (threadIdx.x < 3) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerCta; ++w) t += s_tot[threadIdx.x][w];
+    uint32_t* dst = threadIdx.x == 0 ? sc.group_words : threadIdx.x == 1 ? sc.group_nout : sc.group_nsat;
+    dst[group] = t;
   }
 }
 
+// Pass 2: one block scans the per-group word counts and finishes the header.
+__global__ void __launch_bounds__(1024) encode_scan_kernel(EncodeScratch sc, long long n_groups, long long n_cta_tiles,
+                                                           smaq_packed_header* __restrict__ hdr,
+                                                           uint32_t* __restrict__ table,
+                                                           const float* __restrict__ mean_std,
+                                                           const __grid_constant__ KernelParams kp, int64_t n,
+                                                           int stochastic) {
+  __shared__ unsigned long long s_w[32], s_o[32], s_s[32];
+  __shared__ unsigned long long s_carry[3];
+  const int lane = lane_id(), warp = warp_id();
+  if (threadIdx.x < 3) s_carry[threadIdx.x] = 0;
+  __syncthreads();
+  for (long long base = 0; base < n_groups; base += 1024) {
+    const long long g = base + threadIdx.x;
+    const unsigned long long w = g < n_groups ? sc.group_words[g] : 0ull;
+    const unsigned long long o = g < n_groups ? sc.group_nout[g] : 0ull;
+    const unsigned long long sa = g < n_groups ? sc.group_nsat[g] : 0ull;
+    // inclusive scan of w inside the warp; plain sums of o and sa
+    unsigned long long inc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    const unsigned long long so = warp_sum(o), ss = warp_sum(sa);
+    if (lane == 31) s_w[warp] = inc;
+    if (lane == 0) { s_o[warp] = so; s_s[warp] = ss; }
+    __syncthreads();
+    unsigned long long before = s_carry[0];
+    for (int i = 0; i < warp; ++i) before += s_w[i];
+    if (g < n_groups) sc.group_off[g] = (uint32_t)(before + inc - w);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long tw = 0, to = 0, ts = 0;
+      for (int i = 0; i < 32; ++i) { tw += s_w[i]; to += s_o[i]; ts += s_s[i]; }
+      s_carry[0] += tw; s_carry[1] += to; s_carry[2] += ts;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    hdr->magic = kMagic;
+    hdr->bits_main = kp.bits_main;
+    hdr->bits_outlier = kp.bits_outlier;
+    hdr->stochastic = stochastic;
+    hdr->n = n;
+    hdr->mean = mean_std[0];
+    hdr->std_raw = mean_std[1];
+    hdr->threshold = kp.thr;
+    hdr->range_main = kp.range_main;
+    hdr->range_outlier = kp.range_out;
+    hdr->clamp_lo = kp.clamp_lo;
+    hdr->clamp_hi = kp.clamp_hi;
+    hdr->pad0 = 0.0f;
+    hdr->n_outlier = s_carry[1];
+    hdr->n_saturated = s_carry[2];
+    hdr->extras_words = s_carry[0];
+    hdr->status = 0;
+    table[n_cta_tiles] = (uint32_t)s_carry[0];
+  }
+}
+
+// Pass 3: move every parked segment to its dense position and write the per-CTA-tile table.
+template <int XB>
+__global__ void __launch_bounds__(kPackThreads) encode_place_kernel(EncodeScratch sc, uint32_t* __restrict__ table,
+                                                                    uint32_t* __restrict__ extras,
+                                                                    long long n_cta_tiles, long long n_warp_tiles,
+                                                                    int rounds) {
+  constexpr int kSeg = seg_words(XB);
+  __shared__ uint32_t s_off[kMaxRounds * kWarpsPerCta + 1];
+  const int lane = lane_id(), warp = warp_id();
+  const long long group = blockIdx.x;
+  const long long first_wt = group * rounds * kWarpsPerCta;
+  const int nseg = rounds * kWarpsPerCta;  // <= 32
+  if (warp == 0) {
+    const long long wt = first_wt + lane;
+    const uint32_t wds = (lane < nseg && wt < n_warp_tiles) ? sc.seg_words[wt] : 0u;
+    const uint32_t inc = warp_inclusive_scan(wds);
+    s_off[lane] = sc.group_off[group] + inc - wds;
+    if (lane == 31) s_off[32] = sc.group_off[group] + inc;
+  }
+  __syncthreads();
+  for (int i = warp; i < nseg; i += kWarpsPerCta) {
+    const long long wt = first_wt + i;
+    if (wt >= n_warp_tiles) break;
+    const uint32_t off = s_off[i], cnt = s_off[i + 1] - off;
+    const uint32_t* src = sc.staging + wt * (int64_t)kSeg;
+    for (uint32_t j = lane; j < cnt; j += 32) extras[(size_t)off + j] = src[j];
+  }
+  if ((int)threadIdx.x < rounds) {
+    const long long tile = group * rounds + threadIdx.x;
+    if (tile < n_cta_tiles) table[tile] = s_off[threadIdx.x * kWarpsPerCta];
+  }
+}
+
+// ---- decoder ----------------------------------------------------------------------------------------
 template <int PM, int XB, bool kFast, bool kAllPos>
-__device__ __forceinline__ void decode_tile(const uint32_t* __restrict__ s_ext, uint32_t pos, uint32_t tagw,
+__device__ __forceinline__ void decode_tile(const uint32_t* __restrict__ seg, uint32_t pos, uint32_t tagw,
                                             const uint32_t (&bw)[PM], const Scalars& s, float* __restrict__ y,
                                             int64_t n, int64_t base, bool aligned) {
   constexpr int G = ext_groups(XB);
@@ -363,63 +463,67 @@ __device__ __forceinline__ void decode_tile(const uint32_t* __restrict__ s_ext, 
       const uint32_t gmask = (EPG == 32) ? 0xffffffffu : (((1u << EPG) - 1u) << (g * EPG));
       const uint32_t cnt = __popc(tagw & gmask) * XB;
       const uint32_t w = pos >> 5, sh = pos & 31;
-      win[g] = __funnelshift_r(s_ext[w], s_ext[w + 1], sh);
+      win[g] = __funnelshift_r(seg[w], seg[w + 1], sh);
       pos += cnt;
     }
   }
+  const uint32_t tb = bits_of(s.thr);
   const bool full = aligned && (base + kWarpTile <= n);
+  // lane l owns elements 256k + 8l + j of the tile (k = 0..3, j = 0..7): local index i = 8k + j
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    float code[4], shift[4], rb[4], rr[4];
+  for (int k = 0; k < 4; ++k) {
+    float out[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = 4 * k + j;
-      const bool outl = (tagw >> i) & 1u;
-      uint32_t payload = get_field<PM>(bw, i);
-      if (XB > 0) {
-        const int g = i / EPG;
-        const uint32_t e = win[g] & ((1u << XB) - 1u);
-        if (outl) {
-          payload |= e << PM;
-          win[g] >>= XB;
+    for (int h = 0; h < 4; ++h) {  // four packed pairs
+      float code[2], shift[2], rb[2], rr[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int i = 8 * k + 2 * h + q;
+        const uint32_t m = 0u - ((tagw >> i) & 1u);  // outlier mask
+        uint32_t payload = get_field<PM>(bw, i);
+        if (XB > 0) {
+          const int g = i / EPG;
+          payload |= ((win[g] & ((1u << XB) - 1u)) << PM) & m;
+          win[g] >>= (m & (uint32_t)XB);
         }
+        const uint32_t sb = payload << 31;  // s bit moved to the sign position
+        const float mag = (float)(payload >> 1);
+        code[q] = from_bits(bits_of(mag) | sb);               // -0.0 when s and mag == 0
+        shift[q] = from_bits(((sb ^ 0x80000000u) | tb) & m);  // -t above, +t below, +0 inside
+        rb[q] = select_f(m, s.range_out.b, s.range_main.b);
+        rr[q] = select_f(m, s.range_out.r, s.range_main.r);
       }
-      const uint32_t sbit = payload & 1u;
-      const float mag = (float)(payload >> 1);
-      code[j] = __uint_as_float(__float_as_uint(mag) | (sbit << 31));  // -0.0 when s and mag == 0
-      shift[j] = outl ? (sbit ? s.shift_lo : s.shift_hi) : s.shift_mid;
-      rb[j] = outl ? s.range_out.b : s.range_main.b;
-      rr[j] = outl ? s.range_out.r : s.range_main.r;
+      bool unused = false;
+      const f32x2 yv = decode_pair<kFast, false>(pair(code[0], code[1]), pair(shift[0], shift[1]), pair(rb[0], rb[1]),
+                                                 pair(rr[0], rr[1]), s, kAllPos, unused);
+      out[2 * h] = yv.x;
+      out[2 * h + 1] = yv.y;
     }
-    bool unused = false;
-    const f32x2 y01 = decode_pair<kFast, false>(pair(code[0], code[1]), pair(shift[0], shift[1]), pair(rb[0], rb[1]),
-                                                pair(rr[0], rr[1]), s, kAllPos, unused);
-    const f32x2 y23 = decode_pair<kFast, false>(pair(code[2], code[3]), pair(shift[2], shift[3]), pair(rb[2], rb[3]),
-                                                pair(rr[2], rr[3]), s, kAllPos, unused);
+    const int64_t e = base + 256 * k + 8 * lane;
     if (full) {
-      stg_stream(reinterpret_cast<float4*>(y + base) + 32 * k + lane, make_float4(y01.x, y01.y, y23.x, y23.y));
+      f32x8 o;
+      o.a = make_float4(out[0], out[1], out[2], out[3]);
+      o.b = make_float4(out[4], out[5], out[6], out[7]);
+      stg_stream8(y + e, o);
     } else {
-      const float o[4] = {y01.x, y01.y, y23.x, y23.y};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int64_t e = base + 128 * k + 4 * lane + j;
-        if (e < n) y[e] = o[j];
-      }
+      for (int j = 0; j < 8; ++j)
+        if (e + j < n) y[e + j] = out[j];
     }
   }
 }
 
 template <int PM, int XB>
-__global__ void __launch_bounds__(kPackThreads, 2)
+__global__ void __launch_bounds__(kPackThreads, 4)
     decode_kernel(const smaq_packed_header* __restrict__ hdr, const uint32_t* __restrict__ table,
                   const uint32_t* __restrict__ planes, const uint32_t* __restrict__ extras, float* __restrict__ y,
                   int64_t n, int all_positive, int aligned) {
-  constexpr int kExtWords = kCtaTile * XB / 32 + 2;
-  __shared__ uint32_t s_ext[kExtWords];
+  constexpr int kSeg = seg_words(XB);
+  __shared__ uint32_t s_seg[kWarpsPerCta][kSeg + 2];
   __shared__ uint32_t s_warp[kWarpsPerCta];
   const long long tile = blockIdx.x;
-  const int lane = lane_id();
-  const int64_t wt = (int64_t)tile * kWarpsPerCta + warp_id();
+  const int lane = lane_id(), warp = warp_id();
+  const int64_t wt = (int64_t)tile * kWarpsPerCta + warp;
   const int64_t base = wt * kWarpTile;
 
   const Scalars s = make_scalars(hdr->mean, hdr->std_raw, hdr->threshold, hdr->range_main, hdr->range_outlier,
@@ -433,20 +537,26 @@ __global__ void __launch_bounds__(kPackThreads, 2)
 #pragma unroll
     for (int w = 0; w < PM; ++w) bw[w] = rec[32 * (w + 1)];
   }
-  uint32_t total_bits;
-  const uint32_t pos = cta_exclusive_scan(__popc(tagw) * XB, s_warp, total_bits);
-  const uint32_t words = (total_bits + 31) >> 5;
-  const uint32_t off = table[tile];
-  for (uint32_t i = threadIdx.x; i < words; i += kPackThreads) s_ext[i] = extras[(size_t)off + i];
-  if (threadIdx.x < 2) s_ext[words + threadIdx.x] = 0;
+  // lane offsets inside the warp tile's segment; the segment's place inside the CTA tile
+  const uint32_t nb = __popc(tagw) * XB;
+  const uint32_t inc = warp_inclusive_scan(nb);
+  const uint32_t my_words = (__shfl_sync(0xffffffffu, inc, 31) + 31) >> 5;
+  if (lane == 0) s_warp[warp] = my_words;
   __syncthreads();
+  uint32_t seg_off = table[tile];
+#pragma unroll
+  for (int w = 0; w < kWarpsPerCta; ++w) seg_off += (w < warp) ? s_warp[w] : 0u;
+  for (uint32_t i = lane; i < my_words; i += 32) s_seg[warp][i] = extras[(size_t)seg_off + i];
+  if (lane < 2) s_seg[warp][my_words + lane] = 0;
+  __syncwarp();
   if (base >= n) return;
+  const uint32_t pos = inc - nb;
   if (s.fast) {
-    if (all_positive) decode_tile<PM, XB, true, true>(s_ext, pos, tagw, bw, s, y, n, base, aligned != 0);
-    else decode_tile<PM, XB, true, false>(s_ext, pos, tagw, bw, s, y, n, base, aligned != 0);
+    if (all_positive) decode_tile<PM, XB, true, true>(s_seg[warp], pos, tagw, bw, s, y, n, base, aligned != 0);
+    else decode_tile<PM, XB, true, false>(s_seg[warp], pos, tagw, bw, s, y, n, base, aligned != 0);
   } else {
-    if (all_positive) decode_tile<PM, XB, false, true>(s_ext, pos, tagw, bw, s, y, n, base, aligned != 0);
-    else decode_tile<PM, XB, false, false>(s_ext, pos, tagw, bw, s, y, n, base, aligned != 0);
+    if (all_positive) decode_tile<PM, XB, false, true>(s_seg[warp], pos, tagw, bw, s, y, n, base, aligned != 0);
+    else decode_tile<PM, XB, false, false>(s_seg[warp], pos, tagw, bw, s, y, n, base, aligned != 0);
   }
 }
 
@@ -458,6 +568,14 @@ static bool width_supported(int bits_main, int bits_outlier) {
   return pm == 5 && xb == 2;
 #endif
   return pm >= 3 && pm <= 7 && xb >= 0 && xb <= 4;
+}
+
+static int rounds_for(int64_t n_cta_tiles) {
+  // CTA tiles per CTA: enough groups for >= 4 waves over 3 resident CTAs per SM, at most kMaxRounds
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  int64_t r = n_cta_tiles / ((int64_t)sms * 3 * 4);
+  return (int)(r < 1 ? 1 : (r > kMaxRounds ? kMaxRounds : r));
 }
 
 }  // namespace smaq
@@ -486,9 +604,10 @@ int smaq_packed_layout_for(int64_t n, int32_t bits_main, int32_t bits_outlier, s
   l.planes_off = l.table_off + l.table_bytes;
   l.planes_bytes = l.n_warp_tiles * (int64_t)(1 + pm) * 128;
   l.extras_off = l.planes_off + l.planes_bytes;
-  l.extras_capacity_bytes = align_up(l.n_cta_tiles * (int64_t)(kCtaTile * xb / 32) * 4 + 4, 128);
+  l.extras_capacity_bytes = align_up(l.n_warp_tiles * (int64_t)(kWarpTile * xb / 32) * 4 + 4, 128);
   l.total_capacity_bytes = l.extras_off + l.extras_capacity_bytes;
-  l.workspace_bytes = align_up((int64_t)sizeof(EncodeWs) + l.n_cta_tiles * 8, 128);
+  // scratch: 4 uint32 per group (at most one group per CTA tile) + 1 per warp tile + the parked segments
+  l.workspace_bytes = align_up(l.n_cta_tiles * 16 + l.n_warp_tiles * 4, 256) + l.n_warp_tiles * (int64_t)seg_words(xb) * 4 + 256;
   *out = l;
   return SMAQ_OK;
 }
@@ -505,27 +624,46 @@ int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* p
   if (ws_bytes < (size_t)l.workspace_bytes) return fail(SMAQ_ERR_WORKSPACE, "encode: workspace too small");
   if (!aligned16(packed)) return fail(SMAQ_ERR_ARG, "encode: packed buffer must be 16-byte aligned");
   cudaStream_t stream = (cudaStream_t)stream_;
-  SMAQ_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)l.workspace_bytes, stream));
+  const int rounds = rounds_for(l.n_cta_tiles);
+  const long long n_groups = (l.n_cta_tiles + rounds - 1) / rounds;
   char* pb = (char*)packed;
   auto* hdr = (smaq_packed_header*)(pb + l.header_off);
   auto* table = (uint32_t*)(pb + l.table_off);
   auto* planes = (uint32_t*)(pb + l.planes_off);
   auto* extras = (uint32_t*)(pb + l.extras_off);
-  KernelParams kp = to_kernel_params(*params);
-  const int aligned = aligned16(x) && (!probs || aligned16(probs));
+  const KernelParams kp = to_kernel_params(*params);
+  const int aligned = aligned16(x);
   const int pm = params->bits_main - 1, xb = params->bits_outlier - params->bits_main;
-  const unsigned grid = (unsigned)l.n_cta_tiles;
   const bool st = params->stochastic != 0;
   const bool hp = st && probs != nullptr;
+  const unsigned grid = (unsigned)n_groups;
+  EncodeScratch sc;
+  {
+    uint32_t* w = (uint32_t*)ws;
+    sc.group_words = w;
+    sc.group_nout = w + l.n_cta_tiles;
+    sc.group_nsat = w + 2 * l.n_cta_tiles;
+    sc.group_off = w + 3 * l.n_cta_tiles;
+    sc.seg_words = w + 4 * l.n_cta_tiles;
+    sc.staging = (uint32_t*)((char*)ws + align_up(l.n_cta_tiles * 16 + l.n_warp_tiles * 4, 256));
+  }
 
+#define SMAQ_ENC_LAUNCH(PM_, XB_, ST_, HP_)                                                                        \
+  {                                                                                                                \
+    auto kern = encode_kernel<PM_, XB_, ST_, HP_>;                                                                 \
+    SMAQ_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncodeDynSmem));         \
+    kern<<<grid, kPackThreads, kEncodeDynSmem, stream>>>(x, n, mean_std, probs, kp, planes, sc, l.n_cta_tiles,     \
+                                                         rounds, aligned);                                         \
+    SMAQ_LAUNCH_OK();                                                                                              \
+    encode_scan_kernel<<<1, 1024, 0, stream>>>(sc, n_groups, l.n_cta_tiles, hdr, table, mean_std, kp, n, ST_);     \
+    encode_place_kernel<XB_><<<grid, kPackThreads, 0, stream>>>(sc, table, extras, l.n_cta_tiles, l.n_warp_tiles,  \
+                                                                rounds);                                           \
+  }
 #define SMAQ_ENC(PM_, XB_)                                                                                         \
   if (pm == PM_ && xb == XB_) {                                                                                    \
-    if (!st) encode_kernel<PM_, XB_, false, false><<<grid, kPackThreads, 0, stream>>>(                             \
-          x, n, mean_std, probs, kp, hdr, table, planes, extras, (EncodeWs*)ws, l.n_cta_tiles, aligned);           \
-    else if (hp) encode_kernel<PM_, XB_, true, true><<<grid, kPackThreads, 0, stream>>>(                           \
-          x, n, mean_std, probs, kp, hdr, table, planes, extras, (EncodeWs*)ws, l.n_cta_tiles, aligned);           \
-    else encode_kernel<PM_, XB_, true, false><<<grid, kPackThreads, 0, stream>>>(                                  \
-          x, n, mean_std, probs, kp, hdr, table, planes, extras, (EncodeWs*)ws, l.n_cta_tiles, aligned);           \
+    if (!st) SMAQ_ENC_LAUNCH(PM_, XB_, false, false)                                                               \
+    else if (hp) SMAQ_ENC_LAUNCH(PM_, XB_, true, true)                                                             \
+    else SMAQ_ENC_LAUNCH(PM_, XB_, true, false)                                                                    \
   }
 #define SMAQ_ENC_ROW(PM_) SMAQ_ENC(PM_, 0) SMAQ_ENC(PM_, 1) SMAQ_ENC(PM_, 2) SMAQ_ENC(PM_, 3) SMAQ_ENC(PM_, 4)
 #ifdef SMAQ_PACK_MINIMAL
@@ -535,6 +673,7 @@ int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* p
 #endif
 #undef SMAQ_ENC_ROW
 #undef SMAQ_ENC
+#undef SMAQ_ENC_LAUNCH
   SMAQ_LAUNCH_OK();
   return SMAQ_OK;
 }
@@ -552,7 +691,7 @@ int smaq_decode(const void* packed, size_t packed_bytes, int64_t n, int32_t bits
   auto* table = (const uint32_t*)(pb + l.table_off);
   auto* planes = (const uint32_t*)(pb + l.planes_off);
   auto* extras = (const uint32_t*)(pb + l.extras_off);
-  const int aligned = aligned16(y);
+  const int aligned = aligned32(y);
   const int pm = bits_main - 1, xb = bits_outlier - bits_main;
   const unsigned grid = (unsigned)l.n_cta_tiles;
 #define SMAQ_DEC(PM_, XB_)                                                                                         \

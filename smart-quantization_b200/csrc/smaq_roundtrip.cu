@@ -27,83 +27,100 @@ __device__ __noinline__ float4 roundtrip_group_exact(float4 v, float4 pr, const 
   f32x2 c01 = encode_pair<kStochastic, false>(pair(v.x, v.y), pair(pr.x, pr.y), s, k0, unused);
   f32x2 c23 = encode_pair<kStochastic, false>(pair(v.z, v.w), pair(pr.z, pr.w), s, k1, unused);
   if (saturate) {
-    c01 = pair(saturate_code(c01.x, s, k0.outl0), saturate_code(c01.y, s, k0.outl1));
-    c23 = pair(saturate_code(c23.x, s, k1.outl0), saturate_code(c23.y, s, k1.outl1));
+    c01 = pair(saturate_code(c01.x, s, is_outlier0(k0)), saturate_code(c01.y, s, is_outlier1(k0)));
+    c23 = pair(saturate_code(c23.x, s, is_outlier0(k1)), saturate_code(c23.y, s, is_outlier1(k1)));
   }
   f32x2 y01 = decode_pair<false, false>(c01, k0.shift, k0.range_b, k0.range_r, s, all_positive, unused);
   f32x2 y23 = decode_pair<false, false>(c23, k1.shift, k1.range_b, k1.range_r, s, all_positive, unused);
   return make_float4(y01.x, y01.y, y23.x, y23.y);
 }
 
-// Processes the 4-element group g (elements 4g..4g+3).
+// Processes the 8-element group g (elements 8g..8g+7): one Philox call, four packed pairs.
 template <bool kStochastic, bool kHasProbs, bool kAllPos, bool kSaturate, bool kFast>
-__device__ __forceinline__ float4 roundtrip_group(float4 v, float4 pr, uint64_t g, const Scalars& s,
+__device__ __forceinline__ f32x8 roundtrip_group8(const f32x8& v, f32x8 pr, uint64_t g, const Scalars& s,
                                                   const KernelParams& kp) {
   if (kStochastic && !kHasProbs) {
     const uint4 r = philox_group(kp.keys, g, kp.offset);
-    const f32x2 a = uniform24_pair(r.x, r.y), b = uniform24_pair(r.z, r.w);
-    pr = make_float4(a.x, a.y, b.x, b.y);
+    const f32x2 p0 = uniform16_pair(r.x), p1 = uniform16_pair(r.y), p2 = uniform16_pair(r.z), p3 = uniform16_pair(r.w);
+    pr.a = make_float4(p0.x, p0.y, p1.x, p1.y);
+    pr.b = make_float4(p2.x, p2.y, p3.x, p3.y);
   }
-  if (!kFast) return roundtrip_group_exact<kStochastic>(v, pr, s, kSaturate, kAllPos);
-  PairClass k0, k1;
+  f32x8 o;
+  if (!kFast) {
+    o.a = roundtrip_group_exact<kStochastic>(v.a, pr.a, s, kSaturate, kAllPos);
+    o.b = roundtrip_group_exact<kStochastic>(v.b, pr.b, s, kSaturate, kAllPos);
+    return o;
+  }
+  PairClass k0, k1, k2, k3;
   bool suspect = false;
-  f32x2 c01 = encode_pair<kStochastic, true>(pair(v.x, v.y), pair(pr.x, pr.y), s, k0, suspect);
-  f32x2 c23 = encode_pair<kStochastic, true>(pair(v.z, v.w), pair(pr.z, pr.w), s, k1, suspect);
+  f32x2 c0 = encode_pair<kStochastic, true>(pair(v.a.x, v.a.y), pair(pr.a.x, pr.a.y), s, k0, suspect);
+  f32x2 c1 = encode_pair<kStochastic, true>(pair(v.a.z, v.a.w), pair(pr.a.z, pr.a.w), s, k1, suspect);
+  f32x2 c2 = encode_pair<kStochastic, true>(pair(v.b.x, v.b.y), pair(pr.b.x, pr.b.y), s, k2, suspect);
+  f32x2 c3 = encode_pair<kStochastic, true>(pair(v.b.z, v.b.w), pair(pr.b.z, pr.b.w), s, k3, suspect);
   if (kSaturate) {
-    c01 = pair(saturate_code(c01.x, s, k0.outl0), saturate_code(c01.y, s, k0.outl1));
-    c23 = pair(saturate_code(c23.x, s, k1.outl0), saturate_code(c23.y, s, k1.outl1));
+    c0 = pair(saturate_code(c0.x, s, is_outlier0(k0)), saturate_code(c0.y, s, is_outlier1(k0)));
+    c1 = pair(saturate_code(c1.x, s, is_outlier0(k1)), saturate_code(c1.y, s, is_outlier1(k1)));
+    c2 = pair(saturate_code(c2.x, s, is_outlier0(k2)), saturate_code(c2.y, s, is_outlier1(k2)));
+    c3 = pair(saturate_code(c3.x, s, is_outlier0(k3)), saturate_code(c3.y, s, is_outlier1(k3)));
   }
-  const f32x2 y01 = decode_pair<true, true>(c01, k0.shift, k0.range_b, k0.range_r, s, kAllPos, suspect);
-  const f32x2 y23 = decode_pair<true, true>(c23, k1.shift, k1.range_b, k1.range_r, s, kAllPos, suspect);
-  float4 o = make_float4(y01.x, y01.y, y23.x, y23.y);
-  if (suspect) o = roundtrip_group_exact<kStochastic>(v, pr, s, kSaturate, kAllPos);  // rare
+  const f32x2 y0 = decode_pair<true, true>(c0, k0.shift, k0.range_b, k0.range_r, s, kAllPos, suspect);
+  const f32x2 y1 = decode_pair<true, true>(c1, k1.shift, k1.range_b, k1.range_r, s, kAllPos, suspect);
+  const f32x2 y2 = decode_pair<true, true>(c2, k2.shift, k2.range_b, k2.range_r, s, kAllPos, suspect);
+  const f32x2 y3 = decode_pair<true, true>(c3, k3.shift, k3.range_b, k3.range_r, s, kAllPos, suspect);
+  o.a = make_float4(y0.x, y0.y, y1.x, y1.y);
+  o.b = make_float4(y2.x, y2.y, y3.x, y3.y);
+  if (suspect) {  // rare
+    o.a = roundtrip_group_exact<kStochastic>(v.a, pr.a, s, kSaturate, kAllPos);
+    o.b = roundtrip_group_exact<kStochastic>(v.b, pr.b, s, kSaturate, kAllPos);
+  }
   return o;
 }
 
 constexpr int kRtThreads = 256;
-constexpr int kRtUnroll = 4;  // independent 128-bit loads in flight per thread
+constexpr int kRtUnroll = 2;  // independent 256-bit loads in flight per thread
 
 template <bool kStochastic, bool kHasProbs, bool kAllPos, bool kSaturate, bool kFast>
 __device__ __forceinline__ void roundtrip_body(const float* x, float* y, int64_t n, const float* __restrict__ probs,
                                                const KernelParams& kp, const Scalars& s) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  const int64_t ngroups = n >> 2;
-  const float4* xv = reinterpret_cast<const float4*>(x);
-  const float4* pv = reinterpret_cast<const float4*>(probs);
-  float4* yv = reinterpret_cast<float4*>(y);
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t ngroups = n >> 3;
+  f32x8 zero8;
+  zero8.a = zero8.b = make_float4(0.f, 0.f, 0.f, 0.f);
   int64_t g = tid;
   for (; g + (kRtUnroll - 1) * nthreads < ngroups; g += kRtUnroll * nthreads) {
-    float4 v[kRtUnroll], pr[kRtUnroll];
+    f32x8 v[kRtUnroll], pr[kRtUnroll];
 #pragma unroll
     for (int u = 0; u < kRtUnroll; ++u) {
-      v[u] = ldg_stream(xv + g + u * nthreads);
-      pr[u] = (kStochastic && kHasProbs) ? ldg_stream(pv + g + u * nthreads) : zero4;
+      v[u] = ldg_stream8(x + 8 * (g + u * nthreads));
+      pr[u] = (kStochastic && kHasProbs) ? ldg_stream8(probs + 8 * (g + u * nthreads)) : zero8;
     }
 #pragma unroll
     for (int u = 0; u < kRtUnroll; ++u)
-      stg_stream(yv + g + u * nthreads, roundtrip_group<kStochastic, kHasProbs, kAllPos, kSaturate, kFast>(
-                                            v[u], pr[u], (uint64_t)(g + u * nthreads), s, kp));
+      stg_stream8(y + 8 * (g + u * nthreads), roundtrip_group8<kStochastic, kHasProbs, kAllPos, kSaturate, kFast>(
+                                                   v[u], pr[u], (uint64_t)(g + u * nthreads), s, kp));
   }
   for (; g < ngroups; g += nthreads) {
-    const float4 v = ldg_stream(xv + g);
-    const float4 pr = (kStochastic && kHasProbs) ? ldg_stream(pv + g) : zero4;
-    stg_stream(yv + g, roundtrip_group<kStochastic, kHasProbs, kAllPos, kSaturate, kFast>(v, pr, (uint64_t)g, s, kp));
+    const f32x8 v = ldg_stream8(x + 8 * g);
+    const f32x8 pr = (kStochastic && kHasProbs) ? ldg_stream8(probs + 8 * g) : zero8;
+    stg_stream8(y + 8 * g, roundtrip_group8<kStochastic, kHasProbs, kAllPos, kSaturate, kFast>(v, pr, (uint64_t)g, s, kp));
   }
 }
 
-// One element at a time: tails, unaligned tensors, small tensors.
+// One element at a time: tails, unaligned tensors, small tensors.  Same random stream as the
+// vector path: element i uses half (i & 1) of word (i & 7) >> 1 of Philox group i >> 3.
 template <bool kStochastic, bool kHasProbs>
 __device__ __forceinline__ float roundtrip_element(const float* x, const float* probs, int64_t i, const Scalars& s,
                                                    const KernelParams& kp) {
   float p = 0.f;
   if (kStochastic)
-    p = kHasProbs ? probs[i] : uniform24(philox_word(philox_group(kp.keys, (uint64_t)(i >> 2), kp.offset), (int)(i & 3)));
+    p = kHasProbs ? probs[i]
+                  : uniform16(philox_word(philox_group(kp.keys, (uint64_t)(i >> 3), kp.offset), (int)((i & 7) >> 1)),
+                              (int)(i & 1));
   return roundtrip_scalar<kStochastic>(x[i], p, s, kp.saturate != 0, kp.all_positive != 0);
 }
 
-// Aligned tensors: 128-bit path for whole groups, element path for the last n % 4.
+// 32-byte aligned tensors: 256-bit path for whole groups of 8, element path for the last n % 8.
 template <bool kStochastic, bool kHasProbs, bool kAllPos, bool kSaturate>
 __global__ void __launch_bounds__(kRtThreads) roundtrip_kernel(const float* x, float* y, int64_t n,
                                                                const float* __restrict__ mean_std,
@@ -115,11 +132,11 @@ __global__ void __launch_bounds__(kRtThreads) roundtrip_kernel(const float* x, f
   if (s.fast) roundtrip_body<kStochastic, kHasProbs, kAllPos, kSaturate, true>(x, y, n, probs, kp, s);
   else roundtrip_body<kStochastic, kHasProbs, kAllPos, kSaturate, false>(x, y, n, probs, kp, s);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i = ((n >> 2) << 2) + tid;
+  const int64_t i = ((n >> 3) << 3) + tid;
   if (i < n) y[i] = roundtrip_element<kStochastic, kHasProbs>(x, probs, i, s, kp);
 }
 
-// Tensors whose pointers are only 4-byte aligned (views into larger buffers).
+// Tensors whose pointers are not 32-byte aligned (views into larger buffers).
 template <bool kStochastic, bool kHasProbs>
 __global__ void __launch_bounds__(kRtThreads) roundtrip_unaligned_kernel(const float* x, float* y, int64_t n,
                                                                          const float* __restrict__ mean_std,
@@ -204,7 +221,7 @@ __global__ void __launch_bounds__(kRtThreads) count_outliers_kernel(const float*
 static int rt_grid(int64_t n) {
   int sms = sm_count();
   if (sms <= 0) sms = 148;
-  int64_t want = ((n + 3) / 4 + kRtThreads - 1) / kRtThreads;
+  int64_t want = ((n + 7) / 8 + kRtThreads - 1) / kRtThreads;
   int64_t cap = (int64_t)sms * 8;
   if (want < 1) want = 1;
   return (int)(want < cap ? want : cap);
@@ -233,7 +250,7 @@ int smaq_roundtrip(const float* x, float* y, int64_t n, const float* mean_std, c
   if (n == 0) return SMAQ_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
   const KernelParams kp = to_kernel_params(*params);
-  const bool al = aligned16(x) && aligned16(y) && (!probs || aligned16(probs));
+  const bool al = aligned32(x) && aligned32(y) && (!probs || aligned32(probs));
   const int grid = rt_grid(n);
   const bool st = params->stochastic != 0;
   if (al) {

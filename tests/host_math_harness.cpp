@@ -29,14 +29,14 @@ void harness_roundtrip(const float* x, const float* probs, float* y, float* code
     f32x2 code = pair(0.f, 0.f), out = pair(0.f, 0.f);
     if (fast) {
       code = stochastic ? encode_pair<true, true>(xv, pv, s, k, suspect) : encode_pair<false, true>(xv, pv, s, k, suspect);
-      if (saturate) code = pair(saturate_code(code.x, s, k.outl0), saturate_code(code.y, s, k.outl1));
+      if (saturate) code = pair(saturate_code(code.x, s, is_outlier0(k)), saturate_code(code.y, s, is_outlier1(k)));
       out = decode_pair<true, true>(code, k.shift, k.range_b, k.range_r, s, all_positive != 0, suspect);
     }
     if (suspect) {
       bool unused = false;
       redone += fast;
       code = stochastic ? encode_pair<true, false>(xv, pv, s, k, unused) : encode_pair<false, false>(xv, pv, s, k, unused);
-      if (saturate) code = pair(saturate_code(code.x, s, k.outl0), saturate_code(code.y, s, k.outl1));
+      if (saturate) code = pair(saturate_code(code.x, s, is_outlier0(k)), saturate_code(code.y, s, is_outlier1(k)));
       out = decode_pair<false, false>(code, k.shift, k.range_b, k.range_r, s, all_positive != 0, unused);
     }
     y[i] = out.x;

@@ -143,7 +143,7 @@ def test_plugin_encode_decode_and_size_accounting():
     ratio = 32 * x.numel() / packed.payload_bits()
     assert 4.6 < ratio < 5.3
     # stored bytes: payload + table + alignment only
-    assert packed.used_bytes() * 8 - packed.payload_bits() < 8 * (128 + 4 * (packed.layout.n_cta_tiles + 1) + 128) + 32 * packed.layout.n_cta_tiles
+    assert packed.used_bytes() * 8 - packed.payload_bits() < 8 * (128 + 4 * (packed.layout.n_cta_tiles + 1) + 128) + 32 * packed.layout.n_warp_tiles
     err = (y - xd).abs()
     ms = fp.statistics(xd.view(-1)).cpu()
     assert float(err[(xd - ms[0]).abs() <= 2.5 * ms[1]].max()) <= ms[1].item() / 15 + 1e-6
@@ -180,7 +180,6 @@ def test_full_size_properties(n):
     t = tags.long() & 0xFFFFFFFF
     for b in range(32):
         pop += ((t >> b) & 1).sum(dim=1)
-    per_cta = pop.view(-1, 8).sum(dim=1)
-    words = (per_cta * 2 + 31) // 32
+    words = ((pop * 2 + 31) // 32).view(-1, 8).sum(dim=1)  # word-aligned segment per warp tile
     assert torch.equal(table[1:] - table[:-1], words)
     assert int(pop.sum()) == hdr.n_outlier and int(table[-1]) == hdr.extras_words
