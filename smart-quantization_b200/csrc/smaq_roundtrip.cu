@@ -87,23 +87,45 @@ __device__ __forceinline__ void roundtrip_body(const float* x, float* y, int64_t
   const int64_t ngroups = n >> 3;
   f32x8 zero8;
   zero8.a = zero8.b = make_float4(0.f, 0.f, 0.f, 0.f);
+  // software pipeline: the next pair of 256-bit loads is issued before the current pair is
+  // processed, so every thread keeps 64 bytes in flight through the compute phase
+  const int64_t stride = kRtUnroll * nthreads;
   int64_t g = tid;
-  for (; g + (kRtUnroll - 1) * nthreads < ngroups; g += kRtUnroll * nthreads) {
-    f32x8 v[kRtUnroll], pr[kRtUnroll];
+  f32x8 cur[kRtUnroll], curp[kRtUnroll];
+#pragma unroll
+  for (int u = 0; u < kRtUnroll; ++u) {
+    const int64_t gu = g + u * nthreads;
+    cur[u] = curp[u] = zero8;
+    if (gu < ngroups) {
+      cur[u] = ldg_stream8(x + 8 * gu);
+      if (kStochastic && kHasProbs) curp[u] = ldg_stream8(probs + 8 * gu);
+    }
+  }
+  while (g < ngroups) {
+    const int64_t gn = g + stride;
+    f32x8 nxt[kRtUnroll], nxtp[kRtUnroll];
 #pragma unroll
     for (int u = 0; u < kRtUnroll; ++u) {
-      v[u] = ldg_stream8(x + 8 * (g + u * nthreads));
-      pr[u] = (kStochastic && kHasProbs) ? ldg_stream8(probs + 8 * (g + u * nthreads)) : zero8;
+      const int64_t gu = gn + u * nthreads;
+      nxt[u] = nxtp[u] = zero8;
+      if (gu < ngroups) {
+        nxt[u] = ldg_stream8(x + 8 * gu);
+        if (kStochastic && kHasProbs) nxtp[u] = ldg_stream8(probs + 8 * gu);
+      }
     }
 #pragma unroll
-    for (int u = 0; u < kRtUnroll; ++u)
-      stg_stream8(y + 8 * (g + u * nthreads), roundtrip_group8<kStochastic, kHasProbs, kAllPos, kSaturate, kFast>(
-                                                   v[u], pr[u], (uint64_t)(g + u * nthreads), s, kp));
-  }
-  for (; g < ngroups; g += nthreads) {
-    const f32x8 v = ldg_stream8(x + 8 * g);
-    const f32x8 pr = (kStochastic && kHasProbs) ? ldg_stream8(probs + 8 * g) : zero8;
-    stg_stream8(y + 8 * g, roundtrip_group8<kStochastic, kHasProbs, kAllPos, kSaturate, kFast>(v, pr, (uint64_t)g, s, kp));
+    for (int u = 0; u < kRtUnroll; ++u) {
+      const int64_t gu = g + u * nthreads;
+      if (gu < ngroups)
+        stg_stream8(y + 8 * gu, roundtrip_group8<kStochastic, kHasProbs, kAllPos, kSaturate, kFast>(cur[u], curp[u],
+                                                                                                     (uint64_t)gu, s, kp));
+    }
+#pragma unroll
+    for (int u = 0; u < kRtUnroll; ++u) {
+      cur[u] = nxt[u];
+      curp[u] = nxtp[u];
+    }
+    g = gn;
   }
 }
 
@@ -122,7 +144,7 @@ __device__ __forceinline__ float roundtrip_element(const float* x, const float* 
 
 // 32-byte aligned tensors: 256-bit path for whole groups of 8, element path for the last n % 8.
 template <bool kStochastic, bool kHasProbs, bool kAllPos, bool kSaturate>
-__global__ void __launch_bounds__(kRtThreads) roundtrip_kernel(const float* x, float* y, int64_t n,
+__global__ void __launch_bounds__(kRtThreads, 3) roundtrip_kernel(const float* x, float* y, int64_t n,
                                                                const float* __restrict__ mean_std,
                                                                const float* __restrict__ probs,
                                                                const __grid_constant__ KernelParams kp) {
