@@ -177,7 +177,8 @@ class Pipeline:
         self.packed = torch.empty(self.lay.total_capacity_bytes, dtype=torch.uint8, device=device)
         self.enc_ws = torch.empty(self.lay.workspace_bytes, dtype=torch.uint8, device=device)
         self.y = torch.empty(n, dtype=torch.float32, device=device)
-        self.launches_per_step = 3  # stats, encode, decode kernels (the two workspace memsets are not ours)
+        # stats; encode = quantise+pack, scan of the per-group counts, placement of the extras; decode
+        self.launches_per_step = 5
         self.step_index = 0
 
     def stats(self, x):
@@ -185,9 +186,10 @@ class Pipeline:
         N.check(self.lib.smaq_stats_full(x.data_ptr(), self.n, 1, self.ms.data_ptr(), self.stats_ws.data_ptr(),
                                          self.stats_ws_bytes, N.stream_ptr(self.device)), "stats")
 
-    def encode(self, x):
+    def encode(self, x, count_saturated=False):
         N = self.N
         params = self.fp._params(all_positive=False)
+        params.count_saturated = int(count_saturated)  # plugin default: only under --measure_compression_ratio
         N.check(self.lib.smaq_encode(x.data_ptr(), self.n, self.ms.data_ptr(), None, self.C.byref(params),
                                      self.packed.data_ptr(), self.packed.numel(), self.enc_ws.data_ptr(),
                                      self.enc_ws.numel(), N.stream_ptr(self.device)), "encode")
@@ -276,6 +278,7 @@ def run_b200(args):
         elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
 
+    pipe.encode(x, count_saturated=True)  # untimed: the timed steps run with the plugin's default (no count)
     hdr = pipe.header()
     assert hdr.status == 0 and hdr.n == n, "encode reported a failure"
     f_out = hdr.n_outlier / n

@@ -60,7 +60,9 @@ typedef struct smaq_codec_params {
   int32_t all_positive; /* clamp_min(0) at the end (smart.py:181-182) */
   int32_t saturate;     /* round trip only: clamp codes to what the packed format holds (not in
                            the reference; 0 reproduces smart.py exactly) */
-  int32_t reserved;
+  int32_t count_saturated; /* packed encoder only: fill header.n_saturated (costs ~5 % of the encode
+                           kernel; the plugin sets it under --measure_compression_ratio).  0: the
+                           header field is all ones */
   uint64_t seed;        /* Philox4x32-10 key, used when stochastic && probs == NULL */
   uint64_t offset;      /* Philox stream offset (added to the counter's high words) */
 } smaq_codec_params;
@@ -140,14 +142,15 @@ typedef struct smaq_packed_layout {
 
 /* First bytes of a packed buffer, written by smaq_encode on the device. */
 typedef struct smaq_packed_header {
-  uint32_t magic;            /* 'SQB1' */
+  uint32_t magic;            /* 'SQB2' */
   int32_t bits_main, bits_outlier;
   int32_t stochastic;
   int64_t n;
   float mean, std_raw;       /* statistics the codes are relative to */
   float threshold, range_main, range_outlier, clamp_lo, clamp_hi, pad0;
   uint64_t n_outlier;        /* smart.py:184-187: compressed bits = 8*n_outlier + 6*(n-n_outlier) */
-  uint64_t n_saturated;      /* codes clamped to the field width, or non-finite (H1) */
+  uint64_t n_saturated;      /* scaled values the field width cannot hold, or NaN (H1); ~0 when
+                                not counted (smaq_codec_params.count_saturated == 0) */
   uint64_t extras_words;     /* 32-bit words actually used in the extras section */
   uint64_t status;           /* 0 ok; nonzero: encode aborted (look-back watchdog) */
 } smaq_packed_header;

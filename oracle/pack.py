@@ -1,4 +1,4 @@
-"""CPU oracle for the PACKED SmaQ stream "SQB1" (TEST INFRASTRUCTURE ONLY).
+"""CPU oracle for the PACKED SmaQ stream "SQB2" (TEST INFRASTRUCTURE ONLY).
 
 The reference never materialises codes: SmartFP is fake quantisation (smart.py:154-172) and only
 *accounts* for a size of 6 bits per main element and 8 per outlier (smart.py:184-187).  The
@@ -7,31 +7,38 @@ applied to the integer codes of oracle/smaq.py (which is pinned to the reference
 saturation rule of SURVEY.md §7.3.  DESIGN.md "Packed layout" is the normative text; this file
 is its executable form and the CUDA encoder must reproduce it byte for byte.
 
-Per element the code is split as
-    payload P = (|code| << 1) | s      s = sign bit of the code (main)  /  1 for a LOWER outlier
-    main   : P < 2^pm,  pm = bits_main - 1        (tag bit + pm bits   = bits_main)
-    outlier: P < 2^po,  po = bits_outlier - 1     (tag bit + po bits   = bits_outlier)
-    base = P & (2^pm - 1)   stored for every element at a fixed position
-    ext  = P >> pm          xb = po - pm bits, stored only for outliers, densely
+Per element, with L = 2^(bits-2) - 1 the largest code magnitude its width holds
+(bits = num_bits_main or num_bits_outlier), pm = bits_main - 1, po = bits_outlier - 1, xb = po - pm:
+    c'   = clamp((z + shift) * range, -L, L)            the H1 rule; NaN -> 0 (both counted in
+                                                         n_saturated — a pure function of the data)
+    code = round(c')                                     the reference's rounding (smart.py:93-98 / :169);
+                                                         == clamp(reference code, -L, L)
+    S    = code - [sign bit of z]                        z < 0 implies code <= 0 and z >= 0 implies
+                                                         code >= 0, so S is a two's-complement number of
+                                                         bits-1 bits and (side, code) is recovered from it
+    U    = S + 2^(po-1)
+    base = U mod 2^pm    stored for every element at a fixed position (main: S in two's complement)
+    ext  = U >> pm       xb bits, stored only for outliers, densely   (outlier: U is S, offset binary)
 so the stream holds exactly  n + pm*n + xb*n_out = bits_main*n_main + bits_outlier*n_out  bits
 (+ the per-tile table and word alignment, reported as overhead).
 
-Geometry (chosen so one warp reads its 1024 values with eight coalesced 128-bit loads and every
-lane packs its own 32 values in registers):
-    warp tile = 1024 consecutive elements; lane l (0..31) owns local element i = 8k + j
-                (k = 0..3, j = 0..7)  <->  tile element 256*k + 8*l + j
+Geometry (chosen so one warp reads its 1024 values as one 4 KB bulk copy and every lane packs its own
+32 values in registers with packed fp32 arithmetic):
+    warp tile = 1024 consecutive elements; lane l (0..31) owns four CHUNKS of eight consecutive
+                elements: chunk k (0..3), element j (0..7)  <->  tile element 256*k + 8*l + j
     planes    : per warp tile (1+pm) rows of 32 uint32, row-major [row][lane]:
-                row 0 = tag word (bit i = element i is an outlier),
-                rows 1..pm = the lane's 32 base fields concatenated LSB-first (field i at bit pm*i)
-    extras    : per warp tile, its outliers' ext fields concatenated in (lane, i) order, LSB-first,
-                padded to a whole uint32 (so a warp places them without a block barrier); warp-tile
-                segments follow each other in tile order.
+                row 0 = tag word (bit 8k+j = element (k, j) is an outlier),
+                rows 1..pm = the lane's 32 base fields as a 32*pm-bit string, LSB-first; element
+                (k, j) sits at bit  8*pm*k + 4*pm*(j & 1) + pm*(j >> 1)  (even elements of a chunk
+                first, then the odd ones: the two lanes of the packed fp32 accumulator)
+    extras    : per warp tile, lanes in order, per lane its chunks in order (LSB-first); inside a
+                chunk the outliers' ext fields are concatenated with the FIRST outlier in the MOST
+                significant position (E = E * 2^xb + ext); the warp-tile segment is padded to a
+                whole uint32; warp-tile segments follow each other in tile order.
     CTA tile  = 8 warp tiles; table[t] = first word of CTA tile t's first segment in the extras
                 section, table[n_cta_tiles] = total words (a warp finds its own segment by adding
                 the word counts of the warps before it, which follow from the tag words).
-Elements past n (padding of the last tile) are main elements with payload 0.
-Infinite codes saturate like any other over-range code; NaN codes (NaN statistics or inputs) are
-stored as code 0; both are counted in n_saturated together with the clamped ones.
+Elements past n (padding of the last tile) are main elements with S = 0.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this.
 """
@@ -47,7 +54,7 @@ from .smaq import SmaqConfig, SmaqResult
 WARP_TILE = 1024
 WARPS_PER_CTA = 8
 CTA_TILE = WARP_TILE * WARPS_PER_CTA
-MAGIC = 0x31425153  # 'SQB1' little endian
+MAGIC = 0x32425153  # 'SQB2' little endian
 
 
 @dataclass
@@ -82,20 +89,35 @@ def lane_order_index(n_padded: int) -> np.ndarray:
     return w * WARP_TILE + 256 * k + 8 * l + j
 
 
-def codes_from_result(res: SmaqResult, cfg: SmaqConfig):
-    """(outlier mask, sign/side bit, magnitude, n_saturated) from an UNSATURATED oracle result."""
-    code = res.code.detach().reshape(-1).numpy().astype(np.float32)
-    hi = res.hi.reshape(-1).numpy()
-    lo = res.lo.reshape(-1).numpy()
-    outlier = hi | lo
-    lim = np.where(outlier, cfg.max_code_outlier, cfg.max_code_main).astype(np.float32)
-    finite = ~np.isnan(code)  # +-inf saturates to +-lim, NaN becomes 0
-    clipped = finite & (np.abs(code) > lim)
-    sat = np.clip(np.where(finite, code, 0.0), -lim, lim)
-    mag = np.abs(sat).astype(np.uint32)
-    # main: the code's own sign bit (so trunc's -0.0 survives); outlier: which side of the mean
-    s = np.where(outlier, lo, np.signbit(sat) & finite).astype(np.uint32)
-    return outlier, s, mag, int(clipped.sum() + (~finite).sum())
+def field_bit_positions(pm: int) -> np.ndarray:
+    """Bit position of local element i = 8k + j inside the lane's 32*pm-bit base string."""
+    i = np.arange(32)
+    k, j = i // 8, i % 8
+    return 8 * pm * k + 4 * pm * (j & 1) + pm * (j >> 1)
+
+
+def stored_values(res: SmaqResult, cfg: SmaqConfig):
+    """(outlier mask, S, n_saturated) from an UNSATURATED oracle result (needs extras c, z)."""
+    from .smaq import round_stochastic
+
+    c = res.extras["c"].detach().reshape(-1).clone()
+    z = res.extras["z"].detach().reshape(-1)
+    outlier = (res.hi | res.lo).reshape(-1)
+    lim = torch.where(outlier, float(cfg.max_code_outlier), float(cfg.max_code_main))
+    isn = torch.isnan(c)
+    n_sat = int((isn | (c.abs() > lim)).sum())
+    cc = torch.where(isn, torch.zeros_like(c), torch.maximum(torch.minimum(c, lim), -lim))
+    if cfg.stochastic_rounding:
+        code = round_stochastic(cc, res.extras["probs"].reshape(-1))
+    else:
+        code = cc.trunc()
+    # where nothing was clipped this IS the reference's code (pinned), elsewhere its clamp
+    ref = res.code.detach().reshape(-1)
+    ok = ~isn & ~torch.isnan(ref)
+    assert torch.equal(code[ok], torch.maximum(torch.minimum(ref, lim), -lim)[ok]), "clamp(c) then round != clamp(code)"
+    below = torch.signbit(z) & ~isn
+    S = code.to(torch.int64) - below.to(torch.int64)
+    return outlier.numpy(), S.numpy(), n_sat
 
 
 def pack(res: SmaqResult, cfg: SmaqConfig) -> Packed:
@@ -103,43 +125,54 @@ def pack(res: SmaqResult, cfg: SmaqConfig) -> Packed:
     xb = po - pm
     assert pm >= 2 and xb >= 0
     n = res.code.numel()
-    outlier, s, mag, n_sat = codes_from_result(res, cfg)
-    payload = (mag.astype(np.uint64) << np.uint64(1)) | s.astype(np.uint64)
-    assert np.all(payload[~outlier] < (1 << pm)) and np.all(payload < (1 << po))
+    outlier, S, n_sat = stored_values(res, cfg)
+    lo_m, hi_m = -(cfg.max_code_main + 1), cfg.max_code_main
+    lo_o, hi_o = -(cfg.max_code_outlier + 1), cfg.max_code_outlier
+    assert np.all((S[~outlier] >= lo_m) & (S[~outlier] <= hi_m)) and np.all((S[outlier] >= lo_o) & (S[outlier] <= hi_o))
+    U = (S + (1 << (po - 1))).astype(np.uint64)
 
     n_wt = -(-n // WARP_TILE)
     n_ct = -(-n_wt // WARPS_PER_CTA)
     n_pad = n_wt * WARP_TILE
-    pay = np.zeros(n_pad, dtype=np.uint64)
+    upad = np.full(n_pad, 1 << (po - 1), dtype=np.uint64)   # padding: main, S = 0
     tag = np.zeros(n_pad, dtype=bool)
-    pay[:n] = payload
+    upad[:n] = U
     tag[:n] = outlier
     perm = lane_order_index(n_pad)          # [w, l, i]
-    pay_l = pay[perm]
+    u_l = upad[perm]
     tag_l = tag[perm]
 
     planes = np.zeros((n_wt, 1 + pm, 32), dtype=np.uint32)
     weights = (np.uint64(1) << np.arange(32, dtype=np.uint64))
     planes[:, 0, :] = (tag_l.astype(np.uint64) * weights).sum(axis=2).astype(np.uint32)
-    base = pay_l & np.uint64((1 << pm) - 1)
-    # concatenate 32 pm-bit fields LSB-first into pm words, via a bit matrix
-    bits = ((base[..., None] >> np.arange(pm, dtype=np.uint64)) & np.uint64(1)).reshape(n_wt, 32, 32 * pm)
-    words = (bits.reshape(n_wt, 32, pm, 32).astype(np.uint64) * weights).sum(axis=3).astype(np.uint32)
+    base = u_l & np.uint64((1 << pm) - 1)
+    # scatter the 32 pm-bit fields of each lane into its 32*pm-bit string
+    bits = np.zeros((n_wt, 32, 32 * pm), dtype=np.uint64)
+    pos = field_bit_positions(pm)
+    for b in range(pm):
+        bits[:, :, pos + b] = (base >> np.uint64(b)) & np.uint64(1)
+    words = (bits.reshape(n_wt, 32, pm, 32) * weights).sum(axis=3).astype(np.uint32)
     planes[:, 1:, :] = np.transpose(words, (0, 2, 1))
 
-    # extras: one word-aligned segment per warp tile, fields in (lane, i) order == flattened [w, l, i]
-    ext = (pay_l >> np.uint64(pm)).reshape(n_wt, -1)
-    tflat = tag_l.reshape(n_wt, -1)
+    # extras: one word-aligned segment per warp tile
+    ext = (u_l >> np.uint64(pm))
     seg_words = np.zeros(n_ct * WARPS_PER_CTA, dtype=np.int64)
     chunks = []
     for w in range(n_wt):
-        e = ext[w][tflat[w]]
-        nbits = e.size * xb
+        bl = []
+        if xb:
+            for l in range(32):
+                for k in range(4):
+                    sl = slice(8 * k, 8 * k + 8)
+                    e = ext[w, l, sl][tag_l[w, l, sl]]
+                    # first outlier most significant: LSB-first bit list = reversed field order
+                    for v in e[::-1]:
+                        bl.extend(((int(v) >> t) & 1) for t in range(xb))
+        nbits = len(bl)
         nwords = -(-nbits // 32)
         seg_words[w] = nwords
         if nwords:
-            b = ((e[:, None] >> np.arange(xb, dtype=np.uint64)) & np.uint64(1)).reshape(-1)
-            b = np.concatenate([b, np.zeros(nwords * 32 - nbits, dtype=np.uint64)])
+            b = np.array(bl + [0] * (nwords * 32 - nbits), dtype=np.uint64)
             chunks.append((b.reshape(nwords, 32) * weights).sum(axis=1).astype(np.uint32))
     table = np.zeros(n_ct + 1, dtype=np.uint32)
     table[1:] = np.cumsum(seg_words.reshape(n_ct, WARPS_PER_CTA).sum(axis=1))
@@ -148,8 +181,8 @@ def pack(res: SmaqResult, cfg: SmaqConfig) -> Packed:
                   table=table, extras=extras, n_outlier=int(outlier.sum()), n_saturated=n_sat)
 
 
-def unpack_codes(p: Packed):
-    """Packed -> (outlier mask, s bit, magnitude) in flat element order."""
+def unpack_values(p: Packed):
+    """Packed -> (outlier mask, S) in flat element order."""
     cfg = p.cfg
     pm, po = cfg.num_bits_main - 1, cfg.num_bits_outlier - 1
     xb = po - pm
@@ -158,45 +191,62 @@ def unpack_codes(p: Packed):
     shifts = np.arange(32, dtype=np.uint32)
     tag_l = ((p.planes[:, 0, :, None] >> shifts) & 1).astype(bool)          # [w, l, i]
     words = np.transpose(p.planes[:, 1:, :], (0, 2, 1))                      # [w, l, pm]
-    bits = ((words[..., None] >> shifts) & 1).reshape(n_wt, 32, 32 * pm)     # LSB-first bit string
-    fields = bits.reshape(n_wt, 32, 32, pm).astype(np.uint64)
-    base = (fields << np.arange(pm, dtype=np.uint64)).sum(axis=3)            # [w, l, i]
-    ext = np.zeros(n_wt * 32 * 32, dtype=np.uint64)
-    tflat = tag_l.reshape(-1)
+    bits = ((words[..., None] >> shifts) & 1).reshape(n_wt, 32, 32 * pm).astype(np.uint64)
+    pos = field_bit_positions(pm)
+    base = np.zeros((n_wt, 32, 32), dtype=np.uint64)
+    for b in range(pm):
+        base |= bits[:, :, pos + b] << np.uint64(b)
+    ext = np.zeros((n_wt, 32, 32), dtype=np.uint64)
     word = 0
     for w in range(n_wt):
-        sl = slice(w * WARP_TILE, (w + 1) * WARP_TILE)
-        k = int(tflat[sl].sum())
-        nwords = -(-(k * xb) // 32)
+        k_out = int(tag_l[w].sum())
+        nwords = -(-(k_out * xb) // 32)
         if w % WARPS_PER_CTA == 0:
             assert word == int(p.table[w // WARPS_PER_CTA]), "table does not match the tag words"
-        if k and xb:
+        if k_out and xb:
             seg = p.extras[word: word + nwords]
-            b = ((seg[:, None] >> shifts) & 1).reshape(-1)[: k * xb].reshape(k, xb).astype(np.uint64)
-            ext[np.nonzero(tflat[sl])[0] + sl.start] = (b << np.arange(xb, dtype=np.uint64)).sum(axis=1)
+            sb = ((seg[:, None] >> shifts) & 1).reshape(-1).astype(np.uint64)
+            at = 0
+            for l in range(32):
+                for k in range(4):
+                    idx = np.nonzero(tag_l[w, l, 8 * k: 8 * k + 8])[0] + 8 * k
+                    for i in idx[::-1]:   # LSB-first in the stream = last outlier of the chunk first
+                        v = 0
+                        for t in range(xb):
+                            v |= int(sb[at + t]) << t
+                        ext[w, l, i] = v
+                        at += xb
         word += nwords
-    pay_l = base.reshape(-1) | (ext << np.uint64(pm))
+    u_l = (base | (ext << np.uint64(pm))).reshape(-1)
+    tflat = tag_l.reshape(-1)
     perm = lane_order_index(n_pad).reshape(-1)
-    pay = np.zeros(n_pad, dtype=np.uint64)
+    U = np.zeros(n_pad, dtype=np.int64)
     tag = np.zeros(n_pad, dtype=bool)
-    pay[perm] = pay_l
+    U[perm] = u_l.astype(np.int64)
     tag[perm] = tflat
-    pay, tag = pay[: p.n], tag[: p.n]
-    return tag, (pay & np.uint64(1)).astype(np.uint32), (pay >> np.uint64(1)).astype(np.uint32)
+    U, tag = U[: p.n], tag[: p.n]
+    S_out = U - (1 << (po - 1))
+    if xb > 0:   # main: two's complement on pm bits
+        S_main = np.where(U >= (1 << (pm - 1)), U - (1 << pm), U)
+    else:
+        S_main = U - (1 << (pm - 1))
+    return tag, np.where(tag, S_out, S_main)
 
 
 @torch.no_grad()
 def decode(p: Packed, all_positive: bool = False) -> torch.Tensor:
     """Packed -> fp32, finishing with the reference's own inverse (smart.py:171-172,181-182)."""
     cfg = p.cfg
-    tag, s, mag = unpack_codes(p)
+    tag, S = unpack_values(p)
     tag_t = torch.from_numpy(tag)
-    s_t = torch.from_numpy(s.astype(np.int64)).bool()
-    magf = torch.from_numpy(mag.astype(np.float32))
-    code = torch.where(s_t, -magf, magf)  # -0.0 when s and mag == 0
+    S_t = torch.from_numpy(S)
+    below = S_t < 0
+    code = torch.where(below, S_t + 1, S_t).to(torch.float32)
+    if not cfg.stochastic_rounding:   # trunc yields -0.0 for a zero code on the lower side
+        code = torch.where(below & (code == 0), torch.tensor(-0.0), code)
     t = cfg.main_std_dev_threshold
-    hi = tag_t & ~s_t
-    lo = tag_t & s_t
+    hi = tag_t & ~below
+    lo = tag_t & below
     scalars = (hi * -t) + (lo * t)
     ranges = torch.where(tag_t, cfg.range_outlier, cfg.range_normal)
     mean = torch.tensor(p.mean)

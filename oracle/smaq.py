@@ -168,7 +168,7 @@ def smaq_roundtrip(
     if all_positive:  # smart.py:181-182
         y = y.clamp_min(0.0)
 
-    return SmaqResult(y=y, mean=mean, std=std_raw, hi=hi, lo=lo, code=code, extras={"z": z})
+    return SmaqResult(y=y, mean=mean, std=std_raw, hi=hi, lo=lo, code=code, extras={"z": z, "c": c, "probs": probs})
 
 
 def compressed_bits(res: SmaqResult, cfg: SmaqConfig) -> int:

@@ -4,25 +4,42 @@
 // The reference only ever holds the code as an fp32 value (smart_compress/compress/smart.py:164-169)
 // and accounts for 6 bits per main element and 8 per outlier (smart.py:184-187).  The stream
 // written here has exactly that size plus a 4-byte table entry per 8192 elements and at most 31
-// padding bits per 1024 elements; its layout ("SQB1") is specified in DESIGN.md and restated
+// padding bits per 1024 elements; its layout ("SQB2") is specified in DESIGN.md and restated
 // executable in oracle/pack.py.
+//
+// Stored value of an element.  With L = 2^(bits-2)-1 the largest code magnitude the width holds,
+//   S = clamp(code, -L, L) - [z < 0]      (z < 0 implies code <= 0, z >= 0 implies code >= 0, so S is
+//                                          a two's-complement number of bits-1 bits and the pair
+//                                          (side of the mean, code) is recovered from it: S >= 0 ->
+//                                          upper side, code = S; S < 0 -> lower side, code = S + 1)
+//   U = S + 2^(PO-1)                       PO = bits_outlier - 1, PM = bits_main - 1, XB = PO - PM
+//   base = U mod 2^PM   every element, fixed position      (main: S in two's complement, PM bits)
+//   ext  = U >> PM      XB bits, outliers only, dense       (outlier: U is S in offset binary, PO bits)
 //
 // Mapping to the hardware
 //   * one warp owns 1024 consecutive elements; the tile is brought into shared memory by ONE TMA
 //     bulk copy (cp.async.bulk + mbarrier), double-buffered, so the next tile is in flight while
-//     this one is quantised — these kernels are bound by instruction issue, and without the
-//     prefetch too few bytes are in flight to keep HBM busy (profiles/);
-//   * lane l takes elements 256k + 8l + j (two 128-bit shared loads per chunk; eight elements share
-//     one Philox call) and packs its own
-//     32 codes in registers: one tag word and PM words of base fields — the fixed-position part
-//     of the stream (PM+1 bits per element), stored with coalesced 32-bit row writes.  No
-//     __ballot_sync transposition: 6 votes per element cost more issue slots than the quantiser;
-//   * the variable part — XB extra bits per OUTLIER — is compacted per lane in registers, placed
-//     inside the warp tile by a shuffle prefix scan of the per-lane outlier counts (popc of the
-//     tag word), and placed in the tensor by a single-pass decoupled look-back over groups of CTA
-//     tiles (groups are numbered by an atomic ticket, so a group only ever waits for groups that
-//     are already running).  Placement is deterministic: the stream is byte-identical run to run;
-//   * the decoder needs no scan across tiles: the per-tile word offset is in the table.
+//     this one is quantised;
+//   * lane l takes elements 256k + 8l + j: a "chunk" k is eight consecutive values (two 128-bit
+//     shared loads, one Philox call);
+//   * the hot path (default 6/8-bit widths, power-of-two threshold, statistics in the normal
+//     range) never leaves the floating-point pipes: the quantiser's roundings are the reference's,
+//     and the PACKING is done with exact fp32 arithmetic too — U is split with a round-down FMA,
+//     the 5-bit fields are accumulated four to a float with FFMA2 (weights 32^j on a 2^23 bias, so
+//     the mantissa IS the packed word), the outliers' extra bits with a predicated E = 4E + ext and
+//     the tag bits with predicated adds.  Measured on the first version of this kernel: integer
+//     packing made the half-rate ALU pipe the limiter at 33 % of the HBM roofline (profiles/);
+//   * rare elements leave the hot path per chunk: |z| beyond what an outlier code can hold takes a
+//     clamp-and-count detour (the H1 rule), a zero/denormal/NaN quotient re-runs the chunk with
+//     IEEE division (generic_chunk);
+//   * the variable part — XB extra bits per OUTLIER — is placed inside the warp tile by a shuffle
+//     prefix scan of the per-lane bit counts and shared-memory atomicOr, then in the tensor by
+//     reduce-then-scan over three launches (no block ever waits for another).  Placement is
+//     deterministic: the stream is byte-identical run to run;
+//   * the decoder is a table lookup: every (class, U) pair has ONE decoded value per tensor, so
+//     each CTA evaluates the reference's inverse (smart.py:171-172,181-182, IEEE division) for the
+//     2^PM + 2^(PM+XB) possible fields into shared memory and the element loop is bit-field
+//     extraction + LDS + 256-bit stores.
 //
 // HBM roofline (6/8 bits, fraction f of outliers): encode reads 4 B and writes (6 + 2f)/8 B per
 // element; decode the reverse.  f = 0.165 on the benchmark input -> 4.79 B per element each way.
@@ -34,169 +51,246 @@ constexpr int kWarpTile = 1024;
 constexpr int kWarpsPerCta = 8;
 constexpr int kCtaTile = kWarpTile * kWarpsPerCta;
 constexpr int kPackThreads = 32 * kWarpsPerCta;
-constexpr uint32_t kMagic = 0x31425153u;  // 'SQB1'
+constexpr uint32_t kMagic = 0x32425153u;  // 'SQB2'
 
-// groups of lane-local elements that share one 32-bit extras accumulator: XB * (32 / G) <= 32
-__host__ __device__ constexpr int ext_groups(int xb) { return xb <= 1 ? 1 : xb <= 2 ? 2 : xb <= 4 ? 4 : 8; }
 // 32-bit words of extras a warp tile can need
 __host__ __device__ constexpr int seg_words(int xb) { return xb == 0 ? 1 : kWarpTile * xb / 32; }
 
-template <int PM>
-__device__ __forceinline__ void put_field(uint32_t (&bw)[PM], int i, uint32_t field) {
-  const int pos = PM * i, w = pos >> 5, sh = pos & 31;  // compile-time after unrolling
-  bw[w] += field << sh;                                  // fields never overlap: add == or (one LEA)
-  if (sh + PM > 32) bw[w + 1] += field >> (32 - sh);
-}
-template <int PM>
-__device__ __forceinline__ uint32_t get_field(const uint32_t (&bw)[PM], int i) {
-  const int pos = PM * i, w = pos >> 5, sh = pos & 31;
-  uint32_t v = bw[w] >> sh;
-  if (sh + PM > 32) v |= bw[w + 1] << (32 - sh);
-  return v & ((1u << PM) - 1u);
-}
-
-// What a lane accumulates for its 32 elements of one warp tile.
-template <int PM>
-struct LaneWords {
-  uint32_t tagw;      // bit i: element i is an outlier
-  uint32_t bw[PM];    // 32 base fields of PM bits
-  uint32_t ea[8];     // extras accumulators (ext_groups(XB) of them are used)
-  uint32_t ecnt[8];   // bits held by each
-  uint32_t n_sat;     // codes clipped at the field width / not a number
+// What one lane produces for one chunk (8 elements), as integers.
+//   half[0] / half[1]: the base fields of the even / odd elements of the chunk, 4 x PM bits each
+//                      (element j's field sits at bit PM * (j >> 1) of half[j & 1]);
+//   tag              : bit j = element j is an outlier;
+//   ext              : the outliers' ext fields, FIRST outlier in the MOST significant position
+//                      (XB * popc(tag) bits).
+struct ChunkBits {
+  uint32_t half[2];
+  uint32_t tag;
+  uint32_t ext;
 };
 
-// Integer side of one element: rounded code (fp32) -> stored payload; updates the lane's words.
-//   payload = (min(|code|, limit) << 1) | s,  s = sign bit of the code (main) / of z (outlier: lower side)
-// Branch-free: `m` is the all-ones/zero outlier mask, `zb` the bits of z.  F2I saturates large
-// codes and maps NaN to 0, which is the format's rule; `vmask` is zero for padding elements.
-template <int PM, int XB, bool kCheckNan>
-__device__ __forceinline__ void pack_element(int i, float code, uint32_t m, uint32_t zb, uint32_t vmask,
-                                             const uint32_t lim_main, const uint32_t lim_out, LaneWords<PM>& L) {
-  constexpr int EPG = 32 / ext_groups(XB);
-  const uint32_t a = (uint32_t)abs(__float2int_rz(code));
-  const uint32_t lim = (lim_out & m) | (lim_main & ~m);
-  const uint32_t mag = min(a, lim);
-  uint32_t cb = bits_of(code);
-  bool bad = a > lim;
-  if (kCheckNan) {  // exact path only: the fast path never sees a NaN code (it is flagged upstream)
-    const bool isnan_ = code != code;
-    bad = bad || isnan_;
-    cb = isnan_ ? 0u : cb;
+// ---- generic chunk: any width, IEEE division, padding, NaN — the literal operator sequence ------
+// (also the re-run of a hot chunk that met a zero / denormal / NaN quotient).  Out of line.
+template <int PM, int XB, bool kStochastic>
+__device__ __noinline__ void generic_chunk(const float* __restrict__ xv, const float* __restrict__ pv, int nvalid,
+                                           const Scalars& s, ChunkBits& out, uint32_t& n_sat) {
+  uint32_t h0 = 0, h1 = 0, tag = 0, ext = 0, sat = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t U = 1u << (PM + XB - 1);  // padding: S = 0
+    bool outlier = false;
+    if (j < nvalid) {
+      const float d = sub_rn(xv[j], s.mean);
+      const float z = true_div(d, s.div.b);                          // smart.py:154
+      const bool hi = z > s.thr, lo = z < s.neg_thr;                 // :155-156
+      outlier = hi || lo;                                            // :157
+      const float shift = hi ? s.shift_hi : (lo ? s.shift_lo : s.shift_mid);  // :159-161
+      const float range = outlier ? s.range_out.b : s.range_main.b;  // :162
+      float c = mul_rn(add_rn(z, shift), range);                     // :164
+      const float lim = outlier ? s.lim_out : s.lim_main;
+      const bool isn = c != c;
+      sat += (isn || fabsf(c) > lim) ? 1u : 0u;                      // H1: what the field cannot hold
+      c = isn ? 0.0f : fminf(fmaxf(c, -lim), lim);                   // clamping c == clamping the rounded code
+      float code;
+      if (kStochastic) {                                             // :93-98
+        const float f = floorf(c);
+        const float frac = sub_rn(c, f);
+        const float u = max_nan(add_rn(sub_rn(frac, pv[j]), 0.5f), 0.0f);
+        code = add_rn(f, rintf(u));
+      } else {
+        code = truncf(c);                                            // :169
+      }
+      const int below = (!isn && (bits_of(z) >> 31)) ? 1 : 0;        // sign BIT of z (so -0 counts as below)
+      U = (uint32_t)(__float2int_rz(code) - below + (1 << (PM + XB - 1)));
+    }
+    const uint32_t base = U & ((1u << PM) - 1u);
+    if (j & 1) h1 |= base << (PM * (j >> 1));
+    else h0 |= base << (PM * (j >> 1));
+    if (outlier) {
+      tag |= 1u << j;
+      if (XB > 0) ext = (ext << XB) | (U >> PM);
+    }
   }
-  const uint32_t sbit = ((zb & m) | (cb & ~m)) >> 31;
-  const uint32_t payload = ((mag << 1) | sbit) & vmask;
-  L.n_sat += (bad && vmask) ? 1u : 0u;
-  L.tagw |= m & vmask & (1u << i);
-  put_field<PM>(L.bw, i, payload & ((1u << PM) - 1u));
-  if (XB > 0) {
-    const int g = i / EPG;
-    L.ea[g] |= (payload >> PM) << L.ecnt[g];  // payload >> PM is 0 for a main element
-    L.ecnt[g] += m & vmask & (uint32_t)XB;
-  }
+  out.half[0] = h0;
+  out.half[1] = h1;
+  out.tag = tag;
+  out.ext = ext;
+  n_sat += sat;
 }
 
-// Exact (IEEE-divide) re-computation of one 4-element chunk: degenerate statistics or a flagged
-// chunk.  Out of line; the result comes back in registers.
-struct ExactChunk {
-  float4 code;
-  uint32_t cls;  // bit j: outlier; bit 4+j: z negative
+// ---- hot chunk (PM = 5, XB = 2) -------------------------------------------------------------------
+// Per-tensor constants of the hot path (registers; see make_hot for when it applies).
+struct Hot {
+  bool ok;
+  float mean, nb, r;     // z = (x - mean) / b in three packed instructions (div3): nb = -b, r = rn(1/b)
+  float thr, rm, ro;     // threshold, range_main, range_outlier
+  uint32_t kbits;        // bits of K = thr * range_outlier (exact)
+  float nhk;             // -0.5 / K: turns -+K (the sign of -z) into -+0.5
+  float z_lo, z_hi;      // outside [z_lo, z_hi] a chunk leaves the hot path
+  float lim_out;         // L_out
+  float off_mid;         // 2^(PO-1) - 0.5: U = code + off_mid +- 0.5
 };
-template <bool kStochastic>
-__device__ __noinline__ ExactChunk encode_chunk_exact(float4 v, float4 pr, const Scalars& s) {
-  PairClass k0, k1;
-  bool unused = false;
-  const f32x2 c01 = encode_pair<kStochastic, false>(pair(v.x, v.y), pair(pr.x, pr.y), s, k0, unused);
-  const f32x2 c23 = encode_pair<kStochastic, false>(pair(v.z, v.w), pair(pr.z, pr.w), s, k1, unused);
-  ExactChunk r;
-  r.code = make_float4(c01.x, c01.y, c23.x, c23.y);
-  r.cls = (k0.m0 & 1u) | (k0.m1 & 2u) | (k1.m0 & 4u) | (k1.m1 & 8u) | ((k0.zb0 >> 31) << 4) | ((k0.zb1 >> 31) << 5) |
-          ((k1.zb0 >> 31) << 6) | ((k1.zb1 >> 31) << 7);
+
+__device__ __forceinline__ Hot make_hot(const Scalars& s) {
+  Hot h;
+  h.mean = s.mean;
+  h.nb = -s.div.b;
+  h.r = s.div.r;
+  h.thr = s.thr;
+  h.rm = s.range_main.b;
+  h.ro = s.range_out.b;
+  const float K = mul_rn(s.thr, s.range_out.b);
+  h.kbits = bits_of(K);
+  h.nhk = true_div(-0.5f, K);
+  h.z_lo = 9.094947017729282e-13f;  // 2^-40
+  h.lim_out = s.lim_out;
+  h.off_mid = s.lim_out + 0.5f;  // L_out + 1 == 2^(PO-1)
+  // the largest |z| whose outlier code needs no clamp: fl(z * ro - K) <= L_out
+  float zh = true_div(add_rn(s.lim_out, K), s.range_out.b);
+  for (int it = 0; it < 4 && __fmaf_rn(zh, s.range_out.b, -K) > s.lim_out; ++it) zh = from_bits(bits_of(zh) - 1u);
+  h.z_hi = zh;
+  // (z -+ t) * ro == fma(z, ro, -+K) needs z -+ t exact: t a power of two (then exact for t < |z| < 2^24 t)
+  // and K = t * ro exact
+  const bool thr_pow2 = (bits_of(s.thr) & 0x007FFFFFu) == 0u;
+  const bool k_exact = __fmaf_rn(s.thr, s.range_out.b, -K) == 0.0f;
+  h.ok = s.fast && s.main_fits && thr_pow2 && k_exact && zh > s.thr && zh < 1e6f && K < 1e6f && K > 1e-6f &&
+         __fmaf_rn(zh, s.range_out.b, -K) <= s.lim_out;
+  return h;
+}
+
+__device__ __forceinline__ float min3_nan_abs(float a, float b, float c) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)));
   return r;
 }
+// copysign(min(|v|, lim), v): the H1 clamp in one instruction (FMNMX.XORSIGN)
+__device__ __forceinline__ float clamp_sym(float v, float lim) {
+  float r;
+  asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "f"(lim));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2_rm(f32x2 a, f32x2 b, f32x2 c) {  // round towards -infinity
+#if defined(__CUDA_ARCH__)
+  unsigned long long r;
+  asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pack2(a)), "l"(pack2(b)), "l"(pack2(c)));
+  return unpack2(r);
+#else
+  return pair(__fmaf_rd(a.x, b.x, c.x), __fmaf_rd(a.y, b.y, c.y));
+#endif
+}
 
-// One warp tile: quantise 1024 values and pack them into the lane's words.  `staged` points at the
-// tile in shared memory (TMA), or is null: direct global loads (unaligned tensors, the ragged
-// last tile).
-template <int PM, int XB, bool kStochastic, bool kHasProbs, bool kFast>
-__device__ __forceinline__ void encode_tile(const float* __restrict__ x, int64_t n, const float* __restrict__ probs,
-                                            const KernelParams& kp, const Scalars& s, const float4* staged,
-                                            int64_t base, LaneWords<PM>& L) {
-  const int lane = lane_id();
-  const uint32_t lim_main = (uint32_t)s.lim_main, lim_out = (uint32_t)s.lim_out;
-  L.tagw = 0;
-  L.n_sat = 0;
+// Eight elements: v0 | v1 in memory order; uniforms either explicit (p0 | p1) or the four Philox
+// words `rnd` (16 bits per element).  Returns false when the chunk must be re-run by generic_chunk.
+template <bool kStochastic, bool kHasProbs, bool kCountSat>
+__device__ __forceinline__ bool hot_chunk(const float4& v0, const float4& v1, const float4& p0, const float4& p1,
+                                          const uint4& rnd, const Hot& h, ChunkBits& out, f32x2& sat2) {
+  const f32x2 x[4] = {pair(v0.x, v0.y), pair(v0.z, v0.w), pair(v1.x, v1.y), pair(v1.z, v1.w)};
+  const f32x2 nmean2 = splat(-h.mean), nb2 = splat(h.nb), r2 = splat(h.r);
+  f32x2 z[4];
 #pragma unroll
-  for (int w = 0; w < PM; ++w) L.bw[w] = 0;
+  for (int q = 0; q < 4; ++q) {
+    const f32x2 d = add2(x[q], nmean2);            // x - mean
+    const f32x2 qq = mul2(d, r2);                  // div3: correctly rounded d / b     smart.py:154
+    const f32x2 e = fma2(qq, nb2, d);
+    z[q] = fma2(e, r2, qq);
+  }
+  // a zero, denormal-range or NaN quotient leaves the straight-line path
+  const float m1 = min3_nan_abs(z[0].x, z[0].y, z[1].x), m2 = min3_nan_abs(z[1].y, z[2].x, z[2].y);
+  const float amin = min_nan(min3_nan_abs(z[3].x, z[3].y, m1), m2);  // NaN if any quotient is
+  if (!(amin >= h.z_lo)) return false;
+  // class, scaled value and stored offset of each element                              :155-164
+  bool P[8];
+  float c[8];
+  f32x2 off[4];
+  const f32x2 rm2 = splat(h.rm);
 #pragma unroll
-  for (int g = 0; g < 8; ++g) { L.ea[g] = 0; L.ecnt[g] = 0; }
+  for (int q = 0; q < 4; ++q) {
+    const f32x2 cm = mul2(z[q], rm2);  // main: (z + 0) * range_main
+    // outlier: (z -+ t) * range_outlier == fma(z, ro, -+K), exactly (see make_hot)
+    const float k0 = from_bits((~bits_of(z[q].x) & 0x80000000u) | h.kbits);
+    const float k1 = from_bits((~bits_of(z[q].y) & 0x80000000u) | h.kbits);
+    off[q] = fma2(pair(k0, k1), splat(h.nhk), splat(h.off_mid));  // 2^(PO-1) - [z < 0]
+    P[2 * q] = fabsf(z[q].x) > h.thr;
+    P[2 * q + 1] = fabsf(z[q].y) > h.thr;
+    c[2 * q] = P[2 * q] ? __fmaf_rn(z[q].x, h.ro, k0) : cm.x;
+    c[2 * q + 1] = P[2 * q + 1] ? __fmaf_rn(z[q].y, h.ro, k1) : cm.y;
+  }
+  // H1: what an outlier field cannot hold is clamped (clamping c == clamping the rounded code; a main
+  // element's |c| <= L_main < L_out needs nothing)
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float a0 = clamp_sym(c[2 * q], h.lim_out), a1 = clamp_sym(c[2 * q + 1], h.lim_out);
+    if (kCountSat) sat2 = add2(sat2, pair(a0 != c[2 * q] ? 1.0f : 0.0f, a1 != c[2 * q + 1] ? 1.0f : 0.0f));
+    c[2 * q] = a0;
+    c[2 * q + 1] = a1;
+  }
 
-  const bool full = staged != nullptr;
-  const bool probs_vec = kStochastic && kHasProbs && full && aligned16(probs);
-  // lane l owns elements 256k + 8l + j of the tile (k = 0..3, j = 0..7): local index i = 8k + j
+  // rounding (:93-98 / :169), offset, split into base | ext, accumulation — all exact fp32
+  f32x2 acc = splat(8388608.0f);  // (even, odd) base fields on a 2^23 bias
+  float E = 0.0f, T = 8388608.0f;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int64_t e = base + 256 * k + 8 * lane;
-    float4 v[2], p4[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int64_t eh = e + 4 * h;
-      p4[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (full) v[h] = staged[64 * k + 2 * lane + h];
-      else v[h] = make_float4(eh < n ? x[eh] : 0.f, eh + 1 < n ? x[eh + 1] : 0.f, eh + 2 < n ? x[eh + 2] : 0.f,
-                              eh + 3 < n ? x[eh + 3] : 0.f);
-      if (kStochastic && kHasProbs) {
-        if (probs_vec) p4[h] = ldg_stream(reinterpret_cast<const float4*>(probs + eh));
-        else p4[h] = make_float4(eh < n ? probs[eh] : 0.f, eh + 1 < n ? probs[eh + 1] : 0.f,
-                                 eh + 2 < n ? probs[eh + 2] : 0.f, eh + 3 < n ? probs[eh + 3] : 0.f);
+  for (int q = 0; q < 4; ++q) {
+    const f32x2 c2 = pair(c[2 * q], c[2 * q + 1]);
+    f32x2 U;
+    if (kStochastic) {
+      const f32x2 f = pair(floorf(c2.x), floorf(c2.y));
+      const f32x2 frac = add2(c2, neg2(f));
+      f32x2 r;
+      if (kHasProbs) {
+        const float pa = q == 0 ? p0.x : q == 1 ? p0.z : q == 2 ? p1.x : p1.z;
+        const float pb = q == 0 ? p0.y : q == 1 ? p0.w : q == 2 ? p1.y : p1.w;
+        f32x2 u = add2(add2(frac, pair(-pa, -pb)), splat(0.5f));
+        u = pair(fmaxf(u.x, 0.0f), fmaxf(u.y, 0.0f));                                   // relu
+        r = add2(add2(u, splat(8388608.0f)), splat(-8388608.0f));                       // rint, 0 <= u < 2
+      } else {
+        // p = (k + 1/2) / 2^16 from 16 random bits k, built without a conversion: 2^23 + k by byte
+        // permute, then one FMA.  rint(relu((frac - p) + 0.5)) == 1  <=>  frac - p > 2^-25  (p > 0)
+        const uint32_t w = q == 0 ? rnd.x : q == 1 ? rnd.y : q == 2 ? rnd.z : rnd.w;
+        const f32x2 kf = pair(from_bits(__byte_perm(w, 0x4B000000u, 0x7610)), from_bits(__byte_perm(w, 0x4B000000u, 0x7632)));
+        const f32x2 p = fma2(kf, splat(1.52587890625e-05f), splat(-127.99999237060546875f));
+        const f32x2 t = add2(frac, neg2(p));
+        r = pair(t.x > 2.98023223876953125e-08f ? 1.0f : 0.0f, t.y > 2.98023223876953125e-08f ? 1.0f : 0.0f);
       }
-    }
-    if (kStochastic && !kHasProbs) {
-      const uint4 r = philox_group(kp.keys, (uint64_t)(e >> 3), kp.offset);
-      const f32x2 q0 = uniform16_pair(r.x), q1 = uniform16_pair(r.y), q2 = uniform16_pair(r.z), q3 = uniform16_pair(r.w);
-      p4[0] = make_float4(q0.x, q0.y, q1.x, q1.y);
-      p4[1] = make_float4(q2.x, q2.y, q3.x, q3.y);
-    }
-    bool suspect = false;
-    if (kFast && full) {
-      PairClass k0, k1, k2, k3;
-      const f32x2 c0 = encode_pair<kStochastic, true>(pair(v[0].x, v[0].y), pair(p4[0].x, p4[0].y), s, k0, suspect);
-      const f32x2 c1 = encode_pair<kStochastic, true>(pair(v[0].z, v[0].w), pair(p4[0].z, p4[0].w), s, k1, suspect);
-      const f32x2 c2 = encode_pair<kStochastic, true>(pair(v[1].x, v[1].y), pair(p4[1].x, p4[1].y), s, k2, suspect);
-      const f32x2 c3 = encode_pair<kStochastic, true>(pair(v[1].z, v[1].w), pair(p4[1].z, p4[1].w), s, k3, suspect);
-      if (!suspect) {  // the hot path: branch-free packing of eight elements
-        pack_element<PM, XB, false>(8 * k + 0, c0.x, k0.m0, k0.zb0, 0xFFFFFFFFu, lim_main, lim_out, L);
-        pack_element<PM, XB, false>(8 * k + 1, c0.y, k0.m1, k0.zb1, 0xFFFFFFFFu, lim_main, lim_out, L);
-        pack_element<PM, XB, false>(8 * k + 2, c1.x, k1.m0, k1.zb0, 0xFFFFFFFFu, lim_main, lim_out, L);
-        pack_element<PM, XB, false>(8 * k + 3, c1.y, k1.m1, k1.zb1, 0xFFFFFFFFu, lim_main, lim_out, L);
-        pack_element<PM, XB, false>(8 * k + 4, c2.x, k2.m0, k2.zb0, 0xFFFFFFFFu, lim_main, lim_out, L);
-        pack_element<PM, XB, false>(8 * k + 5, c2.y, k2.m1, k2.zb1, 0xFFFFFFFFu, lim_main, lim_out, L);
-        pack_element<PM, XB, false>(8 * k + 6, c3.x, k3.m0, k3.zb0, 0xFFFFFFFFu, lim_main, lim_out, L);
-        pack_element<PM, XB, false>(8 * k + 7, c3.y, k3.m1, k3.zb1, 0xFFFFFFFFu, lim_main, lim_out, L);
-      }
+      U = add2(add2(f, off[q]), r);
     } else {
-      suspect = true;
+      U = add2(pair(truncf(c2.x), truncf(c2.y)), off[q]);
     }
-    if (suspect) {  // rare: flagged chunk, degenerate statistics, or the ragged last tile
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const ExactChunk ex = encode_chunk_exact<kStochastic>(v[h], p4[h], s);
-        const float cj[4] = {ex.code.x, ex.code.y, ex.code.z, ex.code.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t vmask = (full || (e + 4 * h + j) < n) ? 0xFFFFFFFFu : 0u;
-          const uint32_t m = ((ex.cls >> j) & 1u) ? 0xFFFFFFFFu : 0u;
-          const uint32_t zb = ((ex.cls >> (4 + j)) & 1u) << 31;
-          pack_element<PM, XB, true>(8 * k + 4 * h + j, cj[j], m, zb, vmask, lim_main, lim_out, L);
-        }
-      }
+    const f32x2 hm = fma2_rm(U, splat(0.03125f), splat(8388608.0f));  // 2^23 + floor(U / 32)
+    const f32x2 ex = add2(hm, splat(-8388608.0f));                    // ext
+    const f32x2 lo = fma2(ex, splat(-32.0f), U);                      // base (a main element's ext is dropped)
+    const float wq = q == 0 ? 1.0f : q == 1 ? 32.0f : q == 2 ? 1024.0f : 32768.0f;
+    acc = fma2(lo, splat(wq), acc);
+    if (P[2 * q]) {
+      E = __fmaf_rn(E, 4.0f, ex.x);
+      T = T + (float)(1 << (2 * q));
     }
+    if (P[2 * q + 1]) {
+      E = __fmaf_rn(E, 4.0f, ex.y);
+      T = T + (float)(2 << (2 * q));
+    }
+  }
+  out.half[0] = bits_of(acc.x) & 0x007FFFFFu;
+  out.half[1] = bits_of(acc.y) & 0x007FFFFFu;
+  out.tag = bits_of(T) & 0xFFu;
+  out.ext = bits_of(E + 8388608.0f) & 0xFFFFu;
+  return true;
+}
+
+// ---- per-lane assembly of a warp tile's words from its four chunks ---------------------------------
+template <int PM>
+__device__ __forceinline__ void assemble_base(const ChunkBits (&ch)[4], uint32_t (&bw)[PM]) {
+  constexpr int H = 4 * PM;  // bits per half
+#pragma unroll
+  for (int w = 0; w < PM; ++w) bw[w] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t piece = ch[i >> 1].half[i & 1];
+    const int pos = i * H, w = pos >> 5, sh = pos & 31;  // compile-time after unrolling
+    bw[w] |= piece << sh;
+    if (sh + H > 32) bw[w + 1] |= piece >> (32 - sh);
   }
 }
 
 // ---- TMA bulk copy of one warp tile (4 KB, contiguous) into shared memory ----------------------
-// One lane issues cp.async.bulk; every lane of the warp waits on the warp's mbarrier.  The copy
-// is linear, so lane l finds its chunk k at float4 index 32k + l — the same coalesced mapping a
-// direct 128-bit load would use.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -235,7 +329,7 @@ constexpr int kEncodeDynSmem = kWarpsPerCta * kStages * kStageBytes + 1024;  // 
 // No kernel ever waits on another block, so nothing here can hang, and the placement is a pure
 // function of the input: the stream is byte-identical run to run.  (A single-pass decoupled
 // look-back was measured first: with ~450 groups resident, each group's look-back walk under full
-// HBM load cost ~10x its own compute time — profiles/r1_encode_lookback.txt.)
+// HBM load cost ~10x its own compute time.)
 struct EncodeScratch {
   uint32_t* group_words;  // [n_groups] extras words of each group
   uint32_t* group_nout;   // [n_groups] outliers
@@ -245,95 +339,203 @@ struct EncodeScratch {
   uint32_t* staging;      // [n_warp_tiles][seg_words(XB)] parked segments
 };
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// A chunk the hot path cannot take (or any chunk of a tile that is not hot): the literal sequence.
+template <int PM, int XB, bool kStochastic, bool kHasProbs>
+__device__ __forceinline__ void slow_chunk(const float4 (&v)[2], const float4 (&p4)[2], const uint4& rnd, int nvalid,
+                                           const Scalars& s, ChunkBits& out, uint32_t& n_sat) {
+  float xv[8] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w};
+  float pv[8] = {p4[0].x, p4[0].y, p4[0].z, p4[0].w, p4[1].x, p4[1].y, p4[1].z, p4[1].w};
+  if (kStochastic && !kHasProbs) {
+    pv[0] = uniform16(rnd.x, 0); pv[1] = uniform16(rnd.x, 1); pv[2] = uniform16(rnd.y, 0); pv[3] = uniform16(rnd.y, 1);
+    pv[4] = uniform16(rnd.z, 0); pv[5] = uniform16(rnd.z, 1); pv[6] = uniform16(rnd.w, 0); pv[7] = uniform16(rnd.w, 1);
+  }
+  generic_chunk<PM, XB, kStochastic>(xv, pv, nvalid, s, out, n_sat);
+}
+
+// One warp tile on the hot path: the tile is in shared memory at `stage` (TMA).
+template <bool kStochastic, bool kHasProbs, bool kCountSat>
+__device__ __forceinline__ void hot_tile(uint32_t stage, const float* __restrict__ probs, int64_t base, bool probs_vec,
+                                         const KernelParams& kp, const Scalars& s, const Hot& hot, ChunkBits (&ch)[4],
+                                         uint32_t& n_sat) {
+  const int lane = lane_id();
+  f32x2 sat2 = splat(0.0f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t e = base + 256 * k + 8 * lane;
+    float4 v[2], p4[2];
+    v[0] = lds128(stage + 1024 * k + 32 * lane);
+    v[1] = lds128(stage + 1024 * k + 32 * lane + 16);
+    p4[0] = p4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
+    if (kStochastic && kHasProbs) {
+      if (probs_vec) {
+        p4[0] = ldg_stream(reinterpret_cast<const float4*>(probs + e));
+        p4[1] = ldg_stream(reinterpret_cast<const float4*>(probs + e + 4));
+      } else {
+        p4[0] = make_float4(probs[e], probs[e + 1], probs[e + 2], probs[e + 3]);
+        p4[1] = make_float4(probs[e + 4], probs[e + 5], probs[e + 6], probs[e + 7]);
+      }
+    }
+    if (kStochastic && !kHasProbs) rnd = philox_group(kp.keys, (uint64_t)(e >> 3), kp.offset);
+    if (!hot_chunk<kStochastic, kHasProbs, kCountSat>(v[0], v[1], p4[0], p4[1], rnd, hot, ch[k], sat2))
+      slow_chunk<5, 2, kStochastic, kHasProbs>(v, p4, rnd, 8, s, ch[k], n_sat);
+  }
+  if (kCountSat) n_sat += (uint32_t)__float2int_rn(sat2.x + sat2.y);
+}
+
+// Any other warp tile (other widths, degenerate statistics, unaligned tensors, the ragged last
+// tile): direct global loads with bounds checks.
+template <int PM, int XB, bool kStochastic, bool kHasProbs>
+__device__ __noinline__ void generic_tile(const float* __restrict__ x, int64_t n, const float* __restrict__ probs,
+                                          const KernelParams& kp, const Scalars& s, int64_t base, ChunkBits (&ch)[4],
+                                          uint32_t& n_sat) {
+  const int lane = lane_id();
+  for (int k = 0; k < 4; ++k) {
+    const int64_t e = base + 256 * k + 8 * lane;
+    float4 v[2], p4[2];
+    uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t eh = e + 4 * h;
+      v[h] = make_float4(eh < n ? x[eh] : 0.f, eh + 1 < n ? x[eh + 1] : 0.f, eh + 2 < n ? x[eh + 2] : 0.f,
+                         eh + 3 < n ? x[eh + 3] : 0.f);
+      p4[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kStochastic && kHasProbs)
+        p4[h] = make_float4(eh < n ? probs[eh] : 0.f, eh + 1 < n ? probs[eh + 1] : 0.f, eh + 2 < n ? probs[eh + 2] : 0.f,
+                            eh + 3 < n ? probs[eh + 3] : 0.f);
+    }
+    if (kStochastic && !kHasProbs) rnd = philox_group(kp.keys, (uint64_t)(e >> 3), kp.offset);
+    const int64_t left = n - e;
+    slow_chunk<PM, XB, kStochastic, kHasProbs>(v, p4, rnd, left >= 8 ? 8 : (left > 0 ? (int)left : 0), s, ch[k], n_sat);
+  }
+}
+
 // Pass 1.  One CTA = one group of `rounds` consecutive CTA tiles (8 warp tiles each); each warp
 // runs through its `rounds` warp tiles on its own: while it quantises tile r out of shared
 // memory, TMA is already filling the other stage with tile r+1.  No block barrier in the loop.
-template <int PM, int XB, bool kStochastic, bool kHasProbs>
+template <int PM, int XB, bool kStochastic, bool kHasProbs, bool kCountSat>
 __global__ void __launch_bounds__(kPackThreads, 3)
     encode_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ mean_std,
                   const float* __restrict__ probs, const __grid_constant__ KernelParams kp,
                   uint32_t* __restrict__ planes, EncodeScratch sc, long long n_cta_tiles, int rounds, int aligned) {
-  constexpr int G = ext_groups(XB);
   constexpr int kSeg = seg_words(XB);
+  constexpr bool kCanHot = (PM == 5 && XB == 2);
   extern __shared__ unsigned char dyn_smem[];
-  __shared__ uint32_t s_seg[kWarpsPerCta][kSeg + 1];  // +1: spill word of the last atomicOr
+  __shared__ uint32_t s_seg[kWarpsPerCta][kSeg + 2];  // +2: spill words of the last atomicOr
   __shared__ uint32_t s_tot[3][kWarpsPerCta];
   __shared__ __align__(8) uint64_t s_bar[kWarpsPerCta][kStages];
 
   const int lane = lane_id(), warp = warp_id();
+  uint32_t* seg = s_seg[warp];
   if (lane == 0) {
 #pragma unroll
     for (int st = 0; st < kStages; ++st) mbar_init(&s_bar[warp][st], 1);
     mbar_fence_init();
   }
+  for (int j = lane; j < kSeg + 2; j += 32) seg[j] = 0;  // kept zero between tiles by the copy-out loop
   __syncwarp();
   const long long group = blockIdx.x;
   const long long first_tile = group * rounds;
   const int nrounds = (int)min((long long)rounds, n_cta_tiles - first_tile);
 
   // this warp's two 4 KB stages (1 KB aligned)
-  unsigned char* stage_base =
-      (unsigned char*)(((uintptr_t)dyn_smem + 1023) & ~(uintptr_t)1023) + (size_t)warp * kStages * kStageBytes;
+  const uint32_t stage0 = ((smem_u32(dyn_smem) + 1023u) & ~1023u) + (uint32_t)warp * kStages * kStageBytes;
+  const uint32_t bar0 = smem_u32(&s_bar[warp][0]);
 
   const Scalars s = scalars_from(mean_std[0], mean_std[1], kp);
-  auto tile_base = [&](int r) { return ((int64_t)(first_tile + r) * kWarpsPerCta + warp) * kWarpTile; };
-  // a warp tile is staged through TMA when it lies wholly inside the tensor and x is 16-byte aligned
-  auto tile_is_full = [&](int r) { return aligned && (tile_base(r) + kWarpTile <= n); };
+  const Hot hot = make_hot(s);
+  const bool tma_ok = kCanHot && aligned && hot.ok;  // warp tiles wholly inside the tensor are staged by TMA
+  const bool probs_vec = kStochastic && kHasProbs && aligned16(probs);
+  const int64_t base0 = ((int64_t)first_tile * kWarpsPerCta + warp) * kWarpTile;  // + r * kCtaTile
   auto issue = [&](int r) {
-    if (lane == 0 && tile_is_full(r))
-      tma_load_tile(stage_base + (r % kStages) * kStageBytes, x + tile_base(r), kStageBytes, &s_bar[warp][r % kStages]);
+    const int64_t b = base0 + (int64_t)r * kCtaTile;
+    if (lane == 0 && tma_ok && b + kWarpTile <= n) {
+      const uint32_t dst = stage0 + (r % kStages) * kStageBytes, bar = bar0 + 8 * (r % kStages);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kStageBytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "l"(x + b), "r"(kStageBytes), "r"(bar)
+                   : "memory");
+    }
   };
 
   issue(0);
   uint32_t n_out_total = 0, n_sat_total = 0, words_total = 0;
-  uint32_t* seg = s_seg[warp];
   for (int r = 0; r < nrounds; ++r) {
     if (r + 1 < nrounds) issue(r + 1);  // stage (r+1)%2 was fully consumed in round r-1 (__syncwarp below)
-    const int64_t base = tile_base(r);
+    const int64_t base = base0 + (int64_t)r * kCtaTile;
     if (base >= n) break;  // warp tiles past the end of the tensor: nothing stored (uniform per warp)
-    const int64_t wt = base / kWarpTile;
-    const float4* staged = nullptr;
-    if (tile_is_full(r)) {
+    const int64_t wt = base >> 10;
+    ChunkBits ch[4];
+    if (tma_ok && base + kWarpTile <= n) {
       mbar_wait(&s_bar[warp][r % kStages], (uint32_t)((r / kStages) & 1));
-      staged = reinterpret_cast<const float4*>(stage_base + (r % kStages) * kStageBytes);
+      if constexpr (kCanHot)
+        hot_tile<kStochastic, kHasProbs, kCountSat>(stage0 + (r % kStages) * kStageBytes, probs, base, probs_vec, kp, s, hot,
+                                                    ch, n_sat_total);
+    } else {
+      generic_tile<PM, XB, kStochastic, kHasProbs>(x, n, probs, kp, s, base, ch, n_sat_total);
     }
-    if (XB > 0) {
-      for (int j = lane; j < kSeg + 1; j += 32) seg[j] = 0;
-    }
-    LaneWords<PM> L;
-    if (s.fast) encode_tile<PM, XB, kStochastic, kHasProbs, true>(x, n, probs, kp, s, staged, base, L);
-    else encode_tile<PM, XB, kStochastic, kHasProbs, false>(x, n, probs, kp, s, staged, base, L);
-    __syncwarp();  // stage fully read (lane 0 may refill it); segment zeroing visible to the whole warp
+    __syncwarp();  // stage fully read (lane 0 may refill it)
 
     // fixed-position part of the stream: (1 + PM) rows of 32 words per warp tile, coalesced
+    uint32_t bw[PM];
+    assemble_base<PM>(ch, bw);
+    const uint32_t tagw = ch[0].tag | (ch[1].tag << 8) | (ch[2].tag << 16) | (ch[3].tag << 24);
     uint32_t* rec = planes + wt * (int64_t)((1 + PM) * 32) + lane;
-    rec[0] = L.tagw;
+    rec[0] = tagw;
 #pragma unroll
-    for (int w = 0; w < PM; ++w) rec[32 * (w + 1)] = L.bw[w];
+    for (int w = 0; w < PM; ++w) rec[32 * (w + 1)] = bw[w];
 
-    // variable part: the lane's extras go into this warp tile's word-aligned segment
-    const uint32_t n_out = __popc(L.tagw);
+    // variable part: the lane's extras (chunk groups in order, LSB-first) go into this warp tile's
+    // word-aligned segment
+    const uint32_t n_out = __popc(tagw);
     n_out_total += n_out;
-    n_sat_total += L.n_sat;
     if (XB > 0) {
       const uint32_t inc = warp_inclusive_scan(n_out * XB);
       uint32_t pos = inc - n_out * XB;
+      if (XB <= 2) {  // at most 64 bits per lane: one 64-bit string, two (rarely three) atomics
+        unsigned long long str = 0;
+        uint32_t len = 0;
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        if (L.ecnt[g]) {
+        for (int k = 0; k < 4; ++k) {
+          str |= (unsigned long long)ch[k].ext << len;
+          len += __popc(ch[k].tag) * XB;
+        }
+        if (len) {
           const uint32_t w = pos >> 5, sh = pos & 31;
-          atomicOr(&seg[w], L.ea[g] << sh);
-          if (sh + L.ecnt[g] > 32) atomicOr(&seg[w + 1], L.ea[g] >> (32 - sh));
-          pos += L.ecnt[g];
+          const uint32_t lo32 = (uint32_t)str, hi32 = (uint32_t)(str >> 32);
+          atomicOr(&seg[w], lo32 << sh);
+          const uint32_t mid = __funnelshift_l(lo32, hi32, sh);  // bits 32..63 of (str << sh)
+          if (sh + len > 32) atomicOr(&seg[w + 1], mid);
+          if (sh + len > 64) atomicOr(&seg[w + 2], sh ? (hi32 >> (32 - sh)) : 0u);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t len = __popc(ch[k].tag) * XB;  // <= 32
+          if (len) {
+            const uint32_t w = pos >> 5, sh = pos & 31;
+            atomicOr(&seg[w], ch[k].ext << sh);
+            if (sh + len > 32) atomicOr(&seg[w + 1], ch[k].ext >> (32 - sh));
+            pos += len;
+          }
         }
       }
       const uint32_t nwords = (__shfl_sync(0xffffffffu, inc, 31) + 31) >> 5;
       __syncwarp();
       uint32_t* park = sc.staging + wt * (int64_t)kSeg;
-      for (uint32_t j = lane; j < nwords; j += 32) park[j] = seg[j];
+      for (uint32_t j = lane; j < nwords; j += 32) {  // copy out and re-zero for the next tile
+        park[j] = seg[j];
+        seg[j] = 0;
+      }
       if (lane == 0) sc.seg_words[wt] = nwords;
       words_total += nwords;
-      __syncwarp();  // the copy is done before the next round zeroes the segment
+      __syncwarp();  // the segment is clean before the next round's atomics
     }
   }
 
@@ -360,7 +562,7 @@ __global__ void __launch_bounds__(1024) encode_scan_kernel(EncodeScratch sc, lon
                                                            uint32_t* __restrict__ table,
                                                            const float* __restrict__ mean_std,
                                                            const __grid_constant__ KernelParams kp, int64_t n,
-                                                           int stochastic) {
+                                                           int stochastic, int count_saturated) {
   __shared__ unsigned long long s_w[32], s_o[32], s_s[32];
   __shared__ unsigned long long s_carry[3];
   const int lane = lane_id(), warp = warp_id();
@@ -408,7 +610,7 @@ __global__ void __launch_bounds__(1024) encode_scan_kernel(EncodeScratch sc, lon
     hdr->clamp_hi = kp.clamp_hi;
     hdr->pad0 = 0.0f;
     hdr->n_outlier = s_carry[1];
-    hdr->n_saturated = s_carry[2];
+    hdr->n_saturated = count_saturated ? s_carry[2] : ~0ull;  // all ones: not counted
     hdr->extras_words = s_carry[0];
     hdr->status = 0;
     table[n_cta_tiles] = (uint32_t)s_carry[0];
@@ -449,68 +651,13 @@ __global__ void __launch_bounds__(kPackThreads) encode_place_kernel(EncodeScratc
 }
 
 // ---- decoder ----------------------------------------------------------------------------------------
-template <int PM, int XB, bool kFast, bool kAllPos>
-__device__ __forceinline__ void decode_tile(const uint32_t* __restrict__ seg, uint32_t pos, uint32_t tagw,
-                                            const uint32_t (&bw)[PM], const Scalars& s, float* __restrict__ y,
-                                            int64_t n, int64_t base, bool aligned) {
-  constexpr int G = ext_groups(XB);
-  constexpr int EPG = 32 / G;
-  const int lane = lane_id();
-  uint32_t win[G];
-  if (XB > 0) {
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const uint32_t gmask = (EPG == 32) ? 0xffffffffu : (((1u << EPG) - 1u) << (g * EPG));
-      const uint32_t cnt = __popc(tagw & gmask) * XB;
-      const uint32_t w = pos >> 5, sh = pos & 31;
-      win[g] = __funnelshift_r(seg[w], seg[w + 1], sh);
-      pos += cnt;
-    }
-  }
-  const uint32_t tb = bits_of(s.thr);
-  const bool full = aligned && (base + kWarpTile <= n);
-  // lane l owns elements 256k + 8l + j of the tile (k = 0..3, j = 0..7): local index i = 8k + j
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    float out[8];
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {  // four packed pairs
-      float code[2], shift[2], rb[2], rr[2];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int i = 8 * k + 2 * h + q;
-        const uint32_t m = 0u - ((tagw >> i) & 1u);  // outlier mask
-        uint32_t payload = get_field<PM>(bw, i);
-        if (XB > 0) {
-          const int g = i / EPG;
-          payload |= ((win[g] & ((1u << XB) - 1u)) << PM) & m;
-          win[g] >>= (m & (uint32_t)XB);
-        }
-        const uint32_t sb = payload << 31;  // s bit moved to the sign position
-        const float mag = (float)(payload >> 1);
-        code[q] = from_bits(bits_of(mag) | sb);               // -0.0 when s and mag == 0
-        shift[q] = from_bits(((sb ^ 0x80000000u) | tb) & m);  // -t above, +t below, +0 inside
-        rb[q] = select_f(m, s.range_out.b, s.range_main.b);
-        rr[q] = select_f(m, s.range_out.r, s.range_main.r);
-      }
-      bool unused = false;
-      const f32x2 yv = decode_pair<kFast, false>(pair(code[0], code[1]), pair(shift[0], shift[1]), pair(rb[0], rb[1]),
-                                                 pair(rr[0], rr[1]), s, kAllPos, unused);
-      out[2 * h] = yv.x;
-      out[2 * h + 1] = yv.y;
-    }
-    const int64_t e = base + 256 * k + 8 * lane;
-    if (full) {
-      f32x8 o;
-      o.a = make_float4(out[0], out[1], out[2], out[3]);
-      o.b = make_float4(out[4], out[5], out[6], out[7]);
-      stg_stream8(y + e, o);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (e + j < n) y[e + j] = out[j];
-    }
-  }
+// Field of local element j of chunk k inside the lane's PM-word base string.
+template <int PM>
+__device__ __forceinline__ uint32_t base_field(const uint32_t (&bw)[PM], int k, int j) {
+  const int pos = 8 * PM * k + 4 * PM * (j & 1) + PM * (j >> 1), w = pos >> 5, sh = pos & 31;  // compile time
+  uint32_t v = bw[w] >> sh;
+  if (sh + PM > 32) v |= bw[w + 1] << (32 - sh);
+  return v & ((1u << PM) - 1u);
 }
 
 template <int PM, int XB>
@@ -519,6 +666,8 @@ __global__ void __launch_bounds__(kPackThreads, 4)
                   const uint32_t* __restrict__ planes, const uint32_t* __restrict__ extras, float* __restrict__ y,
                   int64_t n, int all_positive, int aligned) {
   constexpr int kSeg = seg_words(XB);
+  constexpr int kMainEntries = 1 << PM, kOutEntries = 1 << (PM + XB);
+  __shared__ float s_lut[kMainEntries + kOutEntries];  // [main | outlier], indexed by the stored value U
   __shared__ uint32_t s_seg[kWarpsPerCta][kSeg + 2];
   __shared__ uint32_t s_warp[kWarpsPerCta];
   const long long tile = blockIdx.x;
@@ -526,8 +675,27 @@ __global__ void __launch_bounds__(kPackThreads, 4)
   const int64_t wt = (int64_t)tile * kWarpsPerCta + warp;
   const int64_t base = wt * kWarpTile;
 
-  const Scalars s = make_scalars(hdr->mean, hdr->std_raw, hdr->threshold, hdr->range_main, hdr->range_outlier,
-                                 hdr->clamp_lo, hdr->clamp_hi, hdr->bits_main, hdr->bits_outlier);
+  // The decoded value of every possible field, by the reference's own inverse (IEEE division).
+  {
+    const Scalars s = make_scalars(hdr->mean, hdr->std_raw, hdr->threshold, hdr->range_main, hdr->range_outlier,
+                                   hdr->clamp_lo, hdr->clamp_hi, hdr->bits_main, hdr->bits_outlier);
+    const bool stochastic = hdr->stochastic != 0;
+    for (int i = threadIdx.x; i < kMainEntries + kOutEntries; i += kPackThreads) {
+      // S from the field: two's complement (main) / offset binary (outlier)
+      const bool is_out = i >= kMainEntries;
+      const int v = is_out ? i - kMainEntries : i;
+      const int S = is_out ? v - (1 << (PM + XB - 1)) : (v >= (1 << (PM - 1)) && XB > 0 ? v - (1 << PM) : (XB > 0 ? v : v - (1 << (PM - 1))));
+      // S < 0: the lower side, code = S + 1; a zero code there is trunc's -0.0 (stochastic: -1 + 1 = +0)
+      float code = (float)(S < 0 ? S + 1 : S);
+      if (S == -1 && !stochastic) code = -0.0f;
+      const float shift = is_out ? (S < 0 ? s.shift_lo : s.shift_hi) : s.shift_mid;
+      const float rb = is_out ? s.range_out.b : s.range_main.b;
+      bool unused = false;
+      s_lut[i] = decode_pair<false, false>(pair(code, code), pair(shift, shift), pair(rb, rb), pair(1.0f, 1.0f), s,
+                                           all_positive != 0, unused).x;
+    }
+  }
+
   uint32_t tagw = 0, bw[PM];
 #pragma unroll
   for (int w = 0; w < PM; ++w) bw[w] = 0;
@@ -542,7 +710,7 @@ __global__ void __launch_bounds__(kPackThreads, 4)
   const uint32_t inc = warp_inclusive_scan(nb);
   const uint32_t my_words = (__shfl_sync(0xffffffffu, inc, 31) + 31) >> 5;
   if (lane == 0) s_warp[warp] = my_words;
-  __syncthreads();
+  __syncthreads();  // also publishes the table
   uint32_t seg_off = table[tile];
 #pragma unroll
   for (int w = 0; w < kWarpsPerCta; ++w) seg_off += (w < warp) ? s_warp[w] : 0u;
@@ -550,13 +718,44 @@ __global__ void __launch_bounds__(kPackThreads, 4)
   if (lane < 2) s_seg[warp][my_words + lane] = 0;
   __syncwarp();
   if (base >= n) return;
-  const uint32_t pos = inc - nb;
-  if (s.fast) {
-    if (all_positive) decode_tile<PM, XB, true, true>(s_seg[warp], pos, tagw, bw, s, y, n, base, aligned != 0);
-    else decode_tile<PM, XB, true, false>(s_seg[warp], pos, tagw, bw, s, y, n, base, aligned != 0);
-  } else {
-    if (all_positive) decode_tile<PM, XB, false, true>(s_seg[warp], pos, tagw, bw, s, y, n, base, aligned != 0);
-    else decode_tile<PM, XB, false, false>(s_seg[warp], pos, tagw, bw, s, y, n, base, aligned != 0);
+  uint32_t pos = inc - nb;
+  const uint32_t* seg = s_seg[warp];
+  const bool full = aligned && (base + kWarpTile <= n);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t tag = (tagw >> (8 * k)) & 0xFFu;
+    uint32_t win = 0;  // the chunk's ext group, first outlier in the top bits
+    if (XB > 0) {
+      const uint32_t len = __popc(tag) * XB;
+      const uint32_t raw = __funnelshift_r(seg[pos >> 5], seg[(pos >> 5) + 1], pos & 31);
+      win = len ? (raw << (32 - len)) : 0u;
+      pos += len;
+    }
+    float out[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t b = base_field<PM>(bw, k, j);
+      uint32_t idx = b;  // main: S in two's complement
+      if ((tag >> j) & 1u) {
+        idx = kMainEntries + b;
+        if (XB > 0) {
+          idx += (win >> (32 - XB)) << PM;
+          win <<= XB;
+        }
+      }
+      out[j] = s_lut[idx];
+    }
+    const int64_t e = base + 256 * k + 8 * lane;
+    if (full) {
+      f32x8 o;
+      o.a = make_float4(out[0], out[1], out[2], out[3]);
+      o.b = make_float4(out[4], out[5], out[6], out[7]);
+      stg_stream8(y + e, o);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (e + j < n) y[e + j] = out[j];
+    }
   }
 }
 
@@ -636,6 +835,7 @@ int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* p
   const int pm = params->bits_main - 1, xb = params->bits_outlier - params->bits_main;
   const bool st = params->stochastic != 0;
   const bool hp = st && probs != nullptr;
+  const bool cs = params->count_saturated != 0;
   const unsigned grid = (unsigned)n_groups;
   EncodeScratch sc;
   {
@@ -650,12 +850,13 @@ int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* p
 
 #define SMAQ_ENC_LAUNCH(PM_, XB_, ST_, HP_)                                                                        \
   {                                                                                                                \
-    auto kern = encode_kernel<PM_, XB_, ST_, HP_>;                                                                 \
+    auto kern = cs ? encode_kernel<PM_, XB_, ST_, HP_, true> : encode_kernel<PM_, XB_, ST_, HP_, false>;                                                                 \
     SMAQ_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncodeDynSmem));         \
     kern<<<grid, kPackThreads, kEncodeDynSmem, stream>>>(x, n, mean_std, probs, kp, planes, sc, l.n_cta_tiles,     \
                                                          rounds, aligned);                                         \
     SMAQ_LAUNCH_OK();                                                                                              \
-    encode_scan_kernel<<<1, 1024, 0, stream>>>(sc, n_groups, l.n_cta_tiles, hdr, table, mean_std, kp, n, ST_);     \
+    encode_scan_kernel<<<1, 1024, 0, stream>>>(sc, n_groups, l.n_cta_tiles, hdr, table, mean_std, kp, n, ST_,     \
+                                               cs ? 1 : 0);                                                        \
     encode_place_kernel<XB_><<<grid, kPackThreads, 0, stream>>>(sc, table, extras, l.n_cta_tiles, l.n_warp_tiles,  \
                                                                 rounds);                                           \
   }

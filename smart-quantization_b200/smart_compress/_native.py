@@ -39,7 +39,7 @@ class CodecParams(C.Structure):  # smaq_codec_params
         ("stochastic", C.c_int32),
         ("all_positive", C.c_int32),
         ("saturate", C.c_int32),
-        ("reserved", C.c_int32),
+        ("count_saturated", C.c_int32),
         ("seed", C.c_uint64),
         ("offset", C.c_uint64),
     ]

@@ -1,4 +1,4 @@
-"""The materialised SmaQ stream ("SQB1"): what ``SmartFP.encode`` returns and ``SmartFP.decode`` reads.
+"""The materialised SmaQ stream ("SQB2"): what ``SmartFP.encode`` returns and ``SmartFP.decode`` reads.
 
 Not in the reference (which only fake-quantises, smart.py:154-172); named by the build's north
 star.  The buffer lives in device memory; ``header()`` is the only call that synchronises."""

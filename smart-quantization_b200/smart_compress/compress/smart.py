@@ -74,6 +74,9 @@ class SmartFP(CompressionAlgorithmBase):
         p.stochastic = int(bool(hp.stochastic_rounding))
         p.all_positive = int(bool(all_positive))
         p.saturate = int(bool(saturate))
+        # the packed encoder counts what it clipped only when the size accounting is on (like the
+        # reference, which only pays for its accounting under --measure_compression_ratio, base.py:79)
+        p.count_saturated = int(bool(getattr(hp, "measure_compression_ratio", False)))
         # torch.manual_seed() governs the stream, as it governs the reference's rand_like
         p.seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
         p.offset = next(self._calls)

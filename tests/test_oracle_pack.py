@@ -37,8 +37,10 @@ def test_pack_decode_equals_saturated_roundtrip(n, cfgkw):
     xb = cfg.num_bits_outlier - cfg.num_bits_main
     assert p.planes.size * 32 == n_pad * cfg.num_bits_main
     assert 0 <= int(p.table[-1]) * 32 - xb * p.n_outlier < 32 * p.planes.shape[0] + 1  # < 32 pad bits per warp tile
-    assert p.n_saturated == int((res.code.abs() > torch.where(res.hi | res.lo, float(cfg.max_code_outlier),
-                                                               float(cfg.max_code_main))).sum())
+    # n_saturated is a pure function of the data: scaled values the field cannot hold
+    c = res.extras["c"]
+    assert p.n_saturated == int((c.abs() > torch.where(res.hi | res.lo, float(cfg.max_code_outlier),
+                                                        float(cfg.max_code_main))).sum())
 
 
 def test_negative_zero_code_survives_truncation():
@@ -56,10 +58,10 @@ def test_non_finite_codes_are_saturated_or_zeroed_and_counted():
     res = smaq_roundtrip(x, cfg, mean=torch.tensor(0.0), std=torch.tensor(1.0))
     p = opack.pack(res, cfg)
     assert p.n_saturated == 3
-    tag, s, mag = opack.unpack_codes(p)
-    assert tag[3] and mag[3] == 63 and s[3] == 0
-    assert tag[4] and mag[4] == 63 and s[4] == 1
-    assert not tag[5] and mag[5] == 0 and s[5] == 0
+    tag, S = opack.unpack_values(p)
+    assert tag[3] and S[3] == 63          # +inf: upper side, code 63
+    assert tag[4] and S[4] == -64         # -inf: lower side, code -63
+    assert not tag[5] and S[5] == 0       # NaN: main, code 0
 
 
 def test_lane_order_is_a_permutation():
