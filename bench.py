@@ -177,8 +177,8 @@ class Pipeline:
         self.packed = torch.empty(self.lay.total_capacity_bytes, dtype=torch.uint8, device=device)
         self.enc_ws = torch.empty(self.lay.workspace_bytes, dtype=torch.uint8, device=device)
         self.y = torch.empty(n, dtype=torch.float32, device=device)
-        # stats; encode = quantise+pack, scan of the per-group counts, placement of the extras; decode
-        self.launches_per_step = 5
+        # stats; encode = quantise+pack (its last CTA scans the per-group counts), placement of the extras; decode
+        self.launches_per_step = 4
         self.step_index = 0
 
     def stats(self, x):

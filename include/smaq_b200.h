@@ -63,7 +63,7 @@ typedef struct smaq_codec_params {
   int32_t count_saturated; /* packed encoder only: fill header.n_saturated (costs ~5 % of the encode
                            kernel; the plugin sets it under --measure_compression_ratio).  0: the
                            header field is all ones */
-  uint64_t seed;        /* Philox4x32-10 key, used when stochastic && probs == NULL */
+  uint64_t seed;        /* Philox4x32-7 key, used when stochastic && probs == NULL */
   uint64_t offset;      /* Philox stream offset (added to the counter's high words) */
 } smaq_codec_params;
 

@@ -44,6 +44,7 @@ def extra_flags(source: str):
         flags.append("-fmad=false")
     if os.environ.get("SMAQ_DEV") == "1":  # development builds: only the default 6/8-bit packed kernels
         flags.append("-DSMAQ_PACK_MINIMAL")
+    flags += os.environ.get("SMAQ_NVCC_EXTRA", "").split()  # experiments, e.g. -DSMAQ_PHILOX_ROUNDS=7
     return flags
 
 
@@ -58,6 +59,7 @@ def _digest(paths) -> str:
     h = hashlib.sha256()
     h.update(" ".join(NVCC_FLAGS).encode())
     h.update(os.environ.get("SMAQ_DEV", "0").encode())
+    h.update(os.environ.get("SMAQ_NVCC_EXTRA", "").encode())
     for p in sorted(paths):
         with open(p, "rb") as f:
             h.update(p.encode())

@@ -80,11 +80,17 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
   return v;
 }
 
-// ---- Philox4x32-10 (Salmon et al., SC'11): counter-based, so the random number of element i
+// ---- Philox4x32-7 (Salmon et al., SC'11): counter-based, so the random number of element i
 // depends only on (seed, offset, i) and never on the launch geometry.  The ten round keys are
 // derived from the seed on the host and travel in the kernel parameters: in SASS they are
 // constant-bank operands of the LOP3s, not per-round additions. -------------------------------
-constexpr int kPhiloxRounds = 10;
+// Seven rounds: the fewest for which Salmon et al. report Philox4x32 passing BigCrush (their
+// default of ten is a safety margin).  The numbers only decide stochastic-rounding ties; on these
+// issue-bound kernels three rounds are 4-5 % of the run time (profiles/).
+#ifndef SMAQ_PHILOX_ROUNDS
+#define SMAQ_PHILOX_ROUNDS 7
+#endif
+constexpr int kPhiloxRounds = SMAQ_PHILOX_ROUNDS;
 struct PhiloxKeys {
   uint32_t k0[kPhiloxRounds], k1[kPhiloxRounds];
 };

@@ -71,7 +71,7 @@ struct ChunkBits {
 // ---- generic chunk: any width, IEEE division, padding, NaN — the literal operator sequence ------
 // (also the re-run of a hot chunk that met a zero / denormal / NaN quotient).  Out of line.
 template <int PM, int XB, bool kStochastic>
-__device__ __noinline__ void generic_chunk(const float* __restrict__ xv, const float* __restrict__ pv, int nvalid,
+__device__ __forceinline__ void generic_chunk(const float* __restrict__ xv, const float* __restrict__ pv, int nvalid,
                                            const Scalars& s, ChunkBits& out, uint32_t& n_sat) {
   uint32_t h0 = 0, h1 = 0, tag = 0, ext = 0, sat = 0;
 #pragma unroll
@@ -330,15 +330,39 @@ constexpr int kEncodeDynSmem = kWarpsPerCta * kStages * kStageBytes + 1024;  // 
 // function of the input: the stream is byte-identical run to run.  (A single-pass decoupled
 // look-back was measured first: with ~450 groups resident, each group's look-back walk under full
 // HBM load cost ~10x its own compute time.)
+constexpr int kSuperShift = 6;  // groups per super-group = 64
+
 struct EncodeScratch {
-  uint32_t* group_words;  // [n_groups] extras words of each group
-  uint32_t* group_nout;   // [n_groups] outliers
-  uint32_t* group_nsat;   // [n_groups] clipped / NaN codes
-  uint32_t* group_off;    // [n_groups] exclusive prefix of group_words (pass 2)
+  uint32_t* group_words;  // [n_groups] extras words of each group (a group = one CTA of pass 1: <= 32 warp tiles)
   uint32_t* seg_words;    // [n_warp_tiles] words of each warp tile's segment
   uint32_t* staging;      // [n_warp_tiles][seg_words(XB)] parked segments
+  uint32_t* super_off;    // [n_super] exclusive prefix of super_words (written by the last CTA of pass 1)
+  // ---- zero on entry (one memset per call) ----
+  unsigned int* ticket;         // CTAs that have finished pass 1
+  unsigned long long* totals;   // [2] outliers, clipped / NaN codes (integer atomics: order-independent)
+  uint32_t* super_words;        // [n_super] extras words of each run of 64 groups
 };
 
+// What the last CTA of pass 1 needs to finish the header.
+struct HeaderArgs {
+  smaq_packed_header* hdr;
+  uint32_t* table;
+  long long n_super, n_cta_tiles;
+  int64_t n;
+  int stochastic, count_saturated;
+};
+
+__device__ __forceinline__ void red_or_shared(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -346,34 +370,49 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 }
 
 // A chunk the hot path cannot take (or any chunk of a tile that is not hot): the literal sequence.
+// Out of line, arguments and result by value (registers), so that none of its set-up is scheduled
+// into the hot path.  Returns (half0, half1, tag | n_saturated << 8, ext).
 template <int PM, int XB, bool kStochastic, bool kHasProbs>
-__device__ __forceinline__ void slow_chunk(const float4 (&v)[2], const float4 (&p4)[2], const uint4& rnd, int nvalid,
-                                           const Scalars& s, ChunkBits& out, uint32_t& n_sat) {
-  float xv[8] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w};
-  float pv[8] = {p4[0].x, p4[0].y, p4[0].z, p4[0].w, p4[1].x, p4[1].y, p4[1].z, p4[1].w};
+__device__ __noinline__ uint4 slow_chunk(float4 v0, float4 v1, float4 p0, float4 p1, uint4 rnd, int nvalid,
+                                         const Scalars* s) {
+  float xv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+  float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
   if (kStochastic && !kHasProbs) {
     pv[0] = uniform16(rnd.x, 0); pv[1] = uniform16(rnd.x, 1); pv[2] = uniform16(rnd.y, 0); pv[3] = uniform16(rnd.y, 1);
     pv[4] = uniform16(rnd.z, 0); pv[5] = uniform16(rnd.z, 1); pv[6] = uniform16(rnd.w, 0); pv[7] = uniform16(rnd.w, 1);
   }
-  generic_chunk<PM, XB, kStochastic>(xv, pv, nvalid, s, out, n_sat);
+  ChunkBits out;
+  uint32_t n_sat = 0;
+  generic_chunk<PM, XB, kStochastic>(xv, pv, nvalid, *s, out, n_sat);
+  return make_uint4(out.half[0], out.half[1], out.tag | (n_sat << 8), out.ext);
+}
+__device__ __forceinline__ void take_slow(const uint4& r, ChunkBits& out, uint32_t& n_sat) {
+  out.half[0] = r.x;
+  out.half[1] = r.y;
+  out.tag = r.z & 0xFFu;
+  out.ext = r.w;
+  n_sat += r.z >> 8;
 }
 
 // One warp tile on the hot path: the tile is in shared memory at `stage` (TMA).
 template <bool kStochastic, bool kHasProbs, bool kCountSat>
-__device__ __forceinline__ void hot_tile(uint32_t stage, const float* __restrict__ probs, int64_t base, bool probs_vec,
+__device__ __forceinline__ void hot_tile(uint32_t stage, const float* __restrict__ probs, int64_t wt, bool probs_vec,
                                          const KernelParams& kp, const Scalars& s, const Hot& hot, ChunkBits (&ch)[4],
                                          uint32_t& n_sat) {
   const int lane = lane_id();
   f32x2 sat2 = splat(0.0f);
+  // Philox counter of a chunk = index of its first element / 8 = 128 wt + 32 k + lane
+  const uint32_t g_lo = ((uint32_t)wt << 7) | (uint32_t)lane, g_hi = (uint32_t)((uint64_t)wt >> 25);
+  const uint32_t lane_addr = stage + 32 * lane;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int64_t e = base + 256 * k + 8 * lane;
     float4 v[2], p4[2];
-    v[0] = lds128(stage + 1024 * k + 32 * lane);
-    v[1] = lds128(stage + 1024 * k + 32 * lane + 16);
+    v[0] = lds128(lane_addr + 1024 * k);
+    v[1] = lds128(lane_addr + 1024 * k + 16);
     p4[0] = p4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
     if (kStochastic && kHasProbs) {
+      const int64_t e = wt * kWarpTile + 256 * k + 8 * lane;
       if (probs_vec) {
         p4[0] = ldg_stream(reinterpret_cast<const float4*>(probs + e));
         p4[1] = ldg_stream(reinterpret_cast<const float4*>(probs + e + 4));
@@ -382,9 +421,10 @@ __device__ __forceinline__ void hot_tile(uint32_t stage, const float* __restrict
         p4[1] = make_float4(probs[e + 4], probs[e + 5], probs[e + 6], probs[e + 7]);
       }
     }
-    if (kStochastic && !kHasProbs) rnd = philox_group(kp.keys, (uint64_t)(e >> 3), kp.offset);
+    if (kStochastic && !kHasProbs)
+      rnd = philox4x32(kp.keys, g_lo + 32u * k, g_hi, (uint32_t)kp.offset, (uint32_t)(kp.offset >> 32));
     if (!hot_chunk<kStochastic, kHasProbs, kCountSat>(v[0], v[1], p4[0], p4[1], rnd, hot, ch[k], sat2))
-      slow_chunk<5, 2, kStochastic, kHasProbs>(v, p4, rnd, 8, s, ch[k], n_sat);
+      take_slow(slow_chunk<5, 2, kStochastic, kHasProbs>(v[0], v[1], p4[0], p4[1], rnd, 8, &s), ch[k], n_sat);
   }
   if (kCountSat) n_sat += (uint32_t)__float2int_rn(sat2.x + sat2.y);
 }
@@ -392,7 +432,7 @@ __device__ __forceinline__ void hot_tile(uint32_t stage, const float* __restrict
 // Any other warp tile (other widths, degenerate statistics, unaligned tensors, the ragged last
 // tile): direct global loads with bounds checks.
 template <int PM, int XB, bool kStochastic, bool kHasProbs>
-__device__ __noinline__ void generic_tile(const float* __restrict__ x, int64_t n, const float* __restrict__ probs,
+__device__ __forceinline__ void generic_tile(const float* __restrict__ x, int64_t n, const float* __restrict__ probs,
                                           const KernelParams& kp, const Scalars& s, int64_t base, ChunkBits (&ch)[4],
                                           uint32_t& n_sat) {
   const int lane = lane_id();
@@ -412,7 +452,63 @@ __device__ __noinline__ void generic_tile(const float* __restrict__ x, int64_t n
     }
     if (kStochastic && !kHasProbs) rnd = philox_group(kp.keys, (uint64_t)(e >> 3), kp.offset);
     const int64_t left = n - e;
-    slow_chunk<PM, XB, kStochastic, kHasProbs>(v, p4, rnd, left >= 8 ? 8 : (left > 0 ? (int)left : 0), s, ch[k], n_sat);
+    take_slow(slow_chunk<PM, XB, kStochastic, kHasProbs>(v[0], v[1], p4[0], p4[1], rnd,
+                                                         left >= 8 ? 8 : (left > 0 ? (int)left : 0), &s), ch[k], n_sat);
+  }
+}
+
+// Pass 2, run by the LAST CTA of pass 1 to finish (atomic ticket): exclusive scan of the
+// super-group word counts (n / 2 Mi entries), header.
+__device__ __forceinline__ void finish_stream(const EncodeScratch& sc, const HeaderArgs& ha,
+                                              const float* __restrict__ mean_std, const KernelParams& kp) {
+  __shared__ uint32_t s_part[kWarpsPerCta];
+  __shared__ uint32_t s_carry;
+  const int lane = lane_id(), warp = warp_id();
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (long long base = 0; base < ha.n_super; base += kPackThreads) {
+    const long long i = base + threadIdx.x;
+    const uint32_t w = i < ha.n_super ? __ldcg(sc.super_words + i) : 0u;
+    const uint32_t inc = warp_inclusive_scan(w);
+    if (lane == 31) s_part[warp] = inc;
+    __syncthreads();
+    uint32_t before = s_carry, all = 0;
+#pragma unroll
+    for (int k = 0; k < kWarpsPerCta; ++k) {
+      before += k < warp ? s_part[k] : 0u;
+      all += s_part[k];
+    }
+    if (i < ha.n_super) {
+      sc.super_off[i] = before + inc - w;
+      sc.super_words[i] = 0;  // leave the workspace reusable
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += all;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    smaq_packed_header* hdr = ha.hdr;
+    hdr->magic = kMagic;
+    hdr->bits_main = kp.bits_main;
+    hdr->bits_outlier = kp.bits_outlier;
+    hdr->stochastic = ha.stochastic;
+    hdr->n = ha.n;
+    hdr->mean = mean_std[0];
+    hdr->std_raw = mean_std[1];
+    hdr->threshold = kp.thr;
+    hdr->range_main = kp.range_main;
+    hdr->range_outlier = kp.range_out;
+    hdr->clamp_lo = kp.clamp_lo;
+    hdr->clamp_hi = kp.clamp_hi;
+    hdr->pad0 = 0.0f;
+    hdr->n_outlier = __ldcg(sc.totals);
+    hdr->n_saturated = ha.count_saturated ? __ldcg(sc.totals + 1) : ~0ull;  // all ones: not counted
+    hdr->extras_words = s_carry;
+    hdr->status = 0;
+    ha.table[ha.n_cta_tiles] = s_carry;
+    sc.totals[0] = 0;
+    sc.totals[1] = 0;
+    *sc.ticket = 0;
   }
 }
 
@@ -423,7 +519,8 @@ template <int PM, int XB, bool kStochastic, bool kHasProbs, bool kCountSat>
 __global__ void __launch_bounds__(kPackThreads, 3)
     encode_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ mean_std,
                   const float* __restrict__ probs, const __grid_constant__ KernelParams kp,
-                  uint32_t* __restrict__ planes, EncodeScratch sc, long long n_cta_tiles, int rounds, int aligned) {
+                  uint32_t* __restrict__ planes, EncodeScratch sc, long long n_cta_tiles, int rounds, int aligned,
+                  HeaderArgs ha) {
   constexpr int kSeg = seg_words(XB);
   constexpr bool kCanHot = (PM == 5 && XB == 2);
   extern __shared__ unsigned char dyn_smem[];
@@ -432,13 +529,13 @@ __global__ void __launch_bounds__(kPackThreads, 3)
   __shared__ __align__(8) uint64_t s_bar[kWarpsPerCta][kStages];
 
   const int lane = lane_id(), warp = warp_id();
-  uint32_t* seg = s_seg[warp];
+  const uint32_t seg_addr = smem_u32(&s_seg[warp][0]);
   if (lane == 0) {
 #pragma unroll
     for (int st = 0; st < kStages; ++st) mbar_init(&s_bar[warp][st], 1);
     mbar_fence_init();
   }
-  for (int j = lane; j < kSeg + 2; j += 32) seg[j] = 0;  // kept zero between tiles by the copy-out loop
+  for (int j = lane; j < kSeg + 2; j += 32) sts32(seg_addr + 4 * j, 0u);  // kept zero between tiles by the copy-out loop
   __syncwarp();
   const long long group = blockIdx.x;
   const long long first_tile = group * rounds;
@@ -448,8 +545,16 @@ __global__ void __launch_bounds__(kPackThreads, 3)
   const uint32_t stage0 = ((smem_u32(dyn_smem) + 1023u) & ~1023u) + (uint32_t)warp * kStages * kStageBytes;
   const uint32_t bar0 = smem_u32(&s_bar[warp][0]);
 
-  const Scalars s = scalars_from(mean_std[0], mean_std[1], kp);
-  const Hot hot = make_hot(s);
+  // per-tensor constants: derived once per CTA (IEEE divisions, a search loop) and broadcast
+  __shared__ Scalars s_scalars;
+  __shared__ Hot s_hot;
+  if (threadIdx.x == 0) {
+    s_scalars = scalars_from(mean_std[0], mean_std[1], kp);
+    s_hot = make_hot(s_scalars);
+  }
+  __syncthreads();
+  const Scalars s = s_scalars;
+  const Hot hot = s_hot;
   const bool tma_ok = kCanHot && aligned && hot.ok;  // warp tiles wholly inside the tensor are staged by TMA
   const bool probs_vec = kStochastic && kHasProbs && aligned16(probs);
   const int64_t base0 = ((int64_t)first_tile * kWarpsPerCta + warp) * kWarpTile;  // + r * kCtaTile
@@ -475,7 +580,7 @@ __global__ void __launch_bounds__(kPackThreads, 3)
     if (tma_ok && base + kWarpTile <= n) {
       mbar_wait(&s_bar[warp][r % kStages], (uint32_t)((r / kStages) & 1));
       if constexpr (kCanHot)
-        hot_tile<kStochastic, kHasProbs, kCountSat>(stage0 + (r % kStages) * kStageBytes, probs, base, probs_vec, kp, s, hot,
+        hot_tile<kStochastic, kHasProbs, kCountSat>(stage0 + (r % kStages) * kStageBytes, probs, wt, probs_vec, kp, s, hot,
                                                     ch, n_sat_total);
     } else {
       generic_tile<PM, XB, kStochastic, kHasProbs>(x, n, probs, kp, s, base, ch, n_sat_total);
@@ -507,31 +612,33 @@ __global__ void __launch_bounds__(kPackThreads, 3)
           len += __popc(ch[k].tag) * XB;
         }
         if (len) {
-          const uint32_t w = pos >> 5, sh = pos & 31;
+          const uint32_t wa = seg_addr + ((pos >> 5) << 2), sh = pos & 31;
           const uint32_t lo32 = (uint32_t)str, hi32 = (uint32_t)(str >> 32);
-          atomicOr(&seg[w], lo32 << sh);
-          const uint32_t mid = __funnelshift_l(lo32, hi32, sh);  // bits 32..63 of (str << sh)
-          if (sh + len > 32) atomicOr(&seg[w + 1], mid);
-          if (sh + len > 64) atomicOr(&seg[w + 2], sh ? (hi32 >> (32 - sh)) : 0u);
+          red_or_shared(wa, lo32 << sh);
+          if (sh + len > 32) red_or_shared(wa + 4, __funnelshift_l(lo32, hi32, sh));  // bits 32..63 of (str << sh)
+          if (sh + len > 64) red_or_shared(wa + 8, hi32 >> (32 - sh));               // sh > 0 here
         }
       } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint32_t len = __popc(ch[k].tag) * XB;  // <= 32
           if (len) {
-            const uint32_t w = pos >> 5, sh = pos & 31;
-            atomicOr(&seg[w], ch[k].ext << sh);
-            if (sh + len > 32) atomicOr(&seg[w + 1], ch[k].ext >> (32 - sh));
+            const uint32_t wa = seg_addr + ((pos >> 5) << 2), sh = pos & 31;
+            red_or_shared(wa, ch[k].ext << sh);
+            if (sh + len > 32) red_or_shared(wa + 4, ch[k].ext >> (32 - sh));
             pos += len;
           }
         }
       }
-      const uint32_t nwords = (__shfl_sync(0xffffffffu, inc, 31) + 31) >> 5;
+      const uint32_t nwords = (__shfl_sync(0xffffffffu, inc, 31) + 31) >> 5;  // <= kSeg <= 128
       __syncwarp();
-      uint32_t* park = sc.staging + wt * (int64_t)kSeg;
-      for (uint32_t j = lane; j < nwords; j += 32) {  // copy out and re-zero for the next tile
-        park[j] = seg[j];
-        seg[j] = 0;
+      uint32_t* park = sc.staging + wt * (int64_t)kSeg + lane;
+#pragma unroll
+      for (int j = 0; j < (kSeg + 31) / 32; ++j) {  // copy out and re-zero for the next tile
+        if ((uint32_t)(32 * j + lane) < nwords) {
+          park[32 * j] = lds32(seg_addr + 4 * (32 * j + lane));
+          sts32(seg_addr + 4 * (32 * j + lane), 0u);
+        }
       }
       if (lane == 0) sc.seg_words[wt] = nwords;
       words_total += nwords;
@@ -539,7 +646,8 @@ __global__ void __launch_bounds__(kPackThreads, 3)
     }
   }
 
-  // per-group totals (plain stores: no atomics, no pre-zeroed memory)
+  // totals of this CTA's group: the group's word count is stored, and added (integer atomics:
+  // order-independent, so the stream stays deterministic) to its super-group's and the tensor's
   const uint32_t w_out = warp_sum(n_out_total), w_sat = warp_sum(n_sat_total);
   if (lane == 0) {
     s_tot[0][warp] = words_total;
@@ -547,83 +655,35 @@ __global__ void __launch_bounds__(kPackThreads, 3)
     s_tot[2][warp] = w_sat;
   }
   __syncthreads();
+  __shared__ bool s_last;
   if (threadIdx.x < 3) {
     uint32_t t = 0;
 #pragma unroll
     for (int w = 0; w < kWarpsPerCta; ++w) t += s_tot[threadIdx.x][w];
-    uint32_t* dst = threadIdx.x == 0 ? sc.group_words : threadIdx.x == 1 ? sc.group_nout : sc.group_nsat;
-    dst[group] = t;
-  }
-}
-
-// Pass 2: one block scans the per-group word counts and finishes the header.
-__global__ void __launch_bounds__(1024) encode_scan_kernel(EncodeScratch sc, long long n_groups, long long n_cta_tiles,
-                                                           smaq_packed_header* __restrict__ hdr,
-                                                           uint32_t* __restrict__ table,
-                                                           const float* __restrict__ mean_std,
-                                                           const __grid_constant__ KernelParams kp, int64_t n,
-                                                           int stochastic, int count_saturated) {
-  __shared__ unsigned long long s_w[32], s_o[32], s_s[32];
-  __shared__ unsigned long long s_carry[3];
-  const int lane = lane_id(), warp = warp_id();
-  if (threadIdx.x < 3) s_carry[threadIdx.x] = 0;
-  __syncthreads();
-  for (long long base = 0; base < n_groups; base += 1024) {
-    const long long g = base + threadIdx.x;
-    const unsigned long long w = g < n_groups ? sc.group_words[g] : 0ull;
-    const unsigned long long o = g < n_groups ? sc.group_nout[g] : 0ull;
-    const unsigned long long sa = g < n_groups ? sc.group_nsat[g] : 0ull;
-    // inclusive scan of w inside the warp; plain sums of o and sa
-    unsigned long long inc = w;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += t;
-    }
-    const unsigned long long so = warp_sum(o), ss = warp_sum(sa);
-    if (lane == 31) s_w[warp] = inc;
-    if (lane == 0) { s_o[warp] = so; s_s[warp] = ss; }
-    __syncthreads();
-    unsigned long long before = s_carry[0];
-    for (int i = 0; i < warp; ++i) before += s_w[i];
-    if (g < n_groups) sc.group_off[g] = (uint32_t)(before + inc - w);
-    __syncthreads();
     if (threadIdx.x == 0) {
-      unsigned long long tw = 0, to = 0, ts = 0;
-      for (int i = 0; i < 32; ++i) { tw += s_w[i]; to += s_o[i]; ts += s_s[i]; }
-      s_carry[0] += tw; s_carry[1] += to; s_carry[2] += ts;
+      sc.group_words[group] = t;
+      atomicAdd(sc.super_words + (group >> kSuperShift), t);
+    } else {
+      atomicAdd(sc.totals + (threadIdx.x - 1), (unsigned long long)t);
     }
-    __syncthreads();
+    __threadfence();  // the totals are visible before the ticket is
   }
-  if (threadIdx.x == 0) {
-    hdr->magic = kMagic;
-    hdr->bits_main = kp.bits_main;
-    hdr->bits_outlier = kp.bits_outlier;
-    hdr->stochastic = stochastic;
-    hdr->n = n;
-    hdr->mean = mean_std[0];
-    hdr->std_raw = mean_std[1];
-    hdr->threshold = kp.thr;
-    hdr->range_main = kp.range_main;
-    hdr->range_outlier = kp.range_out;
-    hdr->clamp_lo = kp.clamp_lo;
-    hdr->clamp_hi = kp.clamp_hi;
-    hdr->pad0 = 0.0f;
-    hdr->n_outlier = s_carry[1];
-    hdr->n_saturated = count_saturated ? s_carry[2] : ~0ull;  // all ones: not counted
-    hdr->extras_words = s_carry[0];
-    hdr->status = 0;
-    table[n_cta_tiles] = (uint32_t)s_carry[0];
-  }
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(sc.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last) finish_stream(sc, ha, mean_std, kp);
 }
 
-// Pass 3: move every parked segment to its dense position and write the per-CTA-tile table.
+// Pass 3: move every parked segment to its dense position and write the per-CTA-tile table.  One
+// CTA per group (<= 32 warp tiles); eight threads per segment, every load issued before the first
+// store: the pass is latency-bound (three dependent memory round trips), not bandwidth-bound.
 template <int XB>
 __global__ void __launch_bounds__(kPackThreads) encode_place_kernel(EncodeScratch sc, uint32_t* __restrict__ table,
                                                                     uint32_t* __restrict__ extras,
                                                                     long long n_cta_tiles, long long n_warp_tiles,
                                                                     int rounds) {
   constexpr int kSeg = seg_words(XB);
+  constexpr int kPerThread = (kSeg + 7) / 8;
   __shared__ uint32_t s_off[kMaxRounds * kWarpsPerCta + 1];
   const int lane = lane_id(), warp = warp_id();
   const long long group = blockIdx.x;
@@ -632,17 +692,27 @@ __global__ void __launch_bounds__(kPackThreads) encode_place_kernel(EncodeScratc
   if (warp == 0) {
     const long long wt = first_wt + lane;
     const uint32_t wds = (lane < nseg && wt < n_warp_tiles) ? sc.seg_words[wt] : 0u;
+    // this group's offset: its super-group's + the groups before it inside the super-group (<= 63)
+    const long long sg0 = (group >> kSuperShift) << kSuperShift;
+    uint32_t part = (sg0 + lane < group ? sc.group_words[sg0 + lane] : 0u) +
+                    (sg0 + 32 + lane < group ? sc.group_words[sg0 + 32 + lane] : 0u);
+    const uint32_t goff = sc.super_off[group >> kSuperShift] + warp_sum(part);
     const uint32_t inc = warp_inclusive_scan(wds);
-    s_off[lane] = sc.group_off[group] + inc - wds;
-    if (lane == 31) s_off[32] = sc.group_off[group] + inc;
+    s_off[lane] = goff + inc - wds;
+    if (lane == 31) s_off[32] = goff + inc;
   }
   __syncthreads();
-  for (int i = warp; i < nseg; i += kWarpsPerCta) {
-    const long long wt = first_wt + i;
-    if (wt >= n_warp_tiles) break;
+  const int i = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  const long long wt = first_wt + i;
+  if (i < nseg && wt < n_warp_tiles) {
     const uint32_t off = s_off[i], cnt = s_off[i + 1] - off;
     const uint32_t* src = sc.staging + wt * (int64_t)kSeg;
-    for (uint32_t j = lane; j < cnt; j += 32) extras[(size_t)off + j] = src[j];
+    uint32_t v[kPerThread];
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) v[j] = (uint32_t)(sub + 8 * j) < cnt ? __ldcs(src + sub + 8 * j) : 0u;
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j)
+      if ((uint32_t)(sub + 8 * j) < cnt) extras[(size_t)off + sub + 8 * j] = v[j];
   }
   if ((int)threadIdx.x < rounds) {
     const long long tile = group * rounds + threadIdx.x;
@@ -805,8 +875,11 @@ int smaq_packed_layout_for(int64_t n, int32_t bits_main, int32_t bits_outlier, s
   l.extras_off = l.planes_off + l.planes_bytes;
   l.extras_capacity_bytes = align_up(l.n_warp_tiles * (int64_t)(kWarpTile * xb / 32) * 4 + 4, 128);
   l.total_capacity_bytes = l.extras_off + l.extras_capacity_bytes;
-  // scratch: 4 uint32 per group (at most one group per CTA tile) + 1 per warp tile + the parked segments
-  l.workspace_bytes = align_up(l.n_cta_tiles * 16 + l.n_warp_tiles * 4, 256) + l.n_warp_tiles * (int64_t)seg_words(xb) * 4 + 256;
+  // scratch: [group_words: 1 uint32 per group (at most one group per CTA tile) | seg_words: 1 per warp tile |
+  // super_off | parked segments | zeroed tail: ticket, totals, super_words]
+  const int64_t n_super = (l.n_cta_tiles >> kSuperShift) + 1;
+  l.workspace_bytes = align_up(l.n_cta_tiles * 4 + l.n_warp_tiles * 4 + n_super * 4, 256) +
+                      l.n_warp_tiles * (int64_t)seg_words(xb) * 4 + align_up(32 + n_super * 4, 256);
   *out = l;
   return SMAQ_OK;
 }
@@ -837,26 +910,37 @@ int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* p
   const bool hp = st && probs != nullptr;
   const bool cs = params->count_saturated != 0;
   const unsigned grid = (unsigned)n_groups;
+  const int64_t n_super_alloc = (l.n_cta_tiles >> kSuperShift) + 1;
+  const int64_t zero_bytes = align_up(32 + n_super_alloc * 4, 256);
   EncodeScratch sc;
   {
     uint32_t* w = (uint32_t*)ws;
     sc.group_words = w;
-    sc.group_nout = w + l.n_cta_tiles;
-    sc.group_nsat = w + 2 * l.n_cta_tiles;
-    sc.group_off = w + 3 * l.n_cta_tiles;
-    sc.seg_words = w + 4 * l.n_cta_tiles;
-    sc.staging = (uint32_t*)((char*)ws + align_up(l.n_cta_tiles * 16 + l.n_warp_tiles * 4, 256));
+    sc.seg_words = w + l.n_cta_tiles;
+    sc.super_off = w + l.n_cta_tiles + l.n_warp_tiles;
+    sc.staging = (uint32_t*)((char*)ws + align_up(l.n_cta_tiles * 4 + l.n_warp_tiles * 4 + n_super_alloc * 4, 256));
+    char* tail = (char*)ws + l.workspace_bytes - zero_bytes;
+    sc.ticket = (unsigned int*)tail;
+    sc.totals = (unsigned long long*)(tail + 16);
+    sc.super_words = (uint32_t*)(tail + 32);
   }
+  HeaderArgs ha;
+  ha.hdr = hdr;
+  ha.table = table;
+  ha.n_super = ((n_groups - 1) >> kSuperShift) + 1;
+  ha.n_cta_tiles = l.n_cta_tiles;
+  ha.n = n;
+  ha.stochastic = st ? 1 : 0;
+  ha.count_saturated = cs ? 1 : 0;
+  SMAQ_CUDA_OK(cudaMemsetAsync(sc.ticket, 0, (size_t)zero_bytes, stream));
 
 #define SMAQ_ENC_LAUNCH(PM_, XB_, ST_, HP_)                                                                        \
   {                                                                                                                \
     auto kern = cs ? encode_kernel<PM_, XB_, ST_, HP_, true> : encode_kernel<PM_, XB_, ST_, HP_, false>;                                                                 \
     SMAQ_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncodeDynSmem));         \
     kern<<<grid, kPackThreads, kEncodeDynSmem, stream>>>(x, n, mean_std, probs, kp, planes, sc, l.n_cta_tiles,     \
-                                                         rounds, aligned);                                         \
+                                                         rounds, aligned, ha);                                     \
     SMAQ_LAUNCH_OK();                                                                                              \
-    encode_scan_kernel<<<1, 1024, 0, stream>>>(sc, n_groups, l.n_cta_tiles, hdr, table, mean_std, kp, n, ST_,     \
-                                               cs ? 1 : 0);                                                        \
     encode_place_kernel<XB_><<<grid, kPackThreads, 0, stream>>>(sc, table, extras, l.n_cta_tiles, l.n_warp_tiles,  \
                                                                 rounds);                                           \
   }
