@@ -512,21 +512,25 @@ __device__ __forceinline__ void finish_stream(const EncodeScratch& sc, const Hea
   }
 }
 
-// Pass 1.  One CTA = one group of `rounds` consecutive CTA tiles (8 warp tiles each); each warp
-// runs through its `rounds` warp tiles on its own: while it quantises tile r out of shared
-// memory, TMA is already filling the other stage with tile r+1.  No block barrier in the loop.
+// Pass 1.  A GROUP is `rounds` consecutive CTA tiles (<= 32 warp tiles; the unit of the placement
+// pass); a CTA owns `gpc` consecutive groups, so the per-CTA set-up is amortised.  Each warp runs through its warp tiles on its own: while it quantises tile r out of
+// shared memory, TMA is already filling the other stage with tile r+1 (across group boundaries
+// too).  The only block barrier is the one that closes a group.
 template <int PM, int XB, bool kStochastic, bool kHasProbs, bool kCountSat>
 __global__ void __launch_bounds__(kPackThreads, 3)
     encode_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ mean_std,
                   const float* __restrict__ probs, const __grid_constant__ KernelParams kp,
-                  uint32_t* __restrict__ planes, EncodeScratch sc, long long n_cta_tiles, int rounds, int aligned,
-                  HeaderArgs ha) {
+                  uint32_t* __restrict__ planes, EncodeScratch sc, long long n_cta_tiles, int rounds, int gpc,
+                  long long n_groups, int aligned, HeaderArgs ha) {
   constexpr int kSeg = seg_words(XB);
   constexpr bool kCanHot = (PM == 5 && XB == 2);
   extern __shared__ unsigned char dyn_smem[];
   __shared__ uint32_t s_seg[kWarpsPerCta][kSeg + 2];  // +2: spill words of the last atomicOr
-  __shared__ uint32_t s_tot[3][kWarpsPerCta];
+  __shared__ uint32_t s_tot[2][3][kWarpsPerCta];       // double-buffered by group parity
   __shared__ __align__(8) uint64_t s_bar[kWarpsPerCta][kStages];
+  __shared__ Scalars s_scalars;
+  __shared__ Hot s_hot;
+  __shared__ bool s_last;
 
   const int lane = lane_id(), warp = warp_id();
   const uint32_t seg_addr = smem_u32(&s_seg[warp][0]);
@@ -536,18 +540,33 @@ __global__ void __launch_bounds__(kPackThreads, 3)
     mbar_fence_init();
   }
   for (int j = lane; j < kSeg + 2; j += 32) sts32(seg_addr + 4 * j, 0u);  // kept zero between tiles by the copy-out loop
-  __syncwarp();
-  const long long group = blockIdx.x;
-  const long long first_tile = group * rounds;
-  const int nrounds = (int)min((long long)rounds, n_cta_tiles - first_tile);
+  const long long g_first = (long long)blockIdx.x * gpc;
+  const int n_my_groups = (int)min((long long)gpc, n_groups - g_first);
+  const long long first_tile = g_first * rounds;
+  const int nrounds = (int)min((long long)n_my_groups * rounds, n_cta_tiles - first_tile);  // CTA tiles of this CTA
 
   // this warp's two 4 KB stages (1 KB aligned)
   const uint32_t stage0 = ((smem_u32(dyn_smem) + 1023u) & ~1023u) + (uint32_t)warp * kStages * kStageBytes;
   const uint32_t bar0 = smem_u32(&s_bar[warp][0]);
+  const bool tma_ok = kCanHot && aligned;  // warp tiles wholly inside the tensor are staged by TMA
+  const bool probs_vec = kStochastic && kHasProbs && aligned16(probs);
+  const int64_t base0 = ((int64_t)first_tile * kWarpsPerCta + warp) * kWarpTile;  // + r * kCtaTile
+  auto issue = [&](int r) {
+    if (lane == 0) {
+      const int64_t b = base0 + (int64_t)r * kCtaTile;
+      if (tma_ok && b + kWarpTile <= n) {
+        const uint32_t dst = stage0 + (r % kStages) * kStageBytes, bar = bar0 + 8 * (r % kStages);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kStageBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(x + b), "r"(kStageBytes), "r"(bar)
+                     : "memory");
+      }
+    }
+  };
+  __syncwarp();
+  issue(0);  // in flight while thread 0 derives the constants
 
   // per-tensor constants: derived once per CTA (IEEE divisions, a search loop) and broadcast
-  __shared__ Scalars s_scalars;
-  __shared__ Hot s_hot;
   if (threadIdx.x == 0) {
     s_scalars = scalars_from(mean_std[0], mean_std[1], kp);
     s_hot = make_hot(s_scalars);
@@ -555,119 +574,113 @@ __global__ void __launch_bounds__(kPackThreads, 3)
   __syncthreads();
   const Scalars s = s_scalars;
   const Hot hot = s_hot;
-  const bool tma_ok = kCanHot && aligned && hot.ok;  // warp tiles wholly inside the tensor are staged by TMA
-  const bool probs_vec = kStochastic && kHasProbs && aligned16(probs);
-  const int64_t base0 = ((int64_t)first_tile * kWarpsPerCta + warp) * kWarpTile;  // + r * kCtaTile
-  auto issue = [&](int r) {
-    const int64_t b = base0 + (int64_t)r * kCtaTile;
-    if (lane == 0 && tma_ok && b + kWarpTile <= n) {
-      const uint32_t dst = stage0 + (r % kStages) * kStageBytes, bar = bar0 + 8 * (r % kStages);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kStageBytes) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                   "l"(x + b), "r"(kStageBytes), "r"(bar)
-                   : "memory");
-    }
-  };
 
-  issue(0);
-  uint32_t n_out_total = 0, n_sat_total = 0, words_total = 0;
-  for (int r = 0; r < nrounds; ++r) {
-    if (r + 1 < nrounds) issue(r + 1);  // stage (r+1)%2 was fully consumed in round r-1 (__syncwarp below)
-    const int64_t base = base0 + (int64_t)r * kCtaTile;
-    if (base >= n) break;  // warp tiles past the end of the tensor: nothing stored (uniform per warp)
-    const int64_t wt = base >> 10;
-    ChunkBits ch[4];
-    if (tma_ok && base + kWarpTile <= n) {
-      mbar_wait(&s_bar[warp][r % kStages], (uint32_t)((r / kStages) & 1));
-      if constexpr (kCanHot)
-        hot_tile<kStochastic, kHasProbs, kCountSat>(stage0 + (r % kStages) * kStageBytes, probs, wt, probs_vec, kp, s, hot,
-                                                    ch, n_sat_total);
-    } else {
-      generic_tile<PM, XB, kStochastic, kHasProbs>(x, n, probs, kp, s, base, ch, n_sat_total);
-    }
-    __syncwarp();  // stage fully read (lane 0 may refill it)
-
-    // fixed-position part of the stream: (1 + PM) rows of 32 words per warp tile, coalesced
-    uint32_t bw[PM];
-    assemble_base<PM>(ch, bw);
-    const uint32_t tagw = ch[0].tag | (ch[1].tag << 8) | (ch[2].tag << 16) | (ch[3].tag << 24);
-    uint32_t* rec = planes + wt * (int64_t)((1 + PM) * 32) + lane;
-    rec[0] = tagw;
-#pragma unroll
-    for (int w = 0; w < PM; ++w) rec[32 * (w + 1)] = bw[w];
-
-    // variable part: the lane's extras (chunk groups in order, LSB-first) go into this warp tile's
-    // word-aligned segment
-    const uint32_t n_out = __popc(tagw);
-    n_out_total += n_out;
-    if (XB > 0) {
-      const uint32_t inc = warp_inclusive_scan(n_out * XB);
-      uint32_t pos = inc - n_out * XB;
-      if (XB <= 2) {  // at most 64 bits per lane: one 64-bit string, two (rarely three) atomics
-        unsigned long long str = 0;
-        uint32_t len = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          str |= (unsigned long long)ch[k].ext << len;
-          len += __popc(ch[k].tag) * XB;
-        }
-        if (len) {
-          const uint32_t wa = seg_addr + ((pos >> 5) << 2), sh = pos & 31;
-          const uint32_t lo32 = (uint32_t)str, hi32 = (uint32_t)(str >> 32);
-          red_or_shared(wa, lo32 << sh);
-          if (sh + len > 32) red_or_shared(wa + 4, __funnelshift_l(lo32, hi32, sh));  // bits 32..63 of (str << sh)
-          if (sh + len > 64) red_or_shared(wa + 8, hi32 >> (32 - sh));               // sh > 0 here
+  int r = 0;
+  for (int gi = 0; gi < n_my_groups; ++gi) {
+    uint32_t n_out_total = 0, n_sat_total = 0, words_total = 0;
+    const int r_end = min(r + rounds, nrounds);
+    for (; r < r_end; ++r) {
+      if (r + 1 < nrounds) issue(r + 1);  // stage (r+1)%2 was fully consumed in round r-1 (__syncwarp below)
+      const int64_t base = base0 + (int64_t)r * kCtaTile;
+      if (base >= n) continue;  // warp tiles past the end of the tensor: nothing stored (uniform per warp)
+      const int64_t wt = base >> 10;
+      ChunkBits ch[4];
+      if (tma_ok && base + kWarpTile <= n) {
+        mbar_wait(&s_bar[warp][r % kStages], (uint32_t)((r / kStages) & 1));
+        if constexpr (kCanHot) {
+          if (hot.ok)
+            hot_tile<kStochastic, kHasProbs, kCountSat>(stage0 + (r % kStages) * kStageBytes, probs, wt, probs_vec, kp, s,
+                                                        hot, ch, n_sat_total);
+          else
+            generic_tile<PM, XB, kStochastic, kHasProbs>(x, n, probs, kp, s, base, ch, n_sat_total);
         }
       } else {
+        generic_tile<PM, XB, kStochastic, kHasProbs>(x, n, probs, kp, s, base, ch, n_sat_total);
+      }
+      __syncwarp();  // stage fully read (lane 0 may refill it)
+
+      // fixed-position part of the stream: (1 + PM) rows of 32 words per warp tile, coalesced
+      uint32_t bw[PM];
+      assemble_base<PM>(ch, bw);
+      const uint32_t tagw = ch[0].tag | (ch[1].tag << 8) | (ch[2].tag << 16) | (ch[3].tag << 24);
+      uint32_t* rec = planes + wt * (int64_t)((1 + PM) * 32) + lane;
+      rec[0] = tagw;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t len = __popc(ch[k].tag) * XB;  // <= 32
+      for (int w = 0; w < PM; ++w) rec[32 * (w + 1)] = bw[w];
+
+      // variable part: the lane's extras (chunk groups in order, LSB-first) go into this warp tile's
+      // word-aligned segment
+      const uint32_t n_out = __popc(tagw);
+      n_out_total += n_out;
+      if (XB > 0) {
+        const uint32_t inc = warp_inclusive_scan(n_out * XB);
+        uint32_t pos = inc - n_out * XB;
+        if (XB <= 2) {  // at most 64 bits per lane: one 64-bit string, two (rarely three) atomics
+          unsigned long long str = 0;
+          uint32_t len = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            str |= (unsigned long long)ch[k].ext << len;
+            len += __popc(ch[k].tag) * XB;
+          }
           if (len) {
             const uint32_t wa = seg_addr + ((pos >> 5) << 2), sh = pos & 31;
-            red_or_shared(wa, ch[k].ext << sh);
-            if (sh + len > 32) red_or_shared(wa + 4, ch[k].ext >> (32 - sh));
-            pos += len;
+            const uint32_t lo32 = (uint32_t)str, hi32 = (uint32_t)(str >> 32);
+            red_or_shared(wa, lo32 << sh);
+            if (sh + len > 32) red_or_shared(wa + 4, __funnelshift_l(lo32, hi32, sh));  // bits 32..63 of (str << sh)
+            if (sh + len > 64) red_or_shared(wa + 8, hi32 >> (32 - sh));               // sh > 0 here
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t len = __popc(ch[k].tag) * XB;  // <= 32
+            if (len) {
+              const uint32_t wa = seg_addr + ((pos >> 5) << 2), sh = pos & 31;
+              red_or_shared(wa, ch[k].ext << sh);
+              if (sh + len > 32) red_or_shared(wa + 4, ch[k].ext >> (32 - sh));
+              pos += len;
+            }
           }
         }
-      }
-      const uint32_t nwords = (__shfl_sync(0xffffffffu, inc, 31) + 31) >> 5;  // <= kSeg <= 128
-      __syncwarp();
-      uint32_t* park = sc.staging + wt * (int64_t)kSeg + lane;
+        const uint32_t nwords = (__shfl_sync(0xffffffffu, inc, 31) + 31) >> 5;  // <= kSeg <= 128
+        __syncwarp();
+        uint32_t* park = sc.staging + wt * (int64_t)kSeg + lane;
 #pragma unroll
-      for (int j = 0; j < (kSeg + 31) / 32; ++j) {  // copy out and re-zero for the next tile
-        if ((uint32_t)(32 * j + lane) < nwords) {
-          park[32 * j] = lds32(seg_addr + 4 * (32 * j + lane));
-          sts32(seg_addr + 4 * (32 * j + lane), 0u);
+        for (int j = 0; j < (kSeg + 31) / 32; ++j) {  // copy out and re-zero for the next tile
+          if ((uint32_t)(32 * j + lane) < nwords) {
+            park[32 * j] = lds32(seg_addr + 4 * (32 * j + lane));
+            sts32(seg_addr + 4 * (32 * j + lane), 0u);
+          }
         }
+        if (lane == 0) sc.seg_words[wt] = nwords;
+        words_total += nwords;
+        __syncwarp();  // the segment is clean before the next round's atomics
       }
-      if (lane == 0) sc.seg_words[wt] = nwords;
-      words_total += nwords;
-      __syncwarp();  // the segment is clean before the next round's atomics
     }
-  }
 
-  // totals of this CTA's group: the group's word count is stored, and added (integer atomics:
-  // order-independent, so the stream stays deterministic) to its super-group's and the tensor's
-  const uint32_t w_out = warp_sum(n_out_total), w_sat = warp_sum(n_sat_total);
-  if (lane == 0) {
-    s_tot[0][warp] = words_total;
-    s_tot[1][warp] = w_out;
-    s_tot[2][warp] = w_sat;
-  }
-  __syncthreads();
-  __shared__ bool s_last;
-  if (threadIdx.x < 3) {
-    uint32_t t = 0;
-#pragma unroll
-    for (int w = 0; w < kWarpsPerCta; ++w) t += s_tot[threadIdx.x][w];
-    if (threadIdx.x == 0) {
-      sc.group_words[group] = t;
-      atomicAdd(sc.super_words + (group >> kSuperShift), t);
-    } else {
-      atomicAdd(sc.totals + (threadIdx.x - 1), (unsigned long long)t);
+    // totals of this group: its word count is stored, and added (integer atomics: order-independent,
+    // so the stream stays deterministic) to its super-group's and to the tensor's
+    const uint32_t w_out = warp_sum(n_out_total), w_sat = warp_sum(n_sat_total);
+    if (lane == 0) {
+      s_tot[gi & 1][0][warp] = words_total;
+      s_tot[gi & 1][1][warp] = w_out;
+      s_tot[gi & 1][2][warp] = w_sat;
     }
-    __threadfence();  // the totals are visible before the ticket is
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      const long long group = g_first + gi;
+      uint32_t t = 0;
+#pragma unroll
+      for (int w = 0; w < kWarpsPerCta; ++w) t += s_tot[gi & 1][threadIdx.x][w];
+      if (threadIdx.x == 0) {
+        sc.group_words[group] = t;
+        atomicAdd(sc.super_words + (group >> kSuperShift), t);
+      } else {
+        atomicAdd(sc.totals + (threadIdx.x - 1), (unsigned long long)t);
+      }
+    }
   }
+  if (threadIdx.x < 3) __threadfence();  // the totals are visible before the ticket is
   __syncthreads();
   if (threadIdx.x == 0) s_last = atomicAdd(sc.ticket, 1u) == gridDim.x - 1;
   __syncthreads();
@@ -840,11 +853,20 @@ static bool width_supported(int bits_main, int bits_outlier) {
 }
 
 static int rounds_for(int64_t n_cta_tiles) {
-  // CTA tiles per CTA: enough groups for >= 4 waves over 3 resident CTAs per SM, at most kMaxRounds
+  // CTA tiles per group: kMaxRounds unless the tensor is too small to give every SM a few groups
   int sms = sm_count();
   if (sms <= 0) sms = 148;
   int64_t r = n_cta_tiles / ((int64_t)sms * 3 * 4);
   return (int)(r < 1 ? 1 : (r > kMaxRounds ? kMaxRounds : r));
+}
+// Groups per CTA: long enough that the per-CTA set-up is amortised, short enough that the hardware
+// scheduler still has >= 8 CTAs per resident slot to balance the SMs with (measured: one CTA per
+// slot loses 7 % to the tail, one group per CTA loses 8 % to the set-up barrier).
+static int groups_per_cta(int64_t n_groups) {
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  const int64_t g = n_groups / ((int64_t)sms * 3 * 8);
+  return (int)(g < 1 ? 1 : (g > 8 ? 8 : g));
 }
 
 }  // namespace smaq
@@ -909,7 +931,8 @@ int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* p
   const bool st = params->stochastic != 0;
   const bool hp = st && probs != nullptr;
   const bool cs = params->count_saturated != 0;
-  const unsigned grid = (unsigned)n_groups;
+  const int gpc = groups_per_cta(n_groups);
+  const unsigned grid = (unsigned)((n_groups + gpc - 1) / gpc);
   const int64_t n_super_alloc = (l.n_cta_tiles >> kSuperShift) + 1;
   const int64_t zero_bytes = align_up(32 + n_super_alloc * 4, 256);
   EncodeScratch sc;
@@ -939,9 +962,10 @@ int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* p
     auto kern = cs ? encode_kernel<PM_, XB_, ST_, HP_, true> : encode_kernel<PM_, XB_, ST_, HP_, false>;                                                                 \
     SMAQ_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncodeDynSmem));         \
     kern<<<grid, kPackThreads, kEncodeDynSmem, stream>>>(x, n, mean_std, probs, kp, planes, sc, l.n_cta_tiles,     \
-                                                         rounds, aligned, ha);                                     \
+                                                         rounds, gpc, n_groups, aligned, ha);                      \
     SMAQ_LAUNCH_OK();                                                                                              \
-    encode_place_kernel<XB_><<<grid, kPackThreads, 0, stream>>>(sc, table, extras, l.n_cta_tiles, l.n_warp_tiles,  \
+    encode_place_kernel<XB_><<<(unsigned)n_groups, kPackThreads, 0, stream>>>(sc, table, extras, l.n_cta_tiles,    \
+                                                                              l.n_warp_tiles,                      \
                                                                 rounds);                                           \
   }
 #define SMAQ_ENC(PM_, XB_)                                                                                         \
