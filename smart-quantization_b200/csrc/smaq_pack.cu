@@ -656,6 +656,7 @@ __global__ void __launch_bounds__(kPackThreads, 3)
         words_total += nwords;
         __syncwarp();  // the segment is clean before the next round's atomics
       }
+      if (XB == 0 && lane == 0) sc.seg_words[wt] = 0;  // the placement pass still writes the (all-zero) table
     }
 
     // totals of this group: its word count is stored, and added (integer atomics: order-independent,
@@ -901,7 +902,7 @@ int smaq_packed_layout_for(int64_t n, int32_t bits_main, int32_t bits_outlier, s
   // super_off | parked segments | zeroed tail: ticket, totals, super_words]
   const int64_t n_super = (l.n_cta_tiles >> kSuperShift) + 1;
   l.workspace_bytes = align_up(l.n_cta_tiles * 4 + l.n_warp_tiles * 4 + n_super * 4, 256) +
-                      l.n_warp_tiles * (int64_t)seg_words(xb) * 4 + align_up(32 + n_super * 4, 256);
+                      align_up(l.n_warp_tiles * (int64_t)seg_words(xb) * 4, 256) + align_up(32 + n_super * 4, 256);
   *out = l;
   return SMAQ_OK;
 }
