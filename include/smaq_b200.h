@@ -117,7 +117,7 @@ typedef struct smaq_tensor_desc {
   float* y;
   int64_t n;
   int32_t all_positive;
-  int32_t reserved;
+  int32_t stream;       /* Philox stream of this tensor = params->offset + stream */
 } smaq_tensor_desc;
 size_t smaq_multi_workspace_bytes(int32_t count, int64_t total_elems);
 int smaq_roundtrip_multi(const smaq_tensor_desc* descs, int32_t count, int64_t max_n, int64_t total_elems,

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kStatsThreads) multi_small_kernel(const smaq_t
     }
     KernelParams k = kp;
     k.all_positive = d.all_positive;
-    k.offset = kp.offset + (uint64_t)t;  // one Philox stream per tensor
+    k.offset = kp.offset + (uint64_t)(uint32_t)d.stream;  // one Philox stream per tensor
     small_body<kStochastic, false>(d.x, d.y, d.n, nullptr, k, nullptr, smem, bcast);
   }
 }

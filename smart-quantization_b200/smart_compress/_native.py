@@ -64,7 +64,7 @@ class TensorDesc(C.Structure):  # smaq_tensor_desc
         ("y", C.c_void_p),
         ("n", C.c_int64),
         ("all_positive", C.c_int32),
-        ("reserved", C.c_int32),
+        ("stream", C.c_int32),
     ]
 
 

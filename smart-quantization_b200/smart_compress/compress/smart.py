@@ -60,9 +60,11 @@ class SmartFP(CompressionAlgorithmBase):
         self.range_normal = ((2 ** (hp.num_bits_main - 2)) - 1) / hp.main_std_dev_threshold
         self.clamped_range = (1e-4, 1e4) if getattr(hp, "precision", 32) == 16 else (1e-38, 1e38)
         self._calls = itertools.count()  # Philox stream offset: one stream per call
+        self._desc_cache = {}            # compress_many: device descriptor arrays by (pointers, sizes)
+        self._multi_ws = {}
 
     # ------------------------------------------------------------------------------------------
-    def _params(self, all_positive: bool, saturate: bool = False) -> N.CodecParams:
+    def _params(self, all_positive: bool, saturate: bool = False, offset: Optional[int] = None) -> N.CodecParams:
         hp = self.hparams
         p = N.CodecParams()
         p.threshold = hp.main_std_dev_threshold
@@ -79,7 +81,7 @@ class SmartFP(CompressionAlgorithmBase):
         p.count_saturated = int(bool(getattr(hp, "measure_compression_ratio", False)))
         # torch.manual_seed() governs the stream, as it governs the reference's rand_like
         p.seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
-        p.offset = next(self._calls)
+        p.offset = next(self._calls) if offset is None else offset
         return p
 
     def statistics(self, flat: torch.Tensor, sample_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -148,7 +150,7 @@ class SmartFP(CompressionAlgorithmBase):
         flat = src.view(-1)
         out = torch.empty_like(src)
         stream = N.stream_ptr(data.device)
-        params = self._params(all_positive and not use_bn)
+        params = self._params(all_positive and not use_bn, offset=extra.get("_offset"))
         probs_ptr = None
         if probs is not None:
             probs = probs.to(device=data.device, dtype=torch.float32).contiguous()
@@ -181,6 +183,74 @@ class SmartFP(CompressionAlgorithmBase):
         if hp.measure_compression_ratio:
             self.log_size(tag, orig_size, lambda: self._compressed_bits(flat, mean_std, params))
         return out
+
+    # -- many tensors, one launch (the optimizer side) ------------------------------------------
+    @torch.no_grad()
+    def compress_many(self, tensors, kwargs_list=None, tag: str = None):
+        """``[self(t, tag=tag, **kw) for t, kw in zip(tensors, kwargs_list)]`` with every tensor of at most
+        ``smaq_fused_small_max()`` elements handled by ONE launch (``smaq_roundtrip_multi``: per-tensor
+        full statistics + round trip, one Philox stream per tensor).  OptimLP loops the codec over every
+        parameter, gradient and state tensor (reference optimizer.py:69-127); most of them are tiny
+        (median 512 elements for ResNet-18), so per-tensor launches are pure latency.  The batched
+        tensors are updated IN PLACE and returned as the same objects (the reference re-binds ``.data``
+        to a fresh tensor; nothing else aliases optimizer tensors, so the effect is the same)."""
+        hp = self.hparams
+        lib = N.load()
+        small_max = lib.smaq_fused_small_max()
+        per_tensor = (hp.use_sample_stats or hp.use_range_std_dev or hp.measure_compression_ratio
+                      or Globals.profiler is not None)
+        results = list(tensors)
+        batch = []
+        # Philox streams are numbered like the per-tensor loop numbers them: one per tensor that is
+        # actually quantised (numel >= min_size), in order
+        first = None
+        numbered = 0
+        for i, t in enumerate(tensors):
+            kw = kwargs_list[i] if kwargs_list is not None else {}
+            n = t.numel()
+            if n < hp.min_size:
+                results[i] = self(t, tag=tag, **kw)  # comes back untouched (smart.py:125-128)
+                continue
+            if first is None:
+                first = next(self._calls)
+            else:
+                next(self._calls)
+            stream_no = numbered
+            numbered += 1
+            ok = (not per_tensor and n <= small_max and t.is_cuda and t.dtype == torch.float32
+                  and t.is_contiguous() and "batch_norm_stats" not in kw and "_probs" not in kw)
+            if ok:
+                batch.append((i, t, bool(kw.get("all_positive", False)), stream_no))
+            else:
+                results[i] = self(t, tag=tag, _offset=first + stream_no, **kw)
+        if not batch:
+            return results
+        device = batch[0][1].device
+        key = (device, tuple((t.data_ptr(), t.numel(), ap, sn) for _, t, ap, sn in batch))
+        descs = self._desc_cache.get(key)
+        if descs is None:
+            host = (N.TensorDesc * len(batch))()
+            for j, (_, t, ap, sn) in enumerate(batch):
+                host[j].x = host[j].y = t.data_ptr()
+                host[j].n = t.numel()
+                host[j].all_positive = int(ap)
+                host[j].stream = sn
+            raw = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).pin_memory()
+            descs = raw.to(device, non_blocking=True)
+            if len(self._desc_cache) > 64:
+                self._desc_cache.clear()
+            self._desc_cache[key] = descs
+        params = self._params(all_positive=False, offset=first)
+        ws = self._multi_ws.get(device)
+        if ws is None:
+            ws = self._multi_ws[device] = torch.empty(256, dtype=torch.uint8, device=device)
+        N.check(
+            lib.smaq_roundtrip_multi(N.ptr(descs), len(batch), max(t.numel() for _, t, _, _ in batch),
+                                     sum(t.numel() for _, t, _, _ in batch), C.byref(params), int(hp.min_size),
+                                     N.ptr(ws), ws.numel(), N.stream_ptr(device)),
+            "smaq_roundtrip_multi",
+        )
+        return results
 
     # -- materialised stream: encode / decode ---------------------------------------------------
     @torch.no_grad()

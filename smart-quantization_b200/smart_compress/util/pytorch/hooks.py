@@ -15,6 +15,9 @@ def _wrap_fn(fn, **bound):
     def wrapped(*args, **kwargs):
         return fn(*args, **bound, **kwargs)
 
+    many = getattr(fn, "compress_many", None)
+    if many is not None:  # a codec that batches small tensors (SmartFP): OptimLP uses it per phase
+        wrapped.compress_many = lambda tensors, kwargs_list=None: many(tensors, kwargs_list, **bound)
     return wrapped
 
 

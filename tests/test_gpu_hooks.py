@@ -102,3 +102,54 @@ def test_backward_runs_on_autograd_thread_and_matches_forward_stream():
     leaf = torch.randn(64, device=DEV)  # no grad needed: backward returns (None, None)
     out = comp(leaf)
     assert not out.requires_grad
+
+
+def test_compress_many_equals_per_tensor_calls():
+    """The batched optimizer-side path (one smaq_roundtrip_multi launch, in place) must give, bit for bit,
+    what the reference's per-tensor loop gives: same statistics, same Philox stream per tensor."""
+    from smart_compress.compress.smart import SmartFP
+
+    g = torch.Generator().manual_seed(5)
+    sizes = [10, 64, 512, 513, 4096, 32768, 7, 40000, 2048]   # 7 < min_size; 40000 > the fused-small limit
+    tensors = [torch.randn(n, generator=g).to(DEV) for n in sizes]
+    kwargs = [dict(all_positive=(i % 3 == 0)) for i in range(len(sizes))]
+    torch.manual_seed(11)
+    a = SmartFP(hparams())
+    want = [a(t.clone(), tag="optimizer_momentum", **kw) for t, kw in zip(tensors, kwargs)]
+    torch.manual_seed(11)
+    b = SmartFP(hparams())
+    mine = [t.clone() for t in tensors]
+    got = b.compress_many(mine, kwargs, tag="optimizer_momentum")
+    # Philox streams are numbered identically (one per quantised tensor, in order), whichever path a tensor takes
+    for i, (w, r) in enumerate(zip(want, got)):
+        if sizes[i] < 8:
+            assert r is mine[i] and torch.equal(r, tensors[i])
+        else:
+            assert torch.equal(w.view(torch.int32), r.view(torch.int32)), f"tensor {i} ({sizes[i]} elements)"
+
+
+def test_wrapped_optimizer_uses_the_batched_path():
+    from smart_compress.compress.smart import SmartFP
+    from smart_compress.util.pytorch.hooks import wrap_optimizer
+
+    hp = hparams()
+    codec = SmartFP(hp)
+    seen = []
+    orig = codec.compress_many
+    codec.compress_many = lambda tensors, kwargs_list=None, tag=None: (seen.append((tag, len(tensors))),
+                                                                      orig(tensors, kwargs_list, tag=tag))[1]
+    model = small_net()
+    opt = wrap_optimizer(torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9), codec, hp)
+    x = torch.randn(8, 3, 8, 8, device=DEV)
+
+    def closure():
+        opt.zero_grad()
+        loss = model(x).square().mean()
+        loss.backward()
+        return loss
+
+    opt.step(closure)
+    n = len(list(model.parameters()))
+    assert seen == [("optimizer_grad", n), ("optimizer_grad", n), ("optimizer_weight", n), ("optimizer_momentum", n)]
+    for p in model.parameters():
+        assert bool(torch.isfinite(p).all())
