@@ -225,6 +225,158 @@ __global__ void __launch_bounds__(kStatsThreads) multi_small_kernel(const smaq_t
   }
 }
 
+// ---- many tensors of ANY size, three launches ------------------------------------------------------
+// Tensors above kSmallMax are cut into work items of kMultiChunk elements; one block per item.
+//   set-up : item counts per tensor -> exclusive prefix (one block);
+//   stats  : per-item moments (fixed order inside the block);
+//   apply  : every block re-merges its tensor's item moments in item order (deterministic and
+//            identical in every block of that tensor), finalises mean/std and quantises its chunk.
+constexpr int64_t kMultiChunk = 16384;
+
+struct MultiWs {
+  int* prefix;        // [count + 1] first item of each tensor (tensors <= kSmallMax own no items)
+  double* partials;   // [items][3] n, mean, M2
+};
+
+__device__ __forceinline__ int64_t multi_items(int64_t n) { return n > kSmallMax ? (n + kMultiChunk - 1) / kMultiChunk : 0; }
+
+__global__ void __launch_bounds__(kStatsThreads) multi_setup_kernel(const smaq_tensor_desc* __restrict__ descs, int count,
+                                                                    int* __restrict__ prefix) {
+  __shared__ int s_warp[kStatsThreads / 32];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < count; base += kStatsThreads) {
+    const int t = base + threadIdx.x;
+    const int items = t < count ? (int)multi_items(descs[t].n) : 0;
+    const int inc = (int)warp_inclusive_scan((uint32_t)items);
+    if (lane_id() == 31) s_warp[warp_id()] = inc;
+    __syncthreads();
+    int before = s_carry, all = 0;
+#pragma unroll
+    for (int w = 0; w < kStatsThreads / 32; ++w) {
+      before += w < warp_id() ? s_warp[w] : 0;
+      all += s_warp[w];
+    }
+    if (t < count) prefix[t] = before + inc - items;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += all;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) prefix[count] = s_carry;
+}
+
+// item -> (tensor, chunk): the last tensor whose first item is <= item
+__device__ __forceinline__ int multi_find(const int* __restrict__ prefix, int count, int item) {
+  int lo = 0, hi = count - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (prefix[mid] <= item) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kStatsThreads) multi_stats_kernel(const smaq_tensor_desc* __restrict__ descs, int count,
+                                                                    MultiWs ws) {
+  __shared__ Acc smem[kStatsThreads / 32];
+  const int item = blockIdx.x;
+  if (item >= ws.prefix[count]) return;
+  const int t = multi_find(ws.prefix, count, item);
+  const smaq_tensor_desc d = descs[t];
+  const int64_t start = (int64_t)(item - ws.prefix[t]) * kMultiChunk;
+  const int64_t len = min(kMultiChunk, d.n - start);
+  const float* x = d.x + start;
+  Acc acc;
+  acc.m = Moments{0.0, 0.0, 0.0};
+  acc.hi = -INFINITY;
+  acc.lo = INFINITY;
+  if (aligned16(x)) {
+    const float4* xv = reinterpret_cast<const float4*>(x);
+    const int64_t nvec = len >> 2;
+    int64_t v = threadIdx.x;
+    for (; v + 3 * kStatsThreads < nvec; v += 4 * kStatsThreads) {
+      const float4 a = ldg_stream(xv + v), b = ldg_stream(xv + v + kStatsThreads), c = ldg_stream(xv + v + 2 * kStatsThreads),
+                   e = ldg_stream(xv + v + 3 * kStatsThreads);
+      const float r[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, e.x, e.y, e.z, e.w};
+      merge_chunk<0, 16>(acc, r);
+    }
+    for (; v < nvec; v += kStatsThreads) {
+      const float4 a = ldg_stream(xv + v);
+      const float r[4] = {a.x, a.y, a.z, a.w};
+      merge_chunk<0, 4>(acc, r);
+    }
+    const int64_t tail = nvec << 2;
+    if (threadIdx.x < len - tail) merge_one<0>(acc, x[tail + threadIdx.x]);
+  } else {
+    for (int64_t i = threadIdx.x; i < len; i += kStatsThreads) merge_one<0>(acc, x[i]);
+  }
+  acc = block_combine<0>(acc, smem);
+  if (threadIdx.x == 0) {
+    double* p = ws.partials + (size_t)item * 3;
+    p[0] = acc.m.n;
+    p[1] = acc.m.mean;
+    p[2] = acc.m.m2;
+  }
+}
+
+template <bool kStochastic, bool kAllPos, bool kFast>
+__device__ __forceinline__ void multi_apply_chunk(const float* x, float* y, int64_t start, int64_t len, bool vec,
+                                                  const Scalars& s, const KernelParams& k) {
+  f32x8 zero8;
+  zero8.a = zero8.b = make_float4(0.f, 0.f, 0.f, 0.f);
+  int64_t done = 0;
+  if (vec) {
+    const int64_t ngroups = len >> 3;
+    for (int64_t g = threadIdx.x; g < ngroups; g += kStatsThreads) {
+      const f32x8 v = ldg_stream8(x + start + 8 * g);
+      stg_stream8(y + start + 8 * g, roundtrip_group8<kStochastic, false, kAllPos, false, kFast>(
+                                          v, zero8, (uint64_t)((start >> 3) + g), s, k));
+    }
+    done = ngroups << 3;
+  }
+  for (int64_t i = done + threadIdx.x; i < len; i += kStatsThreads)
+    y[start + i] = roundtrip_element<kStochastic, false>(x, nullptr, start + i, s, k);
+}
+
+template <bool kStochastic>
+__global__ void __launch_bounds__(kStatsThreads) multi_apply_kernel(const smaq_tensor_desc* __restrict__ descs, int count,
+                                                                    MultiWs ws, const __grid_constant__ KernelParams kp) {
+  __shared__ Acc smem[kStatsThreads / 32];
+  __shared__ float bcast[2];
+  const int item = blockIdx.x;
+  if (item >= ws.prefix[count]) return;
+  const int t = multi_find(ws.prefix, count, item);
+  const smaq_tensor_desc d = descs[t];
+  const int first = ws.prefix[t], last = ws.prefix[t + 1];
+  Acc f;
+  f.m = Moments{0.0, 0.0, 0.0};
+  f.hi = -INFINITY;
+  f.lo = INFINITY;
+  for (int b = first + threadIdx.x; b < last; b += kStatsThreads) {
+    const double* p = ws.partials + (size_t)b * 3;
+    f.m = merge(f.m, Moments{p[0], p[1], p[2]});
+  }
+  f = block_combine<0>(f, smem);
+  if (threadIdx.x == 0) finalize<0>(f, /*unbiased=*/1, bcast);
+  __syncthreads();
+  KernelParams k = kp;
+  k.all_positive = d.all_positive;
+  k.saturate = 0;
+  k.offset = kp.offset + (uint64_t)(uint32_t)d.stream;
+  const Scalars s = scalars_from(bcast[0], bcast[1], k);
+  const int64_t start = (int64_t)(item - first) * kMultiChunk;
+  const int64_t len = min(kMultiChunk, d.n - start);
+  const bool vec = aligned32(d.x) && aligned32(d.y);
+  if (s.fast) {
+    if (d.all_positive) multi_apply_chunk<kStochastic, true, true>(d.x, d.y, start, len, vec, s, k);
+    else multi_apply_chunk<kStochastic, false, true>(d.x, d.y, start, len, vec, s, k);
+  } else {
+    if (d.all_positive) multi_apply_chunk<kStochastic, true, false>(d.x, d.y, start, len, vec, s, k);
+    else multi_apply_chunk<kStochastic, false, false>(d.x, d.y, start, len, vec, s, k);
+  }
+}
+
 // --measure_compression_ratio only: how many elements classify as outliers.
 __global__ void __launch_bounds__(kRtThreads) count_outliers_kernel(const float* __restrict__ x, int64_t n,
                                                                     const float* __restrict__ mean_std,
@@ -320,29 +472,45 @@ int smaq_roundtrip_small(const float* x, float* y, int64_t n, const float* probs
   return SMAQ_OK;
 }
 
+static int64_t multi_max_items(int32_t count, int64_t total_elems) {
+  return total_elems / smaq::kMultiChunk + count + 1;
+}
+static size_t multi_align(size_t v) { return (v + 255) / 256 * 256; }
+
 size_t smaq_multi_workspace_bytes(int32_t count, int64_t total_elems) {
-  (void)count; (void)total_elems;
-  return 256;
+  if (count < 0 || total_elems < 0) return 0;
+  return multi_align(sizeof(int) * ((size_t)count + 1)) + multi_align((size_t)multi_max_items(count, total_elems) * 24) + 256;
 }
 
 int smaq_roundtrip_multi(const smaq_tensor_desc* descs, int32_t count, int64_t max_n, int64_t total_elems,
                          const smaq_codec_params* params, int64_t min_size, void* ws, size_t ws_bytes,
                          smaq_stream_t stream_) {
   using namespace smaq;
-  (void)ws; (void)ws_bytes; (void)total_elems;
   if (int rc = check_params(params)) return rc;
   if (!descs || count < 0) return fail(SMAQ_ERR_ARG, "roundtrip_multi: bad argument");
   if (count == 0) return SMAQ_OK;
-  if (max_n > kSmallMax)
-    return fail(SMAQ_ERR_UNSUPPORTED, "roundtrip_multi: tensors above %lld elements go through smaq_roundtrip",
-                (long long)kSmallMax);
   cudaStream_t stream = (cudaStream_t)stream_;
   const KernelParams kp = to_kernel_params(*params);
   int sms = sm_count();
   if (sms <= 0) sms = 148;
+  // tensors of at most kSmallMax elements: statistics + round trip in one block each, one launch
   int grid = count < sms * 8 ? count : sms * 8;
   if (params->stochastic) multi_small_kernel<true><<<grid, kStatsThreads, 0, stream>>>(descs, count, min_size, kp);
   else multi_small_kernel<false><<<grid, kStatsThreads, 0, stream>>>(descs, count, min_size, kp);
+  SMAQ_LAUNCH_OK();
+  if (max_n <= kSmallMax) return SMAQ_OK;
+  // the larger ones: work items of kMultiChunk elements
+  if (!ws || ws_bytes < smaq_multi_workspace_bytes(count, total_elems))
+    return fail(SMAQ_ERR_WORKSPACE, "roundtrip_multi: workspace too small (smaq_multi_workspace_bytes)");
+  MultiWs mw;
+  mw.prefix = (int*)ws;
+  mw.partials = (double*)((char*)ws + multi_align(sizeof(int) * ((size_t)count + 1)));
+  const int64_t items = multi_max_items(count, total_elems);
+  if (items > 0x7fffffff) return fail(SMAQ_ERR_UNSUPPORTED, "roundtrip_multi: too many work items");
+  multi_setup_kernel<<<1, kStatsThreads, 0, stream>>>(descs, count, mw.prefix);
+  multi_stats_kernel<<<(unsigned)items, kStatsThreads, 0, stream>>>(descs, count, mw);
+  if (params->stochastic) multi_apply_kernel<true><<<(unsigned)items, kStatsThreads, 0, stream>>>(descs, count, mw, kp);
+  else multi_apply_kernel<false><<<(unsigned)items, kStatsThreads, 0, stream>>>(descs, count, mw, kp);
   SMAQ_LAUNCH_OK();
   return SMAQ_OK;
 }

@@ -187,9 +187,10 @@ class SmartFP(CompressionAlgorithmBase):
     # -- many tensors, one launch (the optimizer side) ------------------------------------------
     @torch.no_grad()
     def compress_many(self, tensors, kwargs_list=None, tag: str = None):
-        """``[self(t, tag=tag, **kw) for t, kw in zip(tensors, kwargs_list)]`` with every tensor of at most
-        ``smaq_fused_small_max()`` elements handled by ONE launch (``smaq_roundtrip_multi``: per-tensor
-        full statistics + round trip, one Philox stream per tensor).  OptimLP loops the codec over every
+        """``[self(t, tag=tag, **kw) for t, kw in zip(tensors, kwargs_list)]`` in at most four launches
+        (``smaq_roundtrip_multi``: per-tensor full statistics + round trip, one Philox stream per tensor;
+        tensors up to ``smaq_fused_small_max()`` elements take one block each, larger ones are cut into
+        work items).  OptimLP loops the codec over every
         parameter, gradient and state tensor (reference optimizer.py:69-127); most of them are tiny
         (median 512 elements for ResNet-18), so per-tensor launches are pure latency.  The batched
         tensors are updated IN PLACE and returned as the same objects (the reference re-binds ``.data``
@@ -217,7 +218,7 @@ class SmartFP(CompressionAlgorithmBase):
                 next(self._calls)
             stream_no = numbered
             numbered += 1
-            ok = (not per_tensor and n <= small_max and t.is_cuda and t.dtype == torch.float32
+            ok = (not per_tensor and t.is_cuda and t.dtype == torch.float32
                   and t.is_contiguous() and "batch_norm_stats" not in kw and "_probs" not in kw)
             if ok:
                 batch.append((i, t, bool(kw.get("all_positive", False)), stream_no))
@@ -241,13 +242,14 @@ class SmartFP(CompressionAlgorithmBase):
                 self._desc_cache.clear()
             self._desc_cache[key] = descs
         params = self._params(all_positive=False, offset=first)
+        total = sum(t.numel() for _, t, _, _ in batch)
+        need = lib.smaq_multi_workspace_bytes(len(batch), total)
         ws = self._multi_ws.get(device)
-        if ws is None:
-            ws = self._multi_ws[device] = torch.empty(256, dtype=torch.uint8, device=device)
+        if ws is None or ws.numel() < need:  # grow-only scratch; calls on one stream are ordered
+            ws = self._multi_ws[device] = torch.empty(need, dtype=torch.uint8, device=device)
         N.check(
-            lib.smaq_roundtrip_multi(N.ptr(descs), len(batch), max(t.numel() for _, t, _, _ in batch),
-                                     sum(t.numel() for _, t, _, _ in batch), C.byref(params), int(hp.min_size),
-                                     N.ptr(ws), ws.numel(), N.stream_ptr(device)),
+            lib.smaq_roundtrip_multi(N.ptr(descs), len(batch), max(t.numel() for _, t, _, _ in batch), total,
+                                     C.byref(params), int(hp.min_size), N.ptr(ws), ws.numel(), N.stream_ptr(device)),
             "smaq_roundtrip_multi",
         )
         return results

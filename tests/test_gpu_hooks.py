@@ -110,7 +110,7 @@ def test_compress_many_equals_per_tensor_calls():
     from smart_compress.compress.smart import SmartFP
 
     g = torch.Generator().manual_seed(5)
-    sizes = [10, 64, 512, 513, 4096, 32768, 7, 40000, 2048]   # 7 < min_size; 40000 > the fused-small limit
+    sizes = [10, 64, 512, 513, 4096, 32768, 7, 40000, 2048, 1 << 20, (1 << 18) + 3]   # 7 < min_size; three above the one-block limit
     tensors = [torch.randn(n, generator=g).to(DEV) for n in sizes]
     kwargs = [dict(all_positive=(i % 3 == 0)) for i in range(len(sizes))]
     torch.manual_seed(11)
@@ -120,12 +120,20 @@ def test_compress_many_equals_per_tensor_calls():
     b = SmartFP(hparams())
     mine = [t.clone() for t in tensors]
     got = b.compress_many(mine, kwargs, tag="optimizer_momentum")
-    # Philox streams are numbered identically (one per quantised tensor, in order), whichever path a tensor takes
+    # Philox streams are numbered identically (one per quantised tensor, in order).  Tensors of one block are
+    # bit-identical to the per-tensor path; the larger ones merge their moments in a different (fixed) order, so
+    # mean/std may differ in the last bits: then only elements on a rounding boundary may move, by one code.
     for i, (w, r) in enumerate(zip(want, got)):
         if sizes[i] < 8:
             assert r is mine[i] and torch.equal(r, tensors[i])
-        else:
+        elif sizes[i] <= 32768:
             assert torch.equal(w.view(torch.int32), r.view(torch.int32)), f"tensor {i} ({sizes[i]} elements)"
+        else:
+            diff = (w - r).abs()
+            step = float(tensors[i].std()) / 15
+            assert float(diff.max()) <= 1.01 * step + 1e-6 and float((diff > 1e-6 * step).float().mean()) < 1e-3, sizes[i]
+    again = b.compress_many([t.clone() for t in tensors], kwargs, tag="optimizer_momentum")
+    assert all(bool(torch.isfinite(t).all()) for t in again)
 
 
 def test_wrapped_optimizer_uses_the_batched_path():
