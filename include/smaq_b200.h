@@ -96,6 +96,13 @@ int smaq_stats_sampled_draw(const float* x, int64_t n, int32_t k, uint64_t seed,
 int smaq_roundtrip(const float* x, float* y, int64_t n, const float* mean_std, const float* probs,
                    const smaq_codec_params* params, smaq_stream_t stream);
 
+/* The whole default call in one entry point — full-tensor unbiased statistics, then the round trip
+ * (smart.py:130-182 with the reference's default flags): what the training hooks issue hundreds of
+ * times per step.  The statistics live in the workspace (last 256 bytes: mean, std).  y may alias x. */
+size_t smaq_compress_workspace_bytes(int64_t n);
+int smaq_compress(const float* x, float* y, int64_t n, const float* probs, const smaq_codec_params* params,
+                  void* ws, size_t ws_bytes, smaq_stream_t stream);
+
 /* Number of outliers (|z| > threshold) under the given statistics — the only quantity the
  * reference's size accounting needs (smart.py:184-187: bits = 8*n_out + 6*(n - n_out)).  Adds the
  * count to *counter (device uint64, caller zeroes it).  Only used under --measure_compression_ratio. */

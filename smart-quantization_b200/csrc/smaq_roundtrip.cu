@@ -174,6 +174,21 @@ __global__ void __launch_bounds__(kRtThreads) roundtrip_unaligned_kernel(const f
 // ResNet-18); two launches per call would be pure launch latency.
 constexpr int64_t kSmallMax = 32768;  // second read comes from L1/L2
 
+// whole groups of 8 with the packed arithmetic of the large kernel (tensor and statistics permitting)
+template <bool kStochastic, bool kHasProbs, bool kAllPos>
+__device__ __forceinline__ int64_t small_groups(const float* x, float* y, int64_t n, const float* probs,
+                                                const KernelParams& kp, const Scalars& s) {
+  f32x8 zero8;
+  zero8.a = zero8.b = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t ngroups = n >> 3;
+  for (int64_t g = threadIdx.x; g < ngroups; g += blockDim.x) {
+    const f32x8 v = ldg_stream8(x + 8 * g);
+    const f32x8 pr = (kStochastic && kHasProbs) ? ldg_stream8(probs + 8 * g) : zero8;
+    stg_stream8(y + 8 * g, roundtrip_group8<kStochastic, kHasProbs, kAllPos, false, true>(v, pr, (uint64_t)g, s, kp));
+  }
+  return ngroups << 3;
+}
+
 template <bool kStochastic, bool kHasProbs>
 __device__ __forceinline__ void small_body(const float* x, float* y, int64_t n, const float* probs,
                                            const KernelParams& kp, float* mean_std_out, Acc* smem, float* bcast) {
@@ -189,7 +204,12 @@ __device__ __forceinline__ void small_body(const float* x, float* y, int64_t n, 
   }
   __syncthreads();
   const Scalars s = scalars_from(bcast[0], bcast[1], kp);
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) y[i] = roundtrip_element<kStochastic, kHasProbs>(x, probs, i, s, kp);
+  int64_t done = 0;
+  if (s.fast && !kp.saturate && aligned32(x) && aligned32(y) && (!(kStochastic && kHasProbs) || aligned32(probs))) {
+    done = kp.all_positive ? small_groups<kStochastic, kHasProbs, true>(x, y, n, probs, kp, s)
+                           : small_groups<kStochastic, kHasProbs, false>(x, y, n, probs, kp, s);
+  }
+  for (int64_t i = done + threadIdx.x; i < n; i += blockDim.x) y[i] = roundtrip_element<kStochastic, kHasProbs>(x, probs, i, s, kp);
   __syncthreads();
 }
 
@@ -470,6 +490,18 @@ int smaq_roundtrip_small(const float* x, float* y, int64_t n, const float* probs
   }
   SMAQ_LAUNCH_OK();
   return SMAQ_OK;
+}
+
+size_t smaq_compress_workspace_bytes(int64_t n) { return smaq_stats_workspace_bytes(n) + 256; }
+
+int smaq_compress(const float* x, float* y, int64_t n, const float* probs, const smaq_codec_params* params, void* ws,
+                  size_t ws_bytes, smaq_stream_t stream) {
+  using namespace smaq;
+  const size_t sb = smaq_stats_workspace_bytes(n);
+  if (!ws || ws_bytes < sb + 256) return fail(SMAQ_ERR_WORKSPACE, "compress: workspace too small (smaq_compress_workspace_bytes)");
+  float* mean_std = (float*)((char*)ws + sb);
+  if (int rc = smaq_stats_full(x, n, /*unbiased=*/1, mean_std, ws, sb, stream)) return rc;
+  return smaq_roundtrip(x, y, n, mean_std, probs, params, stream);
 }
 
 static int64_t multi_max_items(int32_t count, int64_t total_elems) {

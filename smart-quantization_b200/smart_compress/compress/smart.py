@@ -60,6 +60,8 @@ class SmartFP(CompressionAlgorithmBase):
         self.range_normal = ((2 ** (hp.num_bits_main - 2)) - 1) / hp.main_std_dev_threshold
         self.clamped_range = (1e-4, 1e4) if getattr(hp, "precision", 32) == 16 else (1e-38, 1e38)
         self._calls = itertools.count()  # Philox stream offset: one stream per call
+        self._small_max = int(N.load().smaq_fused_small_max())
+        self._call_ws = {}               # (device, stream) -> scratch of the fused statistics + round-trip call
         self._desc_cache = {}            # compress_many: device descriptor arrays by (pointers, sizes)
         self._multi_ws = {}
 
@@ -159,7 +161,18 @@ class SmartFP(CompressionAlgorithmBase):
 
         default_stats = not hp.use_sample_stats and not hp.use_range_std_dev
         mean_std = None
-        if default_stats and not use_bn and numel <= lib.smaq_fused_small_max():
+        if default_stats and not use_bn and numel > self._small_max and not hp.measure_compression_ratio:
+            # the common call of the training hooks: statistics + round trip behind ONE entry point, on a
+            # grow-only scratch buffer per (device, stream) — calls on one stream are ordered
+            key = (data.device.index, stream)
+            ws = self._call_ws.get(key)
+            need = lib.smaq_compress_workspace_bytes(numel)
+            if ws is None or ws.numel() < need:
+                ws = self._call_ws[key] = torch.empty(need, dtype=torch.uint8, device=data.device)
+            N.check(lib.smaq_compress(N.ptr(flat), N.ptr(out), numel, probs_ptr, C.byref(params), N.ptr(ws), ws.numel(),
+                                      stream), "smaq_compress")
+            return out
+        if default_stats and not use_bn and numel <= self._small_max:
             if hp.measure_compression_ratio:
                 mean_std = torch.empty(2, dtype=torch.float32, device=data.device)
             N.check(
