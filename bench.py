@@ -62,6 +62,35 @@ def dist_env():
     return rank, world, local
 
 
+def max_over_ranks(elapsed_ms: float, world: int, device) -> float:
+    """Device time of the slowest rank (every rank gets the same number).  The path shards with no
+    exchange: this all-reduce and the barriers are the only collectives of the bench."""
+    if world <= 1:
+        return float(elapsed_ms)
+    import torch.distributed as dist
+
+    t = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def whole_job_gbs(world: int, bytes_per_rank_step: float, ms_per_step: float) -> float:
+    """Weak scaling: every rank processes its own tensor; the job's throughput is the sum over ranks
+    of the bytes one step moves, over the slowest rank's time."""
+    return world * bytes_per_rank_step / (ms_per_step * 1e-3) / 1e9
+
+
+def traffic_from_profile(kernel: str, log2n: int):
+    """DRAM bytes of one launch of `kernel` from the committed ncu capture (tools/make_profiles.py)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
+    try:
+        with open(path) as f:
+            rec = json.load(f)[kernel]
+    except (OSError, KeyError, ValueError):
+        return None
+    return rec["dram_bytes"] if rec.get("log2n") == log2n else None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -271,11 +300,7 @@ def run_b200(args):
             step(per_kernel)
         t1.record()
         barrier()
-    elapsed_ms = t0.elapsed_time(t1)
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
+    elapsed_ms = max_over_ranks(t0.elapsed_time(t1), world, device)
     ms_per_step = elapsed_ms / args.steps
 
     pipe.encode(x, count_saturated=True)  # untimed: the timed steps run with the plugin's default (no count)
@@ -284,7 +309,7 @@ def run_b200(args):
     f_out = hdr.n_outlier / n
     bpe = bytes_per_element(f_out)
     step_bytes = bpe["step"] * n
-    value = world * step_bytes / (ms_per_step * 1e-3) / 1e9
+    value = whole_job_gbs(world, step_bytes, ms_per_step)
 
     k_ms = {name: statistics.mean(e[i].elapsed_time(e[i + 1]) for e in per_kernel)
             for i, name in enumerate(("stats", "encode", "decode"))}
@@ -334,7 +359,9 @@ def run_b200(args):
             "peak_source": peak_src,
             "unit": "GB/s",
             "frac": round(k_gbs[dominant] / peak, 4),
-            "traffic": None,
+            "traffic": traffic_from_profile(dominant, args.log2n),
+            "traffic_source": "profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                              "`ncu --set full` launch at the same size (null when the size differs)",
             "algorithmic_bytes_per_launch": int(bpe[dominant] * n),
         },
         "packed": {"payload_bits_per_element": round(8 * bpe["packed"], 4),
