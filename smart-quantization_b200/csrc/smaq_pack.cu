@@ -752,12 +752,28 @@ __global__ void __launch_bounds__(kPackThreads, 4)
   constexpr int kSeg = seg_words(XB);
   constexpr int kMainEntries = 1 << PM, kOutEntries = 1 << (PM + XB);
   __shared__ float s_lut[kMainEntries + kOutEntries];  // [main | outlier], indexed by the stored value U
-  __shared__ uint32_t s_seg[kWarpsPerCta][kSeg + 2];
+  __shared__ uint32_t s_ext[kWarpsPerCta * kSeg + 2];  // the CTA tile's extras: all 8 segments, contiguous
   __shared__ uint32_t s_warp[kWarpsPerCta];
   const long long tile = blockIdx.x;
   const int lane = lane_id(), warp = warp_id();
   const int64_t wt = (int64_t)tile * kWarpsPerCta + warp;
   const int64_t base = wt * kWarpTile;
+
+  // Everything this CTA reads from HBM is requested up front, so the three dependent round trips of
+  // the naive order (header -> planes -> table -> extras) overlap: the CTA tile's extras range comes
+  // from the table alone, the warps' places inside it from the tag words.
+  const uint32_t ext_first = table[tile], ext_words = min(table[tile + 1] - ext_first, (uint32_t)(kWarpsPerCta * kSeg));
+  uint32_t tagw = 0, bw[PM];
+#pragma unroll
+  for (int w = 0; w < PM; ++w) bw[w] = 0;
+  if (base < n) {
+    const uint32_t* rec = planes + wt * (int64_t)((1 + PM) * 32) + lane;
+    tagw = __ldcs(rec);
+#pragma unroll
+    for (int w = 0; w < PM; ++w) bw[w] = __ldcs(rec + 32 * (w + 1));
+  }
+  for (uint32_t i = threadIdx.x; i < ext_words + 2; i += kPackThreads)
+    s_ext[i] = i < ext_words ? __ldcs(extras + (size_t)ext_first + i) : 0u;
 
   // The decoded value of every possible field, by the reference's own inverse (IEEE division).
   {
@@ -780,30 +796,18 @@ __global__ void __launch_bounds__(kPackThreads, 4)
     }
   }
 
-  uint32_t tagw = 0, bw[PM];
-#pragma unroll
-  for (int w = 0; w < PM; ++w) bw[w] = 0;
-  if (base < n) {
-    const uint32_t* rec = planes + wt * (int64_t)((1 + PM) * 32) + lane;
-    tagw = rec[0];
-#pragma unroll
-    for (int w = 0; w < PM; ++w) bw[w] = rec[32 * (w + 1)];
-  }
   // lane offsets inside the warp tile's segment; the segment's place inside the CTA tile
   const uint32_t nb = __popc(tagw) * XB;
   const uint32_t inc = warp_inclusive_scan(nb);
   const uint32_t my_words = (__shfl_sync(0xffffffffu, inc, 31) + 31) >> 5;
   if (lane == 0) s_warp[warp] = my_words;
-  __syncthreads();  // also publishes the table
-  uint32_t seg_off = table[tile];
+  __syncthreads();  // LUT, segment sizes and extras are in shared memory
+  uint32_t seg_off = 0;
 #pragma unroll
   for (int w = 0; w < kWarpsPerCta; ++w) seg_off += (w < warp) ? s_warp[w] : 0u;
-  for (uint32_t i = lane; i < my_words; i += 32) s_seg[warp][i] = extras[(size_t)seg_off + i];
-  if (lane < 2) s_seg[warp][my_words + lane] = 0;
-  __syncwarp();
   if (base >= n) return;
-  uint32_t pos = inc - nb;
-  const uint32_t* seg = s_seg[warp];
+  uint32_t pos = 32 * seg_off + inc - nb;  // bit position inside the CTA tile's extras
+  const uint32_t* seg = s_ext;
   const bool full = aligned && (base + kWarpTile <= n);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
