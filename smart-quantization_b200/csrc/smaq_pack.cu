@@ -551,20 +551,31 @@ __global__ void __launch_bounds__(kPackThreads, 3)
   const bool tma_ok = kCanHot && aligned;  // warp tiles wholly inside the tensor are staged by TMA
   const bool probs_vec = kStochastic && kHasProbs && aligned16(probs);
   const int64_t base0 = ((int64_t)first_tile * kWarpsPerCta + warp) * kWarpTile;  // + r * kCtaTile
-  auto issue = [&](int r) {
-    if (lane == 0) {
-      const int64_t b = base0 + (int64_t)r * kCtaTile;
-      if (tma_ok && b + kWarpTile <= n) {
-        const uint32_t dst = stage0 + (r % kStages) * kStageBytes, bar = bar0 + 8 * (r % kStages);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kStageBytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                     "l"(x + b), "r"(kStageBytes), "r"(bar)
-                     : "memory");
-      }
+  // rounds [0, r_full) of this warp lie wholly inside the tensor (staged by TMA); rounds [r_full, r_any)
+  // touch it (ragged last tile, or an unaligned tensor); later rounds are past its end
+  const int64_t left = n - base0;
+  const int r_any = left <= 0 ? 0 : (int)min((int64_t)nrounds, (left + kCtaTile - 1) / kCtaTile);
+  const int r_full = (!tma_ok || left < kWarpTile) ? 0 : (int)min((int64_t)nrounds, (left - kWarpTile) / kCtaTile + 1);
+  // running per-round state (64-bit products are formed once)
+  const float* x_next = x + base0;            // source of the next TMA request
+  int64_t wt = base0 >> 10;                    // warp tile index of the current round
+  uint32_t* rec = planes + wt * (int64_t)((1 + PM) * 32) + lane;
+  uint32_t* park = sc.staging + wt * (int64_t)kSeg + lane;
+  int r_issued = 0;
+  auto issue = [&]() {  // request round r_issued (if it is a staged one)
+    if (r_issued < r_full && lane == 0) {
+      const uint32_t dst = stage0 + (r_issued & 1) * kStageBytes, bar = bar0 + 8 * (r_issued & 1);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kStageBytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "l"(x_next), "r"(kStageBytes), "r"(bar)
+                   : "memory");
     }
+    x_next += kCtaTile;
+    ++r_issued;
   };
+  static_assert(kStages == 2, "stage index is r & 1");
   __syncwarp();
-  issue(0);  // in flight while thread 0 derives the constants
+  issue();  // round 0 is in flight while thread 0 derives the constants
 
   // per-tensor constants: derived once per CTA (IEEE divisions, a search loop) and broadcast
   if (threadIdx.x == 0) {
@@ -579,23 +590,21 @@ __global__ void __launch_bounds__(kPackThreads, 3)
   for (int gi = 0; gi < n_my_groups; ++gi) {
     uint32_t n_out_total = 0, n_sat_total = 0, words_total = 0;
     const int r_end = min(r + rounds, nrounds);
-    for (; r < r_end; ++r) {
-      if (r + 1 < nrounds) issue(r + 1);  // stage (r+1)%2 was fully consumed in round r-1 (__syncwarp below)
-      const int64_t base = base0 + (int64_t)r * kCtaTile;
-      if (base >= n) continue;  // warp tiles past the end of the tensor: nothing stored (uniform per warp)
-      const int64_t wt = base >> 10;
+    for (; r < r_end; ++r, wt += kWarpsPerCta, rec += kWarpsPerCta * (1 + PM) * 32, park += kWarpsPerCta * kSeg) {
+      issue();  // round r + 1: its stage was fully consumed in round r - 1 (__syncwarp below)
+      if (r >= r_any) continue;  // warp tiles past the end of the tensor: nothing stored (uniform per warp)
       ChunkBits ch[4];
-      if (tma_ok && base + kWarpTile <= n) {
-        mbar_wait(&s_bar[warp][r % kStages], (uint32_t)((r / kStages) & 1));
+      if (r < r_full) {
+        mbar_wait(&s_bar[warp][r & 1], (uint32_t)((r >> 1) & 1));
         if constexpr (kCanHot) {
           if (hot.ok)
-            hot_tile<kStochastic, kHasProbs, kCountSat>(stage0 + (r % kStages) * kStageBytes, probs, wt, probs_vec, kp, s,
-                                                        hot, ch, n_sat_total);
+            hot_tile<kStochastic, kHasProbs, kCountSat>(stage0 + (r & 1) * kStageBytes, probs, wt, probs_vec, kp, s, hot, ch,
+                                                        n_sat_total);
           else
-            generic_tile<PM, XB, kStochastic, kHasProbs>(x, n, probs, kp, s, base, ch, n_sat_total);
+            generic_tile<PM, XB, kStochastic, kHasProbs>(x, n, probs, kp, s, wt << 10, ch, n_sat_total);
         }
       } else {
-        generic_tile<PM, XB, kStochastic, kHasProbs>(x, n, probs, kp, s, base, ch, n_sat_total);
+        generic_tile<PM, XB, kStochastic, kHasProbs>(x, n, probs, kp, s, wt << 10, ch, n_sat_total);
       }
       __syncwarp();  // stage fully read (lane 0 may refill it)
 
@@ -603,7 +612,6 @@ __global__ void __launch_bounds__(kPackThreads, 3)
       uint32_t bw[PM];
       assemble_base<PM>(ch, bw);
       const uint32_t tagw = ch[0].tag | (ch[1].tag << 8) | (ch[2].tag << 16) | (ch[3].tag << 24);
-      uint32_t* rec = planes + wt * (int64_t)((1 + PM) * 32) + lane;
       rec[0] = tagw;
 #pragma unroll
       for (int w = 0; w < PM; ++w) rec[32 * (w + 1)] = bw[w];
@@ -644,7 +652,6 @@ __global__ void __launch_bounds__(kPackThreads, 3)
         }
         const uint32_t nwords = (__shfl_sync(0xffffffffu, inc, 31) + 31) >> 5;  // <= kSeg <= 128
         __syncwarp();
-        uint32_t* park = sc.staging + wt * (int64_t)kSeg + lane;
 #pragma unroll
         for (int j = 0; j < (kSeg + 31) / 32; ++j) {  // copy out and re-zero for the next tile
           if ((uint32_t)(32 * j + lane) < nwords) {
