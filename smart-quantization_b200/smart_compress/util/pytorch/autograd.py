@@ -68,3 +68,34 @@ def register_autograd_module(model: nn.Module, compress_fn, hparams: Namespace):
         module.forward = new_forward
 
     return model.apply(patch)
+
+
+class packed_saved_tensors(torch.autograd.graph.saved_tensors_hooks):
+    """Keep what autograd saves for backward as PACKED SmaQ streams (6/8 bits per element with the default
+    flags, one byte of capacity) instead of fp32 — the memory reduction the reference's README claims
+    (README.md:25) but its fake quantisation never delivers, since it stores fp32 (smart.py:154-172).
+
+    Not in the reference and it changes numerics (a saved activation is quantised once more, with its own
+    statistics), so it is opt-in::
+
+        with packed_saved_tensors(codec):
+            loss = model(x).sum()
+        loss.backward()
+
+    Parameters, small tensors (< ``min_numel``) and anything that is not CUDA fp32 are saved as they are.
+    Encoding and decoding run on the calling thread's current stream (the backward pass decodes on
+    autograd's worker thread).  Nothing synchronises: buffers are capacity-sized."""
+
+    def __init__(self, codec, min_numel: int = 1 << 16):
+        def pack(t: torch.Tensor):
+            if (isinstance(t, nn.Parameter) or not t.is_cuda or t.dtype != torch.float32 or t.numel() < min_numel
+                    or not t.is_floating_point()):
+                return t
+            return codec.encode(t.detach())
+
+        def unpack(obj):
+            if isinstance(obj, torch.Tensor):
+                return obj
+            return codec.decode(obj)
+
+        super().__init__(pack, unpack)

@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--no-batched-optimizer", action="store_true",
                     help="per-tensor optimizer-side calls (the reference's loop) instead of compress_many")
+    ap.add_argument("--packed-activations", action="store_true",
+                    help="keep autograd's saved tensors as packed SmaQ streams (not in the reference; changes numerics)")
     ap.add_argument("--only", default="forward,backward,weights,gradients,momentum_vectors",
                     help="which data structures are compressed (reference --no_compress_* flags)")
     return ap.parse_args()
@@ -131,9 +133,17 @@ def main():
     opt = wrap_optimizer(inner, fn, hp) if a.compress != "fp32" else inner
     net = nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
 
+    import contextlib
+
+    from smart_compress.util.pytorch.autograd import packed_saved_tensors
+
+    pack_codec = codec if hasattr(codec, "encode") else codec_and_hparams("smart", set())[0]
+
     def closure():
         opt.zero_grad(set_to_none=True)
-        loss = loss_fn(net)
+        ctx = packed_saved_tensors(pack_codec) if a.packed_activations else contextlib.nullcontext()
+        with ctx:
+            loss = loss_fn(net)
         loss.backward()
         return loss
 
@@ -165,6 +175,8 @@ def main():
             "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms_per_step, 3),
             "wall_ms_per_step": round(1e3 * wall / a.steps, 3), "higher_is_better": True, "scaling": "weak",
             "dtype": "f32", "data": "synthetic", "loss": float(last),
+            "peak_memory_gib": round(torch.cuda.max_memory_allocated() / 2**30, 2),
+            "packed_activations": bool(a.packed_activations),
             "config": {"workload": f"{a.model} random-init, synthetic batch {a.batch}/GPU" +
                        (f" {a.image}x{a.image}" if a.model.startswith("resnet") else f" seq {a.seq}") +
                        f", --compress {a.compress} on {a.only}", "optimizer": type(inner).__name__,
