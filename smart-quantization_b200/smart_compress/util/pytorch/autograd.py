@@ -83,13 +83,17 @@ class packed_saved_tensors(torch.autograd.graph.saved_tensors_hooks):
         loss.backward()
 
     Parameters, small tensors (< ``min_numel``) and anything that is not CUDA fp32 are saved as they are.
+    Caveat: SmaQ has no exact zero, so a saved ReLU *output* comes back with its zeros rounded to small
+    values of either sign and the backward mask ``output > 0`` is wrong for about half of the dead units;
+    pass ``keep=`` to leave such tensors alone (e.g. ``keep=lambda t: bool((t == 0).any())`` at the price of
+    a synchronisation), or use it with smooth activations.
     Encoding and decoding run on the calling thread's current stream (the backward pass decodes on
     autograd's worker thread).  Nothing synchronises: buffers are capacity-sized."""
 
-    def __init__(self, codec, min_numel: int = 1 << 16):
+    def __init__(self, codec, min_numel: int = 1 << 16, keep=None):
         def pack(t: torch.Tensor):
             if (isinstance(t, nn.Parameter) or not t.is_cuda or t.dtype != torch.float32 or t.numel() < min_numel
-                    or not t.is_floating_point()):
+                    or (keep is not None and keep(t))):
                 return t
             return codec.encode(t.detach())
 
