@@ -1,0 +1,143 @@
+"""Edge cases of the hot paths on a real device: special values inside otherwise ordinary tensors (they take
+the per-chunk detours of the packed encoder), exact-zero probabilities, the saturation counter switch, the
+fused statistics+round-trip entry point, workspace reuse across sizes, and concurrent callers."""
+import ctypes as C
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pack as opack
+from oracle.smaq import SmaqConfig, smaq_roundtrip
+from smart_compress import _native as N
+from tests import cabi, cabi_pack
+from tests.golden_util import assert_bit_equal
+from tests.test_gpu_smaq import make_outlier_tensor, make_plugin
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def encode_and_compare(x, cfg, probs, mean, std):
+    res = smaq_roundtrip(x, cfg, probs=probs, mean=mean, std=std)
+    ms = cabi.mean_std_tensor(res.mean, res.std, DEV)
+    pd = None if probs is None else probs.to(DEV)
+    buf, lay = cabi_pack.encode(x.to(DEV), ms, cabi.codec_params(cfg), cfg, probs=pd)
+    p = opack.pack(res, cfg)
+    hdr, table, planes, extras = cabi_pack.sections(buf, lay)
+    assert np.array_equal(planes, p.planes) and np.array_equal(table, p.table) and np.array_equal(extras, p.extras)
+    assert hdr.n_outlier == p.n_outlier and hdr.n_saturated == p.n_saturated
+    y = cabi_pack.decode(buf, lay)
+    assert_bit_equal(y.cpu(), opack.decode(p), "decode vs oracle decode")
+    return hdr
+
+
+@pytest.mark.parametrize("stochastic", [True, False])
+def test_special_values_inside_full_tiles(stochastic):
+    """NaN, +-inf, x == mean (z = 0), -0.0, denormals and huge values scattered through aligned, full warp tiles:
+    each one sends ONE 8-element chunk of the straight-line path to the IEEE-division re-run; everything must
+    still be byte-identical to the oracle."""
+    g = torch.Generator().manual_seed(21)
+    n = 64 * 1024
+    x = torch.randn(n, generator=g)
+    mean, std = torch.tensor(0.25), torch.tensor(1.5)
+    specials = [float("nan"), float("inf"), float("-inf"), 0.25, -0.0, 0.0, 1e-42, -1e-42, 3e38, -3e38, 0.25 + 1e-12,
+                0.25 - 1.5 * 2.0 ** -41, 1.75, -1.25, 4.0, -3.5]   # incl. |z| == 1 and |z| == 2.5 exactly
+    pos = torch.randperm(n, generator=g)[: 4 * len(specials)]
+    for i, p in enumerate(pos):
+        x[p] = specials[i % len(specials)]
+    probs = torch.rand(n, generator=g) if stochastic else None
+    cfg = SmaqConfig(stochastic_rounding=stochastic)
+    hdr = encode_and_compare(x, cfg, probs, mean, std)
+    assert hdr.n_saturated >= 4 * 5  # nan, +-inf, +-3e38
+
+
+def test_zero_probability_rounds_like_the_reference():
+    """p == 0 with a fractional part that rounds to 1.0 is the one case where rint(relu((frac - p) + 0.5)) is 2
+    (SURVEY.md §7.3 H2): the explicit-probs path must reproduce it on the straight-line path."""
+    n = 8192
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(n, generator=g)
+    probs = torch.rand(n, generator=g)
+    mean, std = torch.tensor(0.0), torch.tensor(1.0)
+    x[100] = -2.0 ** -30 / 15.0     # c = -2^-30: floor -1, frac rounds to 1.0
+    probs[100] = 0.0
+    x[4000] = -1e-6
+    probs[4000] = 0.0
+    cfg = SmaqConfig()
+    res = smaq_roundtrip(x, cfg, probs=probs, mean=mean, std=std)
+    assert res.code[100] == 1.0     # the reference's own quirk
+    encode_and_compare(x, cfg, probs, mean, std)
+    ms = cabi.mean_std_tensor(mean, std, DEV)
+    y = cabi.roundtrip(x.to(DEV), ms, cabi.codec_params(cfg), probs=probs.to(DEV))
+    assert_bit_equal(y.cpu(), res.y, "round trip with zero probabilities")
+
+
+def test_saturation_counter_is_optional():
+    x, g = make_outlier_tensor(100000, seed=9)
+    xd = x.to(DEV)
+    cfg = SmaqConfig()
+    ms = cabi.stats_full(xd)
+    on, lay = cabi_pack.encode(xd, ms, cabi.codec_params(cfg, seed=4, count_saturated=True), cfg)
+    off, _ = cabi_pack.encode(xd, ms, cabi.codec_params(cfg, seed=4, count_saturated=False), cfg)
+    h_on, h_off = cabi_pack.sections(on, lay)[0], cabi_pack.sections(off, lay)[0]
+    assert h_off.n_saturated == 2 ** 64 - 1 and 0 < h_on.n_saturated < x.numel()
+    used = lay.extras_off + 4 * h_on.extras_words
+    assert torch.equal(on[128:used], off[128:used])   # the stream itself does not depend on the switch
+    msc = ms.cpu()
+    z = (x - msc[0]) / msc[1]
+    c = torch.where(z.abs() > 1, (z - torch.sign(z)) * cfg.range_outlier, z * cfg.range_normal)
+    assert abs(int((c.abs() > 63).sum()) - h_on.n_saturated) <= 2   # fp32 vs this fp32-ish recomputation
+
+
+@pytest.mark.parametrize("n", [40000, (1 << 20) + 5])
+def test_fused_entry_point_equals_stats_then_roundtrip(n):
+    x, _ = make_outlier_tensor(n, seed=n)
+    xd = x.to(DEV)
+    cfg = SmaqConfig()
+    lib = N.load()
+    params = cabi.codec_params(cfg, seed=99, offset=3)
+    want = cabi.roundtrip(xd, cabi.stats_full(xd), params)
+    y = torch.empty_like(xd)
+    need = lib.smaq_compress_workspace_bytes(n)
+    ws = torch.empty(need + 4096, dtype=torch.uint8, device=DEV)   # larger than needed: reused scratch
+    for _ in range(2):                                              # twice on the same scratch
+        N.check(lib.smaq_compress(xd.data_ptr(), y.data_ptr(), n, None, C.byref(params), ws.data_ptr(), ws.numel(),
+                                  N.stream_ptr(xd.device)), "compress")
+        assert torch.equal(y.view(torch.int32), want.view(torch.int32))
+    small = torch.empty(16, dtype=torch.uint8, device=DEV)
+    assert lib.smaq_compress(xd.data_ptr(), y.data_ptr(), n, None, C.byref(params), small.data_ptr(), 16,
+                             N.stream_ptr(xd.device)) == 3          # SMAQ_ERR_WORKSPACE
+    assert b"workspace" in lib.smaq_b200_last_error()
+
+
+def test_plugin_scratch_reuse_across_sizes_and_threads():
+    """Forward calls come from the main thread, backward calls from autograd's worker: two threads, each on
+    its own stream, sharing one plugin instance, with tensor sizes that grow and shrink."""
+    fp = make_plugin(["--no_stochastic_rounding"])   # deterministic: results comparable across threads
+    sizes = [50000, 300000, 70000, 1 << 20, 33000]
+    xs = [torch.randn(s, device=DEV) for s in sizes]
+    want = [fp(x, tag="t").clone() for x in xs]
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker():
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(20):
+                    for x, w in zip(xs, want):
+                        y = fp(x, tag="t")
+                        if not torch.equal(y, w):
+                            errors.append("mismatch")
+            st.synchronize()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker) for _ in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
