@@ -371,36 +371,56 @@ def run_b200(args):
 
     # ---- end to end through the plugin API with host buffers ---------------------------------------------
     if not args.no_e2e:
-        e2e_steps = max(1, min(args.steps, 5))
+        e2e_steps = max(1, min(args.steps, 20))
         hx = torch.empty(n, dtype=torch.float32, pin_memory=True)
         hy = torch.empty(n, dtype=torch.float32, pin_memory=True)
         hx.copy_(x)
         fp = pipe.fp
-        dx = torch.empty_like(x)
-
-        def e2e_step():
-            dx.copy_(hx, non_blocking=True)          # host -> device, pinned
-            packed = fp.encode(dx)                   # statistics + quantise + pack
-            y = fp.decode(packed, out=pipe.y)        # unpack + de-normalise
-            hy.copy_(y, non_blocking=True)           # device -> host, pinned
-            return packed
-
         del x
         torch.cuda.empty_cache()
-        for _ in range(2):
-            e2e_step()
+        # A pipelined data path, as a loader would run it: step i's host->device copy (stream s_in), its
+        # statistics + encode + decode (s_comp) and the device->host read of its result (s_out) overlap with the
+        # neighbouring steps' — PCIe is full duplex.  Every step still moves its own 4N bytes in and 4N bytes out
+        # inside the timed region; device buffers are double-buffered and guarded by events.
+        s_in, s_comp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+        dxs = [torch.empty(n, dtype=torch.float32, device=device) for _ in range(2)]
+        dys = [pipe.y, torch.empty(n, dtype=torch.float32, device=device)]
+        done_in, done_comp, done_out = {}, {}, {}
+
+        def e2e_step(i):
+            b = i & 1
+            with torch.cuda.stream(s_in):
+                if i - 2 in done_comp:
+                    s_in.wait_event(done_comp[i - 2])    # dxs[b] was the input of step i-2
+                dxs[b].copy_(hx, non_blocking=True)       # host -> device, pinned
+                done_in[i] = s_in.record_event()
+            with torch.cuda.stream(s_comp):
+                s_comp.wait_event(done_in[i])
+                if i - 2 in done_out:
+                    s_comp.wait_event(done_out[i - 2])   # dys[b] was read back by step i-2
+                packed = fp.encode(dxs[b])                # statistics + quantise + pack
+                fp.decode(packed, out=dys[b])             # unpack + de-normalise
+                done_comp[i] = s_comp.record_event()
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done_comp[i])
+                hy.copy_(dys[b], non_blocking=True)       # device -> host, pinned
+                done_out[i] = s_out.record_event()
+
+        def run(first, count):
+            for i in range(first, first + count):
+                e2e_step(i)
+            torch.cuda.current_stream().wait_event(done_out[first + count - 1])
+
+        run(0, 2)
         barrier()
         t0, t1 = ev(), ev()
         t0.record()
-        for _ in range(e2e_steps):
-            e2e_step()
+        for st in (s_in, s_comp, s_out):
+            st.wait_event(t0)
+        run(2, e2e_steps)
         t1.record()
         barrier()
-        e_ms = t0.elapsed_time(t1)
-        if world > 1:
-            t = torch.tensor([e_ms], device=device, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e_ms = float(t.item())
+        e_ms = max_over_ranks(t0.elapsed_time(t1), world, device)
         e_ms /= e2e_steps
         result["e2e"] = {
             "value": round(world * step_bytes / (e_ms * 1e-3) / 1e9, 2),
@@ -409,11 +429,13 @@ def run_b200(args):
             "d2h_bytes_per_step": 4 * n,
             "ms_per_step": round(e_ms, 3),
             "steps": e2e_steps,
-            "api": "SmartFP.encode / SmartFP.decode (smart_compress.compress.smart) on pinned host buffers",
+            "api": "SmartFP.encode / SmartFP.decode (smart_compress.compress.smart) on pinned host buffers; three "
+                   "streams (copy in / compute / copy out), double-buffered: consecutive steps overlap on the full-duplex "
+                   "PCIe link",
             "checksum": float(hy[:: max(1, n // 4096)].double().sum()),
         }
-        x = dx
-        del hx, hy
+        x = dxs[0]
+        del hx, hy, dys
 
     # ---- size / codec sweep and the CPU baseline: rank 0 at N = 1 only ---------------------------------------
     if world == 1 and not args.no_sweep:
