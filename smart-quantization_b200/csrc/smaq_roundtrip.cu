@@ -76,12 +76,160 @@ __device__ __forceinline__ f32x8 roundtrip_group8(const f32x8& v, f32x8 pr, uint
   return o;
 }
 
+// ---- the same group of 8 on the straight-line path of the packed encoder (smaq_pack.cu) -------------------
+// Applies when the per-tensor constants allow the reference's operator sequence to be evaluated in
+// fewer instructions with bit-identical results (see make_rt_hot):
+//   * (z -+ t) * range_outlier == fma(z, range_outlier, -+K), K = t * range_outlier, because z -+ t is exact for a
+//     power-of-two t and |z| < 2^20 t: the outlier value is ONE predicated FMA over the main value z * range_main;
+//   * rint(relu((frac - p) + 0.5)) == [frac - p > 2^-25] for p > 0 (the in-kernel uniforms are (k + 1/2) / 2^16);
+//   * clamping c before rounding == clamping the rounded code (saturate);
+//   * the inverse of an outlier is q -+ (-t) == q + copysign(t, z).
+// Groups with a zero / denormal-range / NaN / huge quotient are re-run with the IEEE-division path.
+struct RtHot {
+  bool ok;
+  float nmean, nb, r;         // z = (x - mean) / b by div3: nb = -b, r = rn(1/b)
+  float thr, rm, ro, rm_r, ro_r;
+  uint32_t kbits, tbits;      // bits of K = t * ro, and of t
+  float z_lo, z_hi;
+  float lim_main, lim_out, std_mul, mean;
+};
+__device__ __forceinline__ RtHot make_rt_hot(const Scalars& s) {
+  RtHot h;
+  h.nmean = -s.mean;
+  h.mean = s.mean;
+  h.nb = -s.div.b;
+  h.r = s.div.r;
+  h.thr = s.thr;
+  h.rm = s.range_main.b;
+  h.ro = s.range_out.b;
+  h.rm_r = s.range_main.r;
+  h.ro_r = s.range_out.r;
+  const float K = mul_rn(s.thr, s.range_out.b);
+  h.kbits = bits_of(K);
+  h.tbits = bits_of(s.thr);
+  h.z_lo = 9.094947017729282e-13f;            // 2^-40
+  h.z_hi = mul_rn(s.thr, 1048576.0f);         // 2^20 t: z -+ t exact, codes far inside the fast inverse's range
+  h.lim_main = s.lim_main;
+  h.lim_out = s.lim_out;
+  h.std_mul = s.std_mul;
+  const bool thr_pow2 = (bits_of(s.thr) & 0x007FFFFFu) == 0u;
+  const bool k_exact = __fmaf_rn(s.thr, s.range_out.b, -K) == 0.0f;
+  h.ok = s.fast && thr_pow2 && k_exact && K < 1e6f && K > 1e-6f && s.thr < 1e6f && s.thr > 1e-6f;
+  return h;
+}
+__device__ __forceinline__ float rt_min3_nan_abs(float a, float b, float c) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)));
+  return r;
+}
+__device__ __forceinline__ float rt_max3_abs(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)));
+  return r;
+}
+__device__ __forceinline__ float rt_clamp_sym(float v, float lim) {  // copysign(min(|v|, lim), v)
+  float r;
+  asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "f"(lim));
+  return r;
+}
+
+template <bool kStochastic, bool kHasProbs, bool kAllPos, bool kSaturate>
+__device__ __forceinline__ f32x8 roundtrip_group8_hot(const f32x8& v, const f32x8& pr, uint64_t g, const Scalars& s,
+                                                      const RtHot& h, const KernelParams& kp) {
+  const f32x2 x[4] = {pair(v.a.x, v.a.y), pair(v.a.z, v.a.w), pair(v.b.x, v.b.y), pair(v.b.z, v.b.w)};
+  const f32x2 nmean2 = splat(h.nmean), nb2 = splat(h.nb), r2 = splat(h.r);
+  f32x2 z[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const f32x2 d = add2(x[q], nmean2);
+    const f32x2 qq = mul2(d, r2);
+    const f32x2 e = fma2(qq, nb2, d);
+    z[q] = fma2(e, r2, qq);                                                              // smart.py:154
+  }
+  const float m1 = rt_min3_nan_abs(z[0].x, z[0].y, z[1].x), m2 = rt_min3_nan_abs(z[1].y, z[2].x, z[2].y);
+  const float amin = min_nan(rt_min3_nan_abs(z[3].x, z[3].y, m1), m2);
+  const float x1 = rt_max3_abs(z[0].x, z[0].y, z[1].x), x2 = rt_max3_abs(z[1].y, z[2].x, z[2].y);
+  const float amax = rt_max3_abs(z[3].x, z[3].y, fmaxf(x1, x2));
+  if (!(amin >= h.z_lo) || amax > h.z_hi) {  // rare: the literal sequence with IEEE division
+    f32x8 p8 = pr;
+    if (kStochastic && !kHasProbs) {
+      const uint4 rr = philox_group(kp.keys, g, kp.offset);
+      const f32x2 p0 = uniform16_pair(rr.x), p1 = uniform16_pair(rr.y), p2 = uniform16_pair(rr.z), p3 = uniform16_pair(rr.w);
+      p8.a = make_float4(p0.x, p0.y, p1.x, p1.y);
+      p8.b = make_float4(p2.x, p2.y, p3.x, p3.y);
+    }
+    f32x8 o;
+    o.a = roundtrip_group_exact<kStochastic>(v.a, p8.a, s, kSaturate, kAllPos);
+    o.b = roundtrip_group_exact<kStochastic>(v.b, p8.b, s, kSaturate, kAllPos);
+    return o;
+  }
+  uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
+  if (kStochastic && !kHasProbs) rnd = philox_group(kp.keys, g, kp.offset);
+  const f32x2 rm2 = splat(h.rm), std2 = splat(h.std_mul);
+  float out[8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const f32x2 cm = mul2(z[q], rm2);                                                    // :164, main
+    const uint32_t zb0 = bits_of(z[q].x), zb1 = bits_of(z[q].y);
+    const bool P0 = fabsf(z[q].x) > h.thr, P1 = fabsf(z[q].y) > h.thr;                   // :155-157
+    const float k0 = from_bits((~zb0 & 0x80000000u) | h.kbits), k1 = from_bits((~zb1 & 0x80000000u) | h.kbits);
+    float c0 = P0 ? __fmaf_rn(z[q].x, h.ro, k0) : cm.x;                                  // :164, outlier
+    float c1 = P1 ? __fmaf_rn(z[q].y, h.ro, k1) : cm.y;
+    if (kSaturate) {  // the H1 rule of the packed format
+      c0 = rt_clamp_sym(c0, P0 ? h.lim_out : h.lim_main);
+      c1 = rt_clamp_sym(c1, P1 ? h.lim_out : h.lim_main);
+    }
+    const f32x2 c2 = pair(c0, c1);
+    f32x2 code;
+    if (kStochastic) {                                                                   // :93-98
+      const f32x2 f = pair(floorf(c0), floorf(c1));
+      const f32x2 frac = add2(c2, neg2(f));
+      f32x2 r;
+      if (kHasProbs) {
+        const float pa = q == 0 ? pr.a.x : q == 1 ? pr.a.z : q == 2 ? pr.b.x : pr.b.z;
+        const float pb = q == 0 ? pr.a.y : q == 1 ? pr.a.w : q == 2 ? pr.b.y : pr.b.w;
+        f32x2 u = add2(add2(frac, pair(-pa, -pb)), splat(0.5f));
+        u = pair(fmaxf(u.x, 0.0f), fmaxf(u.y, 0.0f));
+        r = add2(add2(u, splat(8388608.0f)), splat(-8388608.0f));                        // rint, 0 <= u < 2
+      } else {
+        const uint32_t w = q == 0 ? rnd.x : q == 1 ? rnd.y : q == 2 ? rnd.z : rnd.w;
+        const f32x2 kf = pair(from_bits(__byte_perm(w, 0x4B000000u, 0x7610)), from_bits(__byte_perm(w, 0x4B000000u, 0x7632)));
+        const f32x2 p = fma2(kf, splat(1.52587890625e-05f), splat(-127.99999237060546875f));  // (k + 1/2) / 2^16
+        const f32x2 t = add2(frac, neg2(p));
+        r = pair(t.x > 2.98023223876953125e-08f ? 1.0f : 0.0f, t.y > 2.98023223876953125e-08f ? 1.0f : 0.0f);
+      }
+      code = add2(f, r);
+    } else {
+      code = pair(truncf(c0), truncf(c1));                                               // :169
+    }
+    // inverse (:171-172): q = code / range, then q - shift == q + copysign(t, z) for an outlier, q for a main element
+    const f32x2 rb = pair(P0 ? h.ro : h.rm, P1 ? h.ro : h.rm), rr = pair(P0 ? h.ro_r : h.rm_r, P1 ? h.ro_r : h.rm_r);
+    const f32x2 qq = div3(code, rb, rr);
+    const float t0 = from_bits((zb0 & 0x80000000u) | h.tbits), t1 = from_bits((zb1 & 0x80000000u) | h.tbits);
+    const f32x2 yq = pair(P0 ? add_rn(qq.x, t0) : qq.x, P1 ? add_rn(qq.y, t1) : qq.y);
+    const f32x2 ym = mul2(yq, std2);
+    float y0 = add_rn(ym.x, h.mean), y1 = add_rn(ym.y, h.mean);  // product then sum: scalar adds (never an FFMA2)
+    if (kAllPos) {  // clamp_min(0): keeps NaN and -0 like torch
+      y0 = (y0 < 0.0f) ? 0.0f : y0;
+      y1 = (y1 < 0.0f) ? 0.0f : y1;
+    }
+    out[2 * q] = y0;
+    out[2 * q + 1] = y1;
+  }
+  f32x8 o;
+  o.a = make_float4(out[0], out[1], out[2], out[3]);
+  o.b = make_float4(out[4], out[5], out[6], out[7]);
+  return o;
+}
+
 constexpr int kRtThreads = 256;
 constexpr int kRtUnroll = 2;  // independent 256-bit loads in flight per thread
 
-template <bool kStochastic, bool kHasProbs, bool kAllPos, bool kSaturate, bool kFast>
+// kMode: 0 IEEE division everywhere; 1 three-instruction divisions (encode_pair / decode_pair); 2 the straight-line
+// path of roundtrip_group8_hot
+template <bool kStochastic, bool kHasProbs, bool kAllPos, bool kSaturate, int kMode>
 __device__ __forceinline__ void roundtrip_body(const float* x, float* y, int64_t n, const float* __restrict__ probs,
-                                               const KernelParams& kp, const Scalars& s) {
+                                               const KernelParams& kp, const Scalars& s, const RtHot& h) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   const int64_t ngroups = n >> 3;
@@ -116,9 +264,14 @@ __device__ __forceinline__ void roundtrip_body(const float* x, float* y, int64_t
 #pragma unroll
     for (int u = 0; u < kRtUnroll; ++u) {
       const int64_t gu = g + u * nthreads;
-      if (gu < ngroups)
-        stg_stream8(y + 8 * gu, roundtrip_group8<kStochastic, kHasProbs, kAllPos, kSaturate, kFast>(cur[u], curp[u],
-                                                                                                     (uint64_t)gu, s, kp));
+      if (gu < ngroups) {
+        if (kMode == 2)
+          stg_stream8(y + 8 * gu, roundtrip_group8_hot<kStochastic, kHasProbs, kAllPos, kSaturate>(cur[u], curp[u],
+                                                                                                    (uint64_t)gu, s, h, kp));
+        else
+          stg_stream8(y + 8 * gu, roundtrip_group8<kStochastic, kHasProbs, kAllPos, kSaturate, kMode == 1>(
+                                      cur[u], curp[u], (uint64_t)gu, s, kp));
+      }
     }
 #pragma unroll
     for (int u = 0; u < kRtUnroll; ++u) {
@@ -151,8 +304,10 @@ __global__ void __launch_bounds__(kRtThreads, 3) roundtrip_kernel(const float* x
   const Scalars s = scalars_from(mean_std[0], mean_std[1], kp);
   // uniform branch: the three-instruction division is valid for this tensor, or every division
   // is the IEEE one (degenerate statistics: huge/tiny/NaN std, mean == -0)
-  if (s.fast) roundtrip_body<kStochastic, kHasProbs, kAllPos, kSaturate, true>(x, y, n, probs, kp, s);
-  else roundtrip_body<kStochastic, kHasProbs, kAllPos, kSaturate, false>(x, y, n, probs, kp, s);
+  const RtHot h = make_rt_hot(s);
+  if (h.ok) roundtrip_body<kStochastic, kHasProbs, kAllPos, kSaturate, 2>(x, y, n, probs, kp, s, h);
+  else if (s.fast) roundtrip_body<kStochastic, kHasProbs, kAllPos, kSaturate, 1>(x, y, n, probs, kp, s, h);
+  else roundtrip_body<kStochastic, kHasProbs, kAllPos, kSaturate, 0>(x, y, n, probs, kp, s, h);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i = ((n >> 3) << 3) + tid;
   if (i < n) y[i] = roundtrip_element<kStochastic, kHasProbs>(x, probs, i, s, kp);

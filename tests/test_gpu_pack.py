@@ -149,7 +149,7 @@ def test_plugin_encode_decode_and_size_accounting():
     assert float(err[(xd - ms[0]).abs() <= 2.5 * ms[1]].max()) <= ms[1].item() / 15 + 1e-6
 
 
-@pytest.mark.parametrize("n", [1 << 28])
+@pytest.mark.parametrize("n", [1 << 28, 1 << 30])
 def test_full_size_properties(n):
     """Config-2 scale (256 Mi elements): no oracle at this size; size-independent properties instead —
     packed pipeline == fused kernel under the same Philox stream; header count == counting kernel;
