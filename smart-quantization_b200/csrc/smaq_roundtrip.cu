@@ -335,11 +335,13 @@ __device__ __forceinline__ int64_t small_groups(const float* x, float* y, int64_
                                                 const KernelParams& kp, const Scalars& s) {
   f32x8 zero8;
   zero8.a = zero8.b = make_float4(0.f, 0.f, 0.f, 0.f);
+  const RtHot h = make_rt_hot(s);
   const int64_t ngroups = n >> 3;
   for (int64_t g = threadIdx.x; g < ngroups; g += blockDim.x) {
     const f32x8 v = ldg_stream8(x + 8 * g);
     const f32x8 pr = (kStochastic && kHasProbs) ? ldg_stream8(probs + 8 * g) : zero8;
-    stg_stream8(y + 8 * g, roundtrip_group8<kStochastic, kHasProbs, kAllPos, false, true>(v, pr, (uint64_t)g, s, kp));
+    if (h.ok) stg_stream8(y + 8 * g, roundtrip_group8_hot<kStochastic, kHasProbs, kAllPos, false>(v, pr, (uint64_t)g, s, h, kp));
+    else stg_stream8(y + 8 * g, roundtrip_group8<kStochastic, kHasProbs, kAllPos, false, true>(v, pr, (uint64_t)g, s, kp));
   }
   return ngroups << 3;
 }
@@ -501,12 +503,17 @@ __device__ __forceinline__ void multi_apply_chunk(const float* x, float* y, int6
   f32x8 zero8;
   zero8.a = zero8.b = make_float4(0.f, 0.f, 0.f, 0.f);
   int64_t done = 0;
+  const RtHot h = make_rt_hot(s);
   if (vec) {
     const int64_t ngroups = len >> 3;
     for (int64_t g = threadIdx.x; g < ngroups; g += kStatsThreads) {
       const f32x8 v = ldg_stream8(x + start + 8 * g);
-      stg_stream8(y + start + 8 * g, roundtrip_group8<kStochastic, false, kAllPos, false, kFast>(
-                                          v, zero8, (uint64_t)((start >> 3) + g), s, k));
+      if (kFast && h.ok)
+        stg_stream8(y + start + 8 * g, roundtrip_group8_hot<kStochastic, false, kAllPos, false>(
+                                            v, zero8, (uint64_t)((start >> 3) + g), s, h, k));
+      else
+        stg_stream8(y + start + 8 * g, roundtrip_group8<kStochastic, false, kAllPos, false, kFast>(
+                                            v, zero8, (uint64_t)((start >> 3) + g), s, k));
     }
     done = ngroups << 3;
   }
