@@ -159,7 +159,7 @@ typedef struct smaq_packed_header {
   uint64_t n_saturated;      /* scaled values the field width cannot hold, or NaN (H1); ~0 when
                                 not counted (smaq_codec_params.count_saturated == 0) */
   uint64_t extras_words;     /* 32-bit words actually used in the extras section */
-  uint64_t status;           /* 0 ok; nonzero: encode aborted (look-back watchdog) */
+  uint64_t status;           /* 0 ok (reserved for failure codes) */
 } smaq_packed_header;
 
 int smaq_packed_layout_for(int64_t n, int32_t bits_main, int32_t bits_outlier, smaq_packed_layout* out);

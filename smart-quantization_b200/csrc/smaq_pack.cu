@@ -34,7 +34,7 @@
 //     IEEE division (generic_chunk);
 //   * the variable part — XB extra bits per OUTLIER — is placed inside the warp tile by a shuffle
 //     prefix scan of the per-lane bit counts and shared-memory atomicOr, then in the tensor by
-//     reduce-then-scan over three launches (no block ever waits for another).  Placement is
+//     reduce-then-scan over two launches (no block ever waits for another).  Placement is
 //     deterministic: the stream is byte-identical run to run;
 //   * the decoder is a table lookup: every (class, U) pair has ONE decoded value per tensor, so
 //     each CTA evaluates the reference's inverse (smart.py:171-172,181-182, IEEE division) for the
@@ -296,13 +296,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tma_load_tile(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -324,12 +317,14 @@ constexpr int kEncodeDynSmem = kWarpsPerCta * kStages * kStageBytes + 1024;  // 
 
 // Scratch of one encode call (device).  Placement of the variable-length part is
 // reduce-then-scan: pass 1 (the expensive one, one read of x) quantises, writes the fixed part of
-// the stream and parks every warp tile's extras segment at a fixed stride; pass 2 scans the
-// per-group word counts (one small block); pass 3 moves the segments to their dense positions.
-// No kernel ever waits on another block, so nothing here can hang, and the placement is a pure
-// function of the input: the stream is byte-identical run to run.  (A single-pass decoupled
-// look-back was measured first: with ~450 groups resident, each group's look-back walk under full
-// HBM load cost ~10x its own compute time.)
+// the stream, parks every warp tile's extras segment at a fixed stride and adds each group's word
+// count to its super-group's total (integer atomics: order-independent); the LAST CTA of pass 1 to
+// finish (atomic ticket) scans the n / 2 Mi super-group totals and writes the header; pass 2 (the
+// placement kernel) moves the segments to their dense positions.  No block ever waits on another,
+// so nothing here can hang, and the placement is a pure function of the input: the stream is
+// byte-identical run to run.  (Measured first: a single-pass decoupled look-back — with ~450 groups
+// resident each group's look-back walk under full HBM load cost ~10x its own compute time; and a
+// separate scan kernel over the per-group counts — 20 us plus a launch at 2^28 elements.)
 constexpr int kSuperShift = 6;  // groups per super-group = 64
 
 struct EncodeScratch {
@@ -457,7 +452,7 @@ __device__ __forceinline__ void generic_tile(const float* __restrict__ x, int64_
   }
 }
 
-// Pass 2, run by the LAST CTA of pass 1 to finish (atomic ticket): exclusive scan of the
+// Run by the LAST CTA of pass 1 to finish (atomic ticket): exclusive scan of the
 // super-group word counts (n / 2 Mi entries), header.
 __device__ __forceinline__ void finish_stream(const EncodeScratch& sc, const HeaderArgs& ha,
                                               const float* __restrict__ mean_std, const KernelParams& kp) {
@@ -695,7 +690,7 @@ __global__ void __launch_bounds__(kPackThreads, 3)
   if (s_last) finish_stream(sc, ha, mean_std, kp);
 }
 
-// Pass 3: move every parked segment to its dense position and write the per-CTA-tile table.  One
+// Pass 2: move every parked segment to its dense position and write the per-CTA-tile table.  One
 // CTA per group (<= 32 warp tiles); eight threads per segment, every load issued before the first
 // store: the pass is latency-bound (three dependent memory round trips), not bandwidth-bound.
 template <int XB>
