@@ -442,6 +442,7 @@ def run_b200(args):
         result["sweep"] = sweep(args, device, peak)
     if world == 1 and not args.no_cpu:
         result["cpu_baseline"] = cpu_baseline(bpe["step"], steps=3, warmup=1)
+        result["cpu_baseline"]["same_port_torch_eager_on_this_gpu"] = eager_gpu_baseline(bpe["step"], device)
 
     if rank == 0:
         print(json.dumps(result), flush=True)
@@ -542,6 +543,25 @@ def cpu_baseline(step_bytes_per_element, steps, warmup):
         "ms_per_step": round(best * 1e3, 1),
         "host_cpus": os.cpu_count(),
     }
+
+
+def eager_gpu_baseline(step_bytes_per_element, device, log2n=26, iters=5):
+    """Context, part of the baseline leg: the SAME port of smart.py:110-190 (oracle/smaq.py, ~26 eager torch
+    operators + rand_like + the `if std == 0` host sync) evaluated by torch's own CUDA kernels on this GPU —
+    what running the reference unchanged on a B200 would cost.  A reported baseline, never the product path."""
+    from oracle.smaq import SmaqConfig, smaq_roundtrip
+
+    n = 1 << log2n
+    x = make_input(n, device)
+    cfg = SmaqConfig()
+
+    def fn():
+        return smaq_roundtrip(x, cfg, probs=torch.rand_like(x)).y
+
+    ms, best = time_kernel(fn, iters=iters, warmup=2)
+    return {"ms_per_call": round(ms, 3), "value": round(step_bytes_per_element * n / (ms * 1e-3) / 1e9, 1), "unit": "GB/s",
+            "sample": f"2^{log2n} elements, median of {iters}; torch eager CUDA operators in the reference's order, credited "
+                      f"{step_bytes_per_element:.3f} algorithmic B/element like the GPU step"}
 
 
 def run_reference(args):
