@@ -577,8 +577,11 @@ __global__ void __launch_bounds__(kRtThreads) count_outliers_kernel(const float*
 static int rt_grid(int64_t n) {
   int sms = sm_count();
   if (sms <= 0) sms = 148;
+#ifndef SMAQ_RT_WAVES
+#define SMAQ_RT_WAVES 8
+#endif
   int64_t want = ((n + 7) / 8 + kRtThreads - 1) / kRtThreads;
-  int64_t cap = (int64_t)sms * 8;
+  int64_t cap = (int64_t)sms * SMAQ_RT_WAVES;
   if (want < 1) want = 1;
   return (int)(want < cap ? want : cap);
 }

@@ -143,7 +143,12 @@ __global__ void __launch_bounds__(32) sampled_draw_stats_kernel(const float* __r
 static int stats_grid(int64_t n) {
   int sms = sm_count();
   if (sms <= 0) sms = 148;
-  int64_t want = (n / 4 + kStatsThreads - 1) / kStatsThreads;  // one float4 per thread at least
+#ifndef SMAQ_STATS_EPT
+#define SMAQ_STATS_EPT 128
+#endif
+  // at least SMAQ_STATS_EPT elements per thread before the (fp64, shuffle-heavy) block combine: a small tensor
+  // must not pay one combine per float4 plus a 1000-partial merge in the last block
+  int64_t want = (n + (int64_t)kStatsThreads * SMAQ_STATS_EPT - 1) / ((int64_t)kStatsThreads * SMAQ_STATS_EPT);
   int64_t cap = (int64_t)sms * 8;                              // 8 x 256 threads = 2048 = full occupancy
   if (want < 1) want = 1;
   return (int)(want < cap ? want : cap);
