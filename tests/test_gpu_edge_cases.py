@@ -141,3 +141,23 @@ def test_plugin_scratch_reuse_across_sizes_and_threads():
     for t in threads:
         t.join()
     assert not errors, errors[:3]
+
+
+@pytest.mark.parametrize("t_main,t_out", [(1.5, 3.0), (0.75, 2.0), (2.0, 5.0), (0.5, 1.25), (1.0, 4.0), (3.0, 3.5)])
+@pytest.mark.parametrize("stochastic", [True, False])
+def test_other_thresholds_take_the_right_path(t_main, t_out, stochastic):
+    """The straight-line paths need a power-of-two main threshold (then (z -+ t) * range == fma(z, range, -+K)
+    exactly); any other threshold must fall back to the generic sequence — and both must stay bit-exact, in the
+    fused round trip and in the packed stream."""
+    n = 40000 + 1024 * 8
+    x, g = make_outlier_tensor(n, seed=int(100 * t_main + t_out))
+    probs = torch.rand(n, generator=g) if stochastic else None
+    cfg = SmaqConfig(main_std_dev_threshold=t_main, outlier_std_dev_threshold=t_out, stochastic_rounding=stochastic)
+    res = smaq_roundtrip(x, cfg, probs=probs)
+    ms = cabi.mean_std_tensor(res.mean, res.std, DEV)
+    pd = None if probs is None else probs.to(DEV)
+    y = cabi.roundtrip(x.to(DEV), ms, cabi.codec_params(cfg), probs=pd)
+    assert_bit_equal(y.cpu(), res.y, "round trip")
+    ysat = cabi.roundtrip(x.to(DEV), ms, cabi.codec_params(cfg, saturate=True), probs=pd)
+    assert_bit_equal(ysat.cpu(), smaq_roundtrip(x, cfg, probs=probs, saturate=True).y, "saturated round trip")
+    encode_and_compare(x, cfg, probs, res.mean, res.std)
