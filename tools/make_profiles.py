@@ -39,14 +39,14 @@ for idx, r in enumerate(rows[2:]):
                       "registers": int(g("launch__registers_per_thread")),
                       "issue_active_pct": round(g("smsp__issue_active.avg.pct_of_peak_sustained_active"), 1),
                       "dram_throughput_pct": round(g("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"), 1)}
-    regex = kname.split("(")[0].replace("void ", "").strip()
-    regex = regex.split("<")[0] + ("<" + regex.split("<")[1][:1] if short in ("stats", "s2fp8_stats", "fp8", "s2fp8_apply") else "")
+    base = kname.split("(")[0].replace("void ", "").strip().split("<")[0]
+    # ncu matches kernels by base name: pick this launch by its index among the launches of that name
+    nth = sum(1 for rr in rows[2:2 + idx] if rr[h.index("Kernel Name")].split("(")[0].replace("void ", "").strip().split("<")[0] == base)
     with open(os.path.join(out_dir, f"{tag}_{short}.txt"), "w") as f:
-        f.write(f"# ncu --set full --clock-control none, one launch, N = 2^{log2n} elements; source: {os.path.basename(rep)} (launch {idx})\n")
-        base = ["--kernel-name", f"regex:{regex.split('<')[0]}", "--launch-skip", "0"]
-        rpt = subprocess.run([sys.executable, os.path.join(here, "ncu_report.py"), rep, kname.split("(")[0].replace("void ", "").split("<")[0] +
-                              ("<" + kname.split("<")[1].split(",")[0] if "<" in kname and short in ("stats", "s2fp8_stats", "fp8", "s2fp8_apply") else ""),
-                              str(n)], capture_output=True, text=True).stdout
+        f.write(f"# ncu --set full --clock-control none, one launch, N = 2^{log2n} elements; source: {os.path.basename(rep)} "
+                f"(launch {idx}: {kname[:60]})\n")
+        rpt = subprocess.run([sys.executable, os.path.join(here, "ncu_report.py"), rep, "^" + base + "$", str(n), str(nth)],
+                             capture_output=True, text=True).stdout
         f.write(rpt)
 with open(os.path.join(out_dir, f"{tag}_traffic.json"), "w") as f:
     json.dump(traffic, f, indent=1)
