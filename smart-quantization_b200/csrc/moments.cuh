@@ -36,13 +36,28 @@ struct Acc {
   float lo, hi;
 };
 
+// S2FP8's L = (x == 0 ? 0 : log2|x|) (s2fp8.py:34-35) for the MEAN: lg2.approx (MUFU.LG2, absolute error ~2^-22,
+// subnormals supported) — the mean of 2^30 of them stays within 1e-7 of the exact one, well inside the 1e-6 bar
+// on statistics, and the pass becomes HBM-bound instead of libdevice-bound.  The MAXIMUM of L, which fixes alpha,
+// is not taken from these: it is log2f (libdevice, what torch evaluates) of max|x|, see finalize<2>.
 template <int kKind>
 __device__ __forceinline__ float transform(float v) {
   if (kKind == 2) {
-    float a = fabsf(v);
-    return a == 0.0f ? a : log2f(a);  // s2fp8.py:34-35 (torch.where(X_abs == 0, X_abs, log2(X_abs)))
+    const float a = fabsf(v);
+    return a == 0.0f ? a : __log2f(a);
   }
   return v;
+}
+
+// kind 2 tracks min|x| and max|x| of the RAW values (NaN-propagating like torch.max)
+template <int kCount>
+__device__ __forceinline__ void track_abs(float& lo, float& hi, const float (&raw)[kCount]) {
+#pragma unroll
+  for (int i = 0; i < kCount; ++i) {
+    const float a = fabsf(raw[i]);
+    hi = (a > hi || a != a) ? a : hi;
+    lo = (a < lo || a != a) ? a : lo;
+  }
 }
 
 // Merge a chunk of kCount transformed values held in registers.
@@ -66,12 +81,12 @@ __device__ __forceinline__ void merge_chunk(Acc& acc, const float (&v)[kCount]) 
   c.m2 = (double)m2 - (double)kCount * corr * corr;
   if (c.m2 < 0.0) c.m2 = 0.0;
   acc.m = merge(acc.m, c);
-  if (kKind != 0) {
+  if (kKind == 1) {
 #pragma unroll
     for (int i = 0; i < kCount; ++i) {
       // NaN-propagating min/max like torch.max / torch.min
       acc.hi = (v[i] > acc.hi || v[i] != v[i]) ? v[i] : acc.hi;
-      if (kKind == 1) acc.lo = (v[i] < acc.lo || v[i] != v[i]) ? v[i] : acc.lo;
+      acc.lo = (v[i] < acc.lo || v[i] != v[i]) ? v[i] : acc.lo;
     }
   }
 }
@@ -120,7 +135,11 @@ template <int kKind>
 __device__ __forceinline__ void finalize(const Acc& a, int unbiased, float* out) {
   if (kKind == 2) {
     out[0] = (float)a.m.mean;  // mu  (s2fp8.py:36)
-    out[1] = a.hi;             // m   (s2fp8.py:37)
+    // m = max(L) (s2fp8.py:37).  log2 is monotone, so max over the non-zero elements is log2f(max|x|); an exact
+    // zero contributes L = 0 (the reference's torch.where), which wins when every non-zero |x| is below 1
+    float m = (a.hi == 0.0f) ? 0.0f : log2f(a.hi);   // hi = max|x| (NaN propagates)
+    if (a.lo == 0.0f && m < 0.0f) m = 0.0f;          // lo = min|x|: a zero is present
+    out[1] = m;
     return;
   }
   out[0] = (float)a.m.mean;
