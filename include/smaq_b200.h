@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SMAQ_B200_ABI_VERSION 1
+#define SMAQ_B200_ABI_VERSION 2 /* 2: packed stream SQB2, count_saturated, smaq_compress, tensor_desc.stream */
 
 typedef void* smaq_stream_t; /* cudaStream_t */
 

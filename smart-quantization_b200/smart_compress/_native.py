@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libsmaq_b200.so")
 
 OK = 0
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class NativeLibraryError(RuntimeError):
