@@ -512,7 +512,12 @@ __device__ __forceinline__ void finish_stream(const EncodeScratch& sc, const Hea
 // shared memory, TMA is already filling the other stage with tile r+1 (across group boundaries
 // too).  The only block barrier is the one that closes a group.
 template <int PM, int XB, bool kStochastic, bool kHasProbs, bool kCountSat>
-__global__ void __launch_bounds__(kPackThreads, 3)
+// Two CTAs per SM (100 registers per thread) measured 1 % faster than three (79 registers): this kernel is bound
+// by what each warp can issue, not by latency hiding — 16 resident warps lose nothing against 24.
+#ifndef SMAQ_ENC_CTAS
+#define SMAQ_ENC_CTAS 2
+#endif
+__global__ void __launch_bounds__(kPackThreads, SMAQ_ENC_CTAS)
     encode_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ mean_std,
                   const float* __restrict__ probs, const __grid_constant__ KernelParams kp,
                   uint32_t* __restrict__ planes, EncodeScratch sc, long long n_cta_tiles, int rounds, int gpc,
