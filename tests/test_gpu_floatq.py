@@ -137,3 +137,68 @@ def test_s2fp8_plugin_vs_cpu_oracle_tolerance():
     assert close.float().mean().item() > 0.999
     assert bool(torch.isfinite(y).all())
     assert ((y == 0) == (x == 0)).all()
+
+
+def _s2_cases(case):
+    g = torch.Generator().manual_seed(len(case) * 17)
+    n = 40003
+    if case == "wide":  # |alpha * log2 a| far beyond 125: pow over- and underflows, quads decline
+        x = torch.exp2(torch.rand(n, generator=g) * 120 - 60) * torch.sign(torch.randn(n, generator=g))
+        return x, torch.tensor([-2.0, 1.0])
+    if case == "specials":  # inf / NaN / denormals / +-0 / 1.0 inside otherwise ordinary quads
+        x, _ = interesting_values(n, seed=11)
+        x = x * 1e-3
+        x[:20] = torch.tensor([0.0, -0.0, 1.0, -1.0, 1e-40, -1e-40, 1e-45, 1.1754944e-38, -1.1754942e-38, 3.4e38,
+                               float("inf"), -float("inf"), float("nan"), 0.5, 2.0, 1.0000001, 0.99999994, 3e-39,
+                               -0.0, 7.0])
+        return x, torch.tensor([-9.0, 3.0])
+    if case == "relu":  # half the elements are zeros of either sign
+        x = torch.randn(n, generator=g)
+        x[x < 0] = 0.0
+        x[::5] = -0.0
+        return x, None
+    if case == "tiny":  # magnitudes around FLT_MIN, denormals among them
+        x = torch.randn(n, generator=g) * 1e-37
+        x[::11] *= 1e-3
+        return x, None
+    if case == "steep":  # narrow distribution: alpha ~ 50, exponents saturate both ways
+        x = (1.0 + 0.05 * torch.randn(n, generator=g)) * 3.0
+        return x, None
+    if case == "constant":  # m == mu: alpha = inf, every scalar degenerate
+        return torch.full((n,), 0.37), None
+    raise KeyError(case)
+
+
+@pytest.mark.parametrize("rounding", ["stochastic", "nearest"])
+@pytest.mark.parametrize("case", ["wide", "specials", "relu", "tiny", "steep", "constant"])
+def test_s2fp8_apply_bit_exact_where_the_fast_path_declines(case, rounding):
+    """The packed pow fast path covers ordinary quads only; zeros, denormals, non-finite inputs, results outside
+    the normal range and degenerate scalars go to the direct formula.  Either way: the bits torch's CUDA ops give."""
+    x, mu_max = _s2_cases(case)
+    xd = x.to(DEV)
+    mu_max = cabi.s2fp8_stats(xd) if mu_max is None else mu_max.to(DEV)
+    g = torch.Generator().manual_seed(3)
+    if rounding == "stochastic":
+        r = torch.randint(0, 2**31 - 1, (x.numel(),), generator=g, dtype=torch.int32)
+        got = cabi.s2fp8_apply(xd, mu_max, cabi.floatq_params(5, 2), rand_bits=r.to(DEV))
+    else:
+        r = torch.full((x.numel(),), 1 << 20, dtype=torch.int32)  # adding half a step, then truncating == nearest
+        got = cabi.s2fp8_apply(xd, mu_max, cabi.floatq_params(5, 2, rounding=0))
+    want, _, _, _ = os2.s2fp8(xd, r, mu=mu_max[0].clone(), m=mu_max[1].clone())
+    diff = (got.view(torch.int32) != want.view(torch.int32)) & ~(torch.isnan(got) & torch.isnan(want))
+    assert int(diff.sum()) == 0, f"{case}: {int(diff.sum())} of {x.numel()} differ, first at {int(diff.nonzero()[0])}"
+
+
+def test_s2fp8_apply_in_kernel_philox_rounds_to_a_neighbour():
+    x, _ = s2_input((1 << 18) + 3, seed=21)
+    xd = x.to(DEV)
+    mu_max = cabi.s2fp8_stats(xd)
+    a = cabi.s2fp8_apply(xd, mu_max, cabi.floatq_params(5, 2, seed=4, offset=1))
+    b = cabi.s2fp8_apply(xd, mu_max, cabi.floatq_params(5, 2, seed=4, offset=1))
+    c = cabi.s2fp8_apply(xd, mu_max, cabi.floatq_params(5, 2, seed=4, offset=2))
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    lo = torch.zeros(x.numel(), dtype=torch.int32, device=DEV)
+    down = cabi.s2fp8_apply(xd, mu_max, cabi.floatq_params(5, 2), rand_bits=lo)
+    up = cabi.s2fp8_apply(xd, mu_max, cabi.floatq_params(5, 2), rand_bits=lo + ((1 << 21) - 1))
+    assert bool(((a == down) | (a == up)).all())
+    assert 0.2 < (a == up).float().mean().item() < 0.8
