@@ -36,28 +36,73 @@ struct Acc {
   float lo, hi;
 };
 
-// S2FP8's L = (x == 0 ? 0 : log2|x|) (s2fp8.py:34-35) for the MEAN: lg2.approx (MUFU.LG2, absolute error ~2^-22,
-// subnormals supported) — the mean of 2^30 of them stays within 1e-7 of the exact one, well inside the 1e-6 bar
-// on statistics, and the pass becomes HBM-bound instead of libdevice-bound.  The MAXIMUM of L, which fixes alpha,
-// is not taken from these: it is log2f (libdevice, what torch evaluates) of max|x|, see finalize<2>.
-template <int kKind>
-__device__ __forceinline__ float transform(float v) {
-  if (kKind == 2) {
-    const float a = fabsf(v);
-    return a == 0.0f ? a : __log2f(a);
-  }
-  return v;
-}
+// S2FP8's L = (x == 0 ? 0 : log2|x|) (s2fp8.py:34-35) for the MEAN: lg2.approx (MUFU.LG2, absolute error ~2^-22)
+// — the mean of 2^30 of them stays within 1e-7 of the exact one, well inside the 1e-6 bar on statistics, and the
+// pass becomes HBM-bound instead of libdevice-bound.  The MAXIMUM of L, which fixes alpha, is not taken from
+// these: it is log2f (libdevice, what torch evaluates) of max|x|, see finalize<2>.
 
-// kind 2 tracks min|x| and max|x| of the RAW values (NaN-propagating like torch.max)
+// ---- kind 2 (S2FP8): sum of L and min/max of |x| over a chunk held in registers ----------------------------
+// Only the MEAN of L is needed (no second moment), so the pass carries a double sum and an element count and
+// turns them into a Moments {n, mean, 0} at the end.  min|x| / max|x| propagate NaN like torch.max.
+struct LogSum {
+  double sum;
+  long long count;
+};
+__device__ __forceinline__ float lg2_ftz(float a) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ float stats_min3_nan(float a, float b, float c) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float stats_max3_nan(float a, float b, float c) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// A chunk whose smallest magnitude is a normal number (the common case) costs one MUFU.LG2 and one add per
+// element plus one three-input min/max: flush-to-zero lg2 is exact enough only there.  A chunk that holds a zero
+// (L = 0 by the reference's torch.where), a subnormal (needs the pre-scaled lg2) or a NaN takes the per-element
+// form.  kCount is 1 + 2k so that the running lo/hi complete the last three-input operation.
 template <int kCount>
-__device__ __forceinline__ void track_abs(float& lo, float& hi, const float (&raw)[kCount]) {
+__device__ __forceinline__ void log_chunk(LogSum& ls, float& lo, float& hi, const float (&raw)[kCount]) {
+  float a[kCount];
 #pragma unroll
-  for (int i = 0; i < kCount; ++i) {
-    const float a = fabsf(raw[i]);
-    hi = (a > hi || a != a) ? a : hi;
-    lo = (a < lo || a != a) ? a : lo;
+  for (int i = 0; i < kCount; ++i) a[i] = fabsf(raw[i]);
+  float cmin = a[0], cmax = a[0];
+#pragma unroll
+  for (int i = 1; i + 1 < kCount; i += 2) {
+    cmin = stats_min3_nan(cmin, a[i], a[i + 1]);
+    cmax = stats_max3_nan(cmax, a[i], a[i + 1]);
   }
+  if ((kCount & 1) == 0) {  // even count: the last element pairs with the running value
+    lo = stats_min3_nan(lo, cmin, a[kCount - 1]);
+    hi = stats_max3_nan(hi, cmax, a[kCount - 1]);
+  } else {
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(lo) : "f"(lo), "f"(cmin));
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(hi) : "f"(hi), "f"(cmax));
+  }
+  float chunk_min = cmin;
+  if ((kCount & 1) == 0) asm("min.NaN.f32 %0, %1, %2;" : "=f"(chunk_min) : "f"(cmin), "f"(a[kCount - 1]));
+  float l[kCount];
+  if (chunk_min >= 1.17549435e-38f) {  // false for NaN
+#pragma unroll
+    for (int i = 0; i < kCount; ++i) l[i] = lg2_ftz(a[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < kCount; ++i) l[i] = a[i] == 0.0f ? 0.0f : __log2f(a[i]);
+  }
+  // pairwise tree: short dependency chains, fixed order
+#pragma unroll
+  for (int w = 1; w < kCount; w <<= 1) {
+#pragma unroll
+    for (int i = 0; i + w < kCount; i += 2 * w) l[i] += l[i + w];
+  }
+  ls.sum += (double)l[0];
+  ls.count += kCount;
 }
 
 // Merge a chunk of kCount transformed values held in registers.

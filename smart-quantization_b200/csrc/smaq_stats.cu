@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(kStatsThreads) stats_kernel(const float* __res
   acc.m = Moments{0.0, 0.0, 0.0};
   acc.hi = -INFINITY;
   acc.lo = INFINITY;
+  LogSum ls = {0.0, 0};  // kind 2 only
 
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -45,31 +46,35 @@ __global__ void __launch_bounds__(kStatsThreads) stats_kernel(const float* __res
       float4 a = ldg_stream(xv + v), b = ldg_stream(xv + v + nthreads), c = ldg_stream(xv + v + 2 * nthreads),
              d = ldg_stream(xv + v + 3 * nthreads);
       float r[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
-      if (kKind == 2) track_abs<16>(acc.lo, acc.hi, r);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) r[i] = transform<kKind>(r[i]);
+      if (kKind == 2) {
+        log_chunk<16>(ls, acc.lo, acc.hi, r);
+        continue;
+      }
       merge_chunk<kKind, 16>(acc, r);
     }
     for (; v < nvec; v += nthreads) {
       float4 a = ldg_stream(xv + v);
-      float raw[4] = {a.x, a.y, a.z, a.w};
-      if (kKind == 2) track_abs<4>(acc.lo, acc.hi, raw);
-      float r[4] = {transform<kKind>(a.x), transform<kKind>(a.y), transform<kKind>(a.z), transform<kKind>(a.w)};
+      float r[4] = {a.x, a.y, a.z, a.w};
+      if (kKind == 2) {
+        log_chunk<4>(ls, acc.lo, acc.hi, r);
+        continue;
+      }
       merge_chunk<kKind, 4>(acc, r);
     }
     const int64_t tail = nvec << 2;
     if (tid < n - tail) {
       float raw[1] = {x[tail + tid]};
-      if (kKind == 2) track_abs<1>(acc.lo, acc.hi, raw);
-      merge_one<kKind>(acc, transform<kKind>(raw[0]));
+      if (kKind == 2) log_chunk<1>(ls, acc.lo, acc.hi, raw);
+      else merge_one<kKind>(acc, raw[0]);
     }
   } else {
     for (int64_t i = tid; i < n; i += nthreads) {
       float raw[1] = {x[i]};
-      if (kKind == 2) track_abs<1>(acc.lo, acc.hi, raw);
-      merge_one<kKind>(acc, transform<kKind>(raw[0]));
+      if (kKind == 2) log_chunk<1>(ls, acc.lo, acc.hi, raw);
+      else merge_one<kKind>(acc, raw[0]);
     }
   }
+  if (kKind == 2 && ls.count > 0) acc.m = Moments{(double)ls.count, ls.sum / (double)ls.count, 0.0};
 
   acc = block_combine<kKind>(acc, smem);
   if (threadIdx.x == 0) {

@@ -202,3 +202,31 @@ def test_s2fp8_apply_in_kernel_philox_rounds_to_a_neighbour():
     up = cabi.s2fp8_apply(xd, mu_max, cabi.floatq_params(5, 2), rand_bits=lo + ((1 << 21) - 1))
     assert bool(((a == down) | (a == up)).all())
     assert 0.2 < (a == up).float().mean().item() < 0.8
+
+
+@pytest.mark.parametrize("case", ["relu", "tiny", "steep", "nan", "inf", "all_zero", "one_zero"])
+def test_s2fp8_statistics_chunks_with_zeros_subnormals_and_non_finite(case):
+    """The statistics pass takes a lean route for chunks of normal numbers and a per-element one for chunks that
+    hold a zero (L = 0), a subnormal or a NaN: both against the fp64 evaluation of s2fp8.py:33-37."""
+    if case in ("relu", "tiny", "steep"):
+        x, _ = _s2_cases(case)
+    else:
+        x = torch.randn(100003, generator=torch.Generator().manual_seed(5)) * 0.3
+        if case == "nan":
+            x[77777] = float("nan")
+        elif case == "inf":
+            x[5] = -float("inf")
+        elif case == "all_zero":
+            x.zero_()
+        elif case == "one_zero":
+            x = x.abs() * 0.01 + 1e-4  # every log2 negative: the single zero's L = 0 is the maximum
+            x[31337] = 0.0
+    mu, m = os2.s2fp8_statistics(x.double())
+    got = cabi.s2fp8_stats(x.to(DEV)).cpu()
+    for g, w, tol in ((got[0].item(), mu.item(), 1e-6), (got[1].item(), m.item(), 2e-7)):
+        if w != w:
+            assert g != g
+        elif abs(w) == float("inf") or w == 0.0:
+            assert g == w
+        else:
+            assert abs(g - w) <= tol * abs(w), (case, g, w)
