@@ -201,6 +201,12 @@ int smaq_s2fp8_stats(const float* x, int64_t n, float* mu_max, void* ws, size_t 
 int smaq_s2fp8_apply(const float* x, float* y, int64_t n, const float* mu_max, const int32_t* rand_bits,
                      const smaq_floatq_params* params, smaq_stream_t stream);
 
+/* Test hook, not part of the reference's surface: out[i] = a[i] ** y[0] evaluated by the S2FP8 apply kernel's
+ * packed fast path for every group of four elements it accepts (accepted[i / 4] = 1), by powf otherwise.  The
+ * parity tests compare it bit for bit with torch.pow on the same GPU over all magnitudes: the quantised output
+ * of smaq_s2fp8_apply alone would hide a one-ulp difference with probability 1 - 2^-21 per element. */
+int smaq_selftest_pow(const float* a, const float* y, float* out, int32_t* accepted, int64_t n, smaq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,12 @@ __device__ __forceinline__ Moments merge(const Moments& a, const Moments& b) {
   double w = b.n / r.n;
   r.mean = a.mean + delta * w;
   r.m2 = a.m2 + b.m2 + delta * delta * (a.n * w);
+  if (!(fabs(delta) <= 1.7976931348623157e308)) {
+    // an infinite (or NaN) partial mean: torch's sum-then-divide keeps inf + inf = inf where the difference form
+    // would make NaN of it, and its second moment about an infinite mean is NaN
+    r.mean = a.mean * (a.n / r.n) + b.mean * w;
+    r.m2 = delta - delta;
+  }
   return r;
 }
 

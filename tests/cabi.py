@@ -117,5 +117,16 @@ def s2fp8_apply(x, mu_max, params, rand_bits=None):
     return y
 
 
+def selftest_pow(a, y):
+    """(a ** y, accepted-per-quad) through the S2FP8 fast path's pow (test hook)."""
+    lib = N.load()
+    out = torch.empty_like(a)
+    acc = torch.empty((a.numel() + 3) // 4, dtype=torch.int32, device=a.device)
+    yt = torch.tensor([float(y)], dtype=torch.float32, device=a.device)
+    N.check(lib.smaq_selftest_pow(a.data_ptr(), yt.data_ptr(), out.data_ptr(), acc.data_ptr(), a.numel(),
+                                  N.stream_ptr(a.device)), "selftest_pow")
+    return out, acc
+
+
 def mean_std_tensor(mean, std, dev):
     return torch.tensor([float(mean), float(std)], dtype=torch.float32, device=dev)

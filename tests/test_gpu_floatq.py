@@ -230,3 +230,37 @@ def test_s2fp8_statistics_chunks_with_zeros_subnormals_and_non_finite(case):
             assert g == w
         else:
             assert abs(g - w) <= tol * abs(w), (case, g, w)
+
+
+@pytest.mark.parametrize("y", [0.37, 1.0, 1.5, 2.0, 3.75, 7.3, 0.015625, 21.4, 1e-3, 63.0])
+def test_s2fp8_fast_pow_is_torch_pow_bit_for_bit(y):
+    """The packed pow restates libdevice's powf main line; here its RAW result (no quantisation to hide a last-bit
+    difference) against torch.pow with a tensor exponent — the op s2fp8.py:44 runs — over every binade."""
+    g = torch.Generator().manual_seed(int(y * 1000) + 1)
+    n = 1 << 22
+    bits = torch.randint(0x00800000, 0x7F800000, (n,), generator=g, dtype=torch.int32)  # every normal float
+    a = bits.view(torch.float32).clone()
+    near_one = 1.0 + (torch.rand(n // 4, generator=g) - 0.5) * 2.0 ** torch.randint(-23, 0, (n // 4,), generator=g).float()
+    a[: n // 4] = near_one.abs()
+    a[n // 4: n // 4 + 8] = torch.tensor([1.0, 2.0, 0.5, 1.17549435e-38, 3.4028234663852886e38, 0.99999994, 1.0000001, 4.0])
+    ad = a.to(DEV)
+    want = torch.pow(ad, torch.tensor(y, dtype=torch.float32, device=DEV))
+    got, acc = cabi.selftest_pow(ad, y)
+    diff = got.view(torch.int32) != want.view(torch.int32)
+    assert int(diff.sum()) == 0, f"y={y}: {int(diff.sum())} differ, e.g. a={a[diff.cpu()][:4].tolist()}"
+    frac = acc.float().mean().item()
+    # accepted iff |y * log2 a| <= 125 for the whole quad: most quads for small y, a shrinking share as y grows
+    assert frac > 0.0
+    if y <= 0.37:
+        assert frac > 0.99
+
+
+def test_s2fp8_fast_pow_declines_what_it_must():
+    a = torch.tensor([0.0, 1.0, 1.0, 1.0,   1e-40, 1.0, 1.0, 1.0,   float("inf"), 1.0, 1.0, 1.0,
+                      float("nan"), 1.0, 1.0, 1.0,   2.0 ** 100, 1.0, 1.0, 1.0,   2.0 ** -100, 1.0, 1.0, 1.0,
+                      3.0, 1.0, 0.5, 7.0], device=DEV)
+    got, acc = cabi.selftest_pow(a, 1.5)
+    assert acc.tolist() == [0, 0, 0, 0, 0, 0, 1]
+    want = torch.pow(a, torch.tensor(1.5, device=DEV))
+    same = (got.view(torch.int32) == want.view(torch.int32)) | (torch.isnan(got) & torch.isnan(want))
+    assert bool(same.all())
