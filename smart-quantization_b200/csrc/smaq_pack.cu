@@ -169,7 +169,9 @@ __device__ __forceinline__ float clamp_sym(float v, float lim) {
   return r;
 }
 __device__ __forceinline__ f32x2 fma2_rm(f32x2 a, f32x2 b, f32x2 c) {  // round towards -infinity
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(SMAQ_SCALAR_PAIRS)
+  return pair(__fmaf_rd(a.x, b.x, c.x), __fmaf_rd(a.y, b.y, c.y));
+#elif defined(__CUDA_ARCH__)
   unsigned long long r;
   asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pack2(a)), "l"(pack2(b)), "l"(pack2(c)));
   return unpack2(r);
