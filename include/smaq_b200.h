@@ -98,8 +98,12 @@ int smaq_roundtrip(const float* x, float* y, int64_t n, const float* mean_std, c
 
 /* The whole default call in one entry point — full-tensor unbiased statistics, then the round trip
  * (smart.py:130-182 with the reference's default flags): what the training hooks issue hundreds of
- * times per step.  The statistics live in the workspace (last 256 bytes: mean, std).  y may alias x. */
+ * times per step.  The statistics live in the workspace (last 256 bytes: mean, std).  y may alias x.
+ * The workspace is initialised ONCE after allocation with smaq_compress_workspace_init (it zeroes the arrival
+ * ticket of the statistics pass; every call leaves it zero again, so no memset node is issued per call).  Calls
+ * sharing a workspace must be ordered on one stream.  An uninitialised workspace gives undefined statistics. */
 size_t smaq_compress_workspace_bytes(int64_t n);
+int smaq_compress_workspace_init(void* ws, size_t ws_bytes, smaq_stream_t stream);
 int smaq_compress(const float* x, float* y, int64_t n, const float* probs, const smaq_codec_params* params,
                   void* ws, size_t ws_bytes, smaq_stream_t stream);
 

@@ -157,4 +157,8 @@ __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v) {
   return v;
 }
 
+// smaq_stats_full for a workspace whose ticket word is known to be zero (smaq_stats.cu; used by smaq_compress)
+int stats_full_zeroed_ws(const float* x, int64_t n, int unbiased, float* mean_std, void* ws, size_t ws_bytes,
+                         cudaStream_t stream);
+
 }  // namespace smaq

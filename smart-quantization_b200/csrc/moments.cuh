@@ -9,19 +9,31 @@ struct Moments {
   double n, mean, m2;
 };
 
+// 1 / n for a count n (an integer below 2^53 held in a double), to within an ulp or two: float reciprocal plus
+// two Newton steps.  A correctly rounded fp64 division is a ~40-instruction dependent chain, and a statistics
+// pass over a SMALL tensor is nothing but ~30 merges in sequence (per-thread chunks, five shuffle rounds, the
+// warps, the blocks): with the division the pass took 12 us however small the tensor.  The weight only scales
+// the difference of two partial means, so an ulp in it moves the mean by ~1e-16 of that difference.
+__device__ __forceinline__ double count_reciprocal(double n) {
+  double r = (double)__frcp_rn((float)n);
+  r = fma(r, fma(-n, r, 1.0), r);
+  r = fma(r, fma(-n, r, 1.0), r);
+  return r;
+}
+
 __device__ __forceinline__ Moments merge(const Moments& a, const Moments& b) {
   if (b.n == 0.0) return a;
   if (a.n == 0.0) return b;
   Moments r;
   r.n = a.n + b.n;
   double delta = b.mean - a.mean;
-  double w = b.n / r.n;
+  double w = b.n * count_reciprocal(r.n);
   r.mean = a.mean + delta * w;
   r.m2 = a.m2 + b.m2 + delta * delta * (a.n * w);
   if (!(fabs(delta) <= 1.7976931348623157e308)) {
     // an infinite (or NaN) partial mean: torch's sum-then-divide keeps inf + inf = inf where the difference form
     // would make NaN of it, and its second moment about an infinite mean is NaN
-    r.mean = a.mean * (a.n / r.n) + b.mean * w;
+    r.mean = a.mean * (a.n * count_reciprocal(r.n)) + b.mean * w;
     r.m2 = delta - delta;
   }
   return r;
@@ -154,31 +166,73 @@ constexpr int kPartialDoubles = 5;  // n, mean, m2, lo, hi
 __device__ __forceinline__ float nanmax(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
 __device__ __forceinline__ float nanmin(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
 
-template <int kKind>
-__device__ __forceinline__ Acc block_combine(Acc acc, Acc* smem /* [warps] */) {
+// ---- block-level combination without merges -----------------------------------------------------------------
+// Chan's pairwise merge costs a reciprocal and ~20 dependent fp64 operations, and a tree over a block is 8 of
+// them in sequence — twice per statistics kernel, which made a pass over a 256 KB tensor take 9 us.  The same
+// combination as two plain sums:   N = sum n_t,  mean = sum(n_t mean_t) / N,
+//                                  M2 = sum(m2_t + n_t (mean_t - mean)^2)
+// (the second needs the first's result): fp64 additions through a fixed shuffle tree — deterministic — and one
+// division.  Infinite / NaN partial means propagate as in merge(): mean = inf, M2 = NaN.
+__device__ __forceinline__ double shfl_xor_f64(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+
+// Sum of `a` and of `b` over the block, NaN-propagating max of hi and min of lo; the result is valid in EVERY
+// thread.  smem: one Acc per warp (fields reused: m.n <- a, m.mean <- b).  Ends with a barrier: smem is free.
+template <bool kMinMax>
+__device__ __forceinline__ void block_sum2(double& a, double& b, float& hi, float& lo, Acc* smem) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    Moments other = shfl_xor(acc.m, o);
-    // fixed pairing order: lower lane's data is always the left operand
-    acc.m = (lane_id() & o) ? merge(other, acc.m) : merge(acc.m, other);
-    if (kKind != 0) {
-      acc.hi = nanmax(acc.hi, __shfl_xor_sync(0xffffffffu, acc.hi, o));
-      acc.lo = nanmin(acc.lo, __shfl_xor_sync(0xffffffffu, acc.lo, o));
+    a += shfl_xor_f64(a, o);
+    b += shfl_xor_f64(b, o);
+    if (kMinMax) {
+      hi = nanmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      lo = nanmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
     }
   }
-  if (lane_id() == 0) smem[warp_id()] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    Acc t = smem[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
-      t.m = merge(t.m, smem[w].m);
-      t.hi = nanmax(t.hi, smem[w].hi);
-      t.lo = nanmin(t.lo, smem[w].lo);
-    }
-    acc = t;
+  if (lane_id() == 0) {
+    smem[warp_id()].m.n = a;
+    smem[warp_id()].m.mean = b;
+    smem[warp_id()].hi = hi;
+    smem[warp_id()].lo = lo;
   }
   __syncthreads();
-  return acc;  // valid in thread 0
+  const int warps = (int)(blockDim.x >> 5);
+  a = smem[0].m.n;
+  b = smem[0].m.mean;
+  hi = smem[0].hi;
+  lo = smem[0].lo;
+  for (int w = 1; w < warps; ++w) {  // same order in every thread
+    a += smem[w].m.n;
+    b += smem[w].m.mean;
+    if (kMinMax) {
+      hi = nanmax(hi, smem[w].hi);
+      lo = nanmin(lo, smem[w].lo);
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ double weighted_mean(double n, double s1) { return n > 0.0 ? s1 / n : 0.0; }
+// a partial's contribution to M2 about the combined mean
+__device__ __forceinline__ double m2_about(const Moments& m, double mean) {
+  if (m.n == 0.0) return 0.0;
+  const double d = m.mean - mean;
+  return m.m2 + m.n * (d * d);
+}
+
+template <int kKind>
+__device__ __forceinline__ Acc block_combine(Acc acc, Acc* smem /* [warps] */) {
+  double n = acc.m.n, s1 = acc.m.n == 0.0 ? 0.0 : acc.m.n * acc.m.mean;
+  float hi = acc.hi, lo = acc.lo;
+  block_sum2<kKind != 0>(n, s1, hi, lo, smem);
+  const double mean = weighted_mean(n, s1);
+  double q = m2_about(acc.m, mean), unused = 0.0;
+  float h2 = 0.f, l2 = 0.f;
+  block_sum2<false>(q, unused, h2, l2, smem);
+  Acc r;
+  r.m = Moments{n, mean, q};
+  r.hi = hi;
+  r.lo = lo;
+  return r;  // valid in every thread
 }
 
 // Final scalar step shared by the grid kernel and the small-tensor kernels.

@@ -665,8 +665,14 @@ int smaq_compress(const float* x, float* y, int64_t n, const float* probs, const
   const size_t sb = smaq_stats_workspace_bytes(n);
   if (!ws || ws_bytes < sb + 256) return fail(SMAQ_ERR_WORKSPACE, "compress: workspace too small (smaq_compress_workspace_bytes)");
   float* mean_std = (float*)((char*)ws + sb);
-  if (int rc = smaq_stats_full(x, n, /*unbiased=*/1, mean_std, ws, sb, stream)) return rc;
+  if (int rc = stats_full_zeroed_ws(x, n, /*unbiased=*/1, mean_std, ws, sb, (cudaStream_t)stream)) return rc;
   return smaq_roundtrip(x, y, n, mean_std, probs, params, stream);
+}
+
+int smaq_compress_workspace_init(void* ws, size_t ws_bytes, smaq_stream_t stream) {
+  if (!ws || ws_bytes < 16) return smaq::fail(SMAQ_ERR_WORKSPACE, "compress_workspace_init: workspace too small");
+  SMAQ_CUDA_OK(cudaMemsetAsync(ws, 0, 16, (cudaStream_t)stream));
+  return SMAQ_OK;
 }
 
 static int64_t multi_max_items(int32_t count, int64_t total_elems) {

@@ -77,6 +77,10 @@ __global__ void __launch_bounds__(kStatsThreads) stats_kernel(const float* __res
   if (kKind == 2 && ls.count > 0) acc.m = Moments{(double)ls.count, ls.sum / (double)ls.count, 0.0};
 
   acc = block_combine<kKind>(acc, smem);
+  if (gridDim.x == 1) {  // one block: nothing to hand over
+    if (threadIdx.x == 0) finalize<kKind>(acc, unbiased, out);
+    return;
+  }
   if (threadIdx.x == 0) {
     double* p = ws->partials + (size_t)blockIdx.x * kPartialDoubles;
     p[0] = acc.m.n; p[1] = acc.m.mean; p[2] = acc.m.m2; p[3] = (double)acc.lo; p[4] = (double)acc.hi;
@@ -88,19 +92,31 @@ __global__ void __launch_bounds__(kStatsThreads) stats_kernel(const float* __res
   if (!is_last) return;
   __threadfence();
 
-  // last block: combine the per-block moments in block order (fixed tree => deterministic)
-  Acc f;
-  f.m = Moments{0.0, 0.0, 0.0};
-  f.hi = -INFINITY;
-  f.lo = INFINITY;
+  // last block: the per-block moments by the same two sums (moments.cuh), partials re-read for the second
+  const double* parts = ws->partials;
+  double tn = 0.0, s1 = 0.0;
+  float hi = -INFINITY, lo = INFINITY;
   for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
-    const volatile double* p = ws->partials + (size_t)b * kPartialDoubles;
-    Moments m{p[0], p[1], p[2]};
-    f.m = merge(f.m, m);
-    f.lo = nanmin(f.lo, (float)p[3]);
-    f.hi = nanmax(f.hi, (float)p[4]);
+    const double* p = parts + (size_t)b * kPartialDoubles;
+    const double pn = __ldcg(p), pm = __ldcg(p + 1);
+    tn += pn;
+    s1 += pn == 0.0 ? 0.0 : pn * pm;
+    lo = nanmin(lo, (float)__ldcg(p + 3));
+    hi = nanmax(hi, (float)__ldcg(p + 4));
   }
-  f = block_combine<kKind>(f, smem);
+  block_sum2<true>(tn, s1, hi, lo, smem);
+  const double mean = weighted_mean(tn, s1);
+  double q = 0.0, unused = 0.0;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+    const double* p = parts + (size_t)b * kPartialDoubles;
+    q += m2_about(Moments{__ldcg(p), __ldcg(p + 1), __ldcg(p + 2)}, mean);
+  }
+  float h2 = 0.f, l2 = 0.f;
+  block_sum2<false>(q, unused, h2, l2, smem);
+  Acc f;
+  f.m = Moments{tn, mean, q};
+  f.hi = hi;
+  f.lo = lo;
   if (threadIdx.x == 0) {
     finalize<kKind>(f, unbiased, out);
     ws->ticket = 0;  // leave the workspace reusable
@@ -172,17 +188,24 @@ static int stats_grid(int64_t n) {
 
 template <int kKind>
 static int launch_stats(const float* x, int64_t n, int unbiased, float* out, void* ws, size_t ws_bytes,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, bool ticket_is_zero = false) {
   if (!x || !out || !ws || n <= 0) return fail(SMAQ_ERR_ARG, "stats: null pointer or n <= 0");
   if (ws_bytes < smaq_stats_workspace_bytes(n)) return fail(SMAQ_ERR_WORKSPACE, "stats: workspace too small");
   int grid = stats_grid(n);
-  SMAQ_CUDA_OK(cudaMemsetAsync(ws, 0, 16, stream));
+  // the arrival ticket must start at zero; the kernel's last block leaves it at zero again, so a workspace
+  // that was zeroed once (smaq_compress_workspace_init) needs no memset node per call
+  if (!ticket_is_zero && grid > 1) SMAQ_CUDA_OK(cudaMemsetAsync(ws, 0, 16, stream));
   if (aligned16(x))
     stats_kernel<kKind, true><<<grid, kStatsThreads, 0, stream>>>(x, n, unbiased, out, (StatsWs*)ws);
   else
     stats_kernel<kKind, false><<<grid, kStatsThreads, 0, stream>>>(x, n, unbiased, out, (StatsWs*)ws);
   SMAQ_LAUNCH_OK();
   return SMAQ_OK;
+}
+
+int stats_full_zeroed_ws(const float* x, int64_t n, int unbiased, float* mean_std, void* ws, size_t ws_bytes,
+                         cudaStream_t stream) {
+  return launch_stats<0>(x, n, unbiased, mean_std, ws, ws_bytes, stream, /*ticket_is_zero=*/true);
 }
 
 }  // namespace smaq

@@ -124,6 +124,7 @@ _SIGNATURES = {
     "smaq_stats_sampled_draw": (C.c_int, [_P, _I64, C.c_int32, C.c_uint64, C.c_uint64, _P, _P]),
     "smaq_roundtrip": (C.c_int, [_P, _P, _I64, _P, _P, C.POINTER(CodecParams), _P]),
     "smaq_compress_workspace_bytes": (C.c_size_t, [_I64]),
+    "smaq_compress_workspace_init": (C.c_int, [_P, C.c_size_t, _P]),
     "smaq_compress": (C.c_int, [_P, _P, _I64, _P, C.POINTER(CodecParams), _P, C.c_size_t, _P]),
     "smaq_count_outliers": (C.c_int, [_P, _I64, _P, C.POINTER(CodecParams), _P, _P]),
     "smaq_fused_small_max": (_I64, []),

@@ -178,6 +178,7 @@ class SmartFP(CompressionAlgorithmBase):
             need = lib.smaq_compress_workspace_bytes(numel)
             if ws is None or ws.numel() < need:
                 ws = self._call_ws[key] = torch.empty(need, dtype=torch.uint8, device=data.device)
+                N.check(lib.smaq_compress_workspace_init(N.ptr(ws), ws.numel(), stream), "smaq_compress_workspace_init")
             N.check(lib.smaq_compress(N.ptr(flat), N.ptr(out), numel, probs_ptr, C.byref(params), N.ptr(ws), ws.numel(),
                                       stream), "smaq_compress")
             return out

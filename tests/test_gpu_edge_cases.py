@@ -101,7 +101,8 @@ def test_fused_entry_point_equals_stats_then_roundtrip(n):
     want = cabi.roundtrip(xd, cabi.stats_full(xd), params)
     y = torch.empty_like(xd)
     need = lib.smaq_compress_workspace_bytes(n)
-    ws = torch.empty(need + 4096, dtype=torch.uint8, device=DEV)   # larger than needed: reused scratch
+    ws = torch.full((need + 4096,), 0xA5, dtype=torch.uint8, device=DEV)   # larger than needed, dirty: reused scratch
+    N.check(lib.smaq_compress_workspace_init(ws.data_ptr(), ws.numel(), N.stream_ptr(xd.device)), "init")  # once
     for _ in range(2):                                              # twice on the same scratch
         N.check(lib.smaq_compress(xd.data_ptr(), y.data_ptr(), n, None, C.byref(params), ws.data_ptr(), ws.numel(),
                                   N.stream_ptr(xd.device)), "compress")

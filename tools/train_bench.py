@@ -43,6 +43,8 @@ def parse():
                     help="per-tensor optimizer-side calls (the reference's loop) instead of compress_many")
     ap.add_argument("--packed-activations", action="store_true",
                     help="keep autograd's saved tensors as packed SmaQ streams (not in the reference; changes numerics)")
+    ap.add_argument("--profile", action="store_true",
+                    help="after the timed steps, run 3 more under torch.profiler and print GPU-busy time and the top kernels to stderr")
     ap.add_argument("--only", default="forward,backward,weights,gradients,momentum_vectors",
                     help="which data structures are compressed (reference --no_compress_* flags)")
     return ap.parse_args()
@@ -183,6 +185,25 @@ def main():
                        "batched_optimizer_side": not a.no_batched_optimizer},
             "codec_calls_per_step": {k: v // a.steps for k, v in sorted(calls.items(), key=lambda kv: str(kv[0]))},
         }))
+    if a.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                opt.step(closure)
+            torch.cuda.synchronize()
+        ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+        busy = sum(e.device_time for e in ev) / 3e3
+        ours = sum(e.device_time for e in ev if "smaq" in e.name or "floatq" in e.name) / 3e3
+        print(f"[profile] GPU busy {busy:.3f} ms/step of {ms_per_step:.3f}; codec kernels {ours:.3f} ms/step; "
+              f"{len(ev) // 3} GPU ops/step", file=sys.stderr)
+        agg = Counter()
+        cnt = Counter()
+        for e in ev:
+            agg[e.name[:70]] += e.device_time / 3e3
+            cnt[e.name[:70]] += 1
+        for k, v in agg.most_common(14):
+            print(f"[profile] {v:8.3f} ms  x{cnt[k] // 3:<4d} {k}", file=sys.stderr)
     if world > 1:
         dist.destroy_process_group()
 
