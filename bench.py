@@ -233,8 +233,10 @@ class Pipeline:
         return self.N.PackedHeader.from_buffer_copy(raw)
 
 
-def time_kernel(fn, iters=5, warmup=2):
-    """Median device time (ms) of fn() with CUDA events on the current stream."""
+def time_kernel(fn, iters=5, warmup=2, reps=1):
+    """Median device time (ms) of fn() with CUDA events on the current stream.  reps > 1: that many calls are
+    queued between the two events and the time divided — for launches so short that a pair of events around
+    ONE of them would mostly time the events."""
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -242,10 +244,11 @@ def time_kernel(fn, iters=5, warmup=2):
     for _ in range(iters):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        for _ in range(reps):
+            fn()
         b.record()
         b.synchronize()
-        times.append(a.elapsed_time(b))
+        times.append(a.elapsed_time(b) / reps)
     return statistics.median(times), min(times)
 
 
@@ -459,7 +462,9 @@ def sweep(args, device, peak):
     from smart_compress.util.pytorch.quantization import make_floatq_params
 
     lib = N.load()
-    out = {"smaq": [], "note": "median device ms of 5 launches after 2 warm-ups; sizes below ~2^25 fit in the 126 MB L2"}
+    out = {"smaq": [], "note": "median of 5 device timings after 2 warm-ups; up to 2^26 elements each timing queues 20 "
+                               "launches between the events (a lone short launch would mostly time the events) — those "
+                               "sizes fit in the 126 MB L2 and are partly bound by the host's launch rate"}
     fp = make_plugin()
     top = min(args.log2n, 30)
     for log2n in range(20, top + 1, 2):
@@ -474,11 +479,12 @@ def sweep(args, device, peak):
         sws_b = lib.smaq_stats_workspace_bytes(n)
         sws = torch.empty(sws_b, dtype=torch.uint8, device=device)
         st = N.stream_ptr(device)
-        t_stats, _ = time_kernel(lambda: lib.smaq_stats_full(x.data_ptr(), n, 1, ms.data_ptr(), sws.data_ptr(), sws_b, st))
-        t_rt, _ = time_kernel(lambda: lib.smaq_roundtrip(x.data_ptr(), y.data_ptr(), n, ms.data_ptr(), None, C.byref(params), st))
+        reps = 20 if log2n <= 26 else 1
+        t_stats, _ = time_kernel(lambda: lib.smaq_stats_full(x.data_ptr(), n, 1, ms.data_ptr(), sws.data_ptr(), sws_b, st), reps=reps)
+        t_rt, _ = time_kernel(lambda: lib.smaq_roundtrip(x.data_ptr(), y.data_ptr(), n, ms.data_ptr(), None, C.byref(params), st), reps=reps)
         t_enc, _ = time_kernel(lambda: lib.smaq_encode(x.data_ptr(), n, ms.data_ptr(), None, C.byref(params),
-                                                       packed.data_ptr(), packed.numel(), ws.data_ptr(), ws.numel(), st))
-        t_dec, _ = time_kernel(lambda: lib.smaq_decode(packed.data_ptr(), packed.numel(), n, 6, 8, 0, y.data_ptr(), st))
+                                                       packed.data_ptr(), packed.numel(), ws.data_ptr(), ws.numel(), st), reps=reps)
+        t_dec, _ = time_kernel(lambda: lib.smaq_decode(packed.data_ptr(), packed.numel(), n, 6, 8, 0, y.data_ptr(), st), reps=reps)
         hdr = N.PackedHeader.from_buffer_copy(bytes(packed[: C.sizeof(N.PackedHeader)].cpu().numpy()))
         bpe = bytes_per_element(hdr.n_outlier / n)
         row = {"log2n": log2n}

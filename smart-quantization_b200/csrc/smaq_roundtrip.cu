@@ -580,10 +580,14 @@ static int rt_grid(int64_t n) {
 #ifndef SMAQ_RT_WAVES
 #define SMAQ_RT_WAVES 8
 #endif
-  int64_t want = ((n + 7) / 8 + kRtThreads - 1) / kRtThreads;
-  int64_t cap = (int64_t)sms * SMAQ_RT_WAVES;
-  if (want < 1) want = 1;
-  return (int)(want < cap ? want : cap);
+  // One CTA per 256 groups of 8 while that fits one resident wave (3 CTAs of 80 registers per SM).  Beyond it
+  // threads loop: a mid-size tensor runs as exactly one wave (2.7 waves of short CTAs cost 2^21..2^23 elements up
+  // to 30 %: the third wave is mostly idle SMs), a huge one as SMAQ_RT_WAVES CTAs per SM slot (many short CTAs
+  // even out the tail: 2 % at 2^30).  tools/midsize_bench.py, bench.py sweep.
+  const int64_t want = ((n + 7) / 8 + kRtThreads - 1) / kRtThreads;
+  const int64_t wave = (int64_t)sms * 3;
+  if (want <= wave) return (int)(want < 1 ? 1 : want);
+  return (int)(want >= wave * 64 ? (int64_t)sms * SMAQ_RT_WAVES : wave);
 }
 
 template <bool kStochastic, bool kHasProbs>

@@ -176,12 +176,16 @@ static int stats_grid(int64_t n) {
   int sms = sm_count();
   if (sms <= 0) sms = 148;
 #ifndef SMAQ_STATS_EPT
-#define SMAQ_STATS_EPT 128
+#define SMAQ_STATS_EPT 16
 #endif
-  // at least SMAQ_STATS_EPT elements per thread before the (fp64, shuffle-heavy) block combine: a small tensor
-  // must not pay one combine per float4 plus a 1000-partial merge in the last block
+  // one 16-element chunk per thread until the grid fills ONE resident wave (4 CTAs per SM at ~56 registers), then
+  // threads loop.  Measured over 2^16..2^30 elements (tools/midsize_bench.py): a second wave only starts late, and
+  // 128 elements per thread made a 256 KB tensor wait out eight dependent memory round trips in two CTAs
   int64_t want = (n + (int64_t)kStatsThreads * SMAQ_STATS_EPT - 1) / ((int64_t)kStatsThreads * SMAQ_STATS_EPT);
-  int64_t cap = (int64_t)sms * 8;                              // 8 x 256 threads = 2048 = full occupancy
+#ifndef SMAQ_STATS_CTAS_PER_SM
+#define SMAQ_STATS_CTAS_PER_SM 4
+#endif
+  int64_t cap = (int64_t)sms * SMAQ_STATS_CTAS_PER_SM;
   if (want < 1) want = 1;
   return (int)(want < cap ? want : cap);
 }
