@@ -870,16 +870,25 @@ static int rounds_for(int64_t n_cta_tiles) {
   // CTA tiles per group: kMaxRounds unless the tensor is too small to give every SM a few groups
   int sms = sm_count();
   if (sms <= 0) sms = 148;
-  int64_t r = n_cta_tiles / ((int64_t)sms * 3 * 4);
+#ifndef SMAQ_ENC_ROUNDS_DIV
+#define SMAQ_ENC_ROUNDS_DIV 12
+#endif
+  int64_t r = n_cta_tiles / ((int64_t)sms * SMAQ_ENC_ROUNDS_DIV);
   return (int)(r < 1 ? 1 : (r > kMaxRounds ? kMaxRounds : r));
 }
-// Groups per CTA: long enough that the per-CTA set-up is amortised, short enough that the hardware
-// scheduler still has >= 8 CTAs per resident slot to balance the SMs with (measured: one CTA per
-// slot loses 7 % to the tail, one group per CTA loses 8 % to the set-up barrier).
+// Groups per CTA.  A CTA pipelines its groups (the next tile's TMA is in flight while the current one is
+// packed), so one group per CTA leaves every tile's load latency exposed: a 2^24-element tensor ran as 2048
+// one-group CTAs in 7 waves at 21 % of the HBM peak.  Rule: fill the resident slots (SMAQ_ENC_CTAS per SM) once,
+// then deepen the CTAs up to 8 groups, then add whole waves: w = ceil(groups / (8 slots)) waves of CTAs with
+// ceil(groups / (w slots)) groups each — full waves at every size, and for huge tensors the >= 8 CTAs per slot
+// the hardware scheduler needs to even out the tail (one CTA per slot measured 7 % slower at 2^30).
 static int groups_per_cta(int64_t n_groups) {
   int sms = sm_count();
   if (sms <= 0) sms = 148;
-  const int64_t g = n_groups / ((int64_t)sms * 3 * 8);
+  const int64_t slots = (int64_t)sms * SMAQ_ENC_CTAS;
+  if (n_groups <= slots) return 1;
+  const int64_t waves = (n_groups + 8 * slots - 1) / (8 * slots);
+  const int64_t g = (n_groups + waves * slots - 1) / (waves * slots);
   return (int)(g < 1 ? 1 : (g > 8 ? 8 : g));
 }
 

@@ -16,6 +16,8 @@ import torch  # noqa: E402
 
 from bench import make_input, make_plugin  # noqa: E402
 from smart_compress import _native as N  # noqa: E402
+from smart_compress.compress.packed import packed_layout  # noqa: E402
+from smart_compress.util.pytorch.quantization import make_floatq_params  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--min", type=int, default=14)
@@ -77,6 +79,18 @@ for log2n in range(a.min, a.max + 1):
     t_s = queued(lambda: lib.smaq_stats_full(x.data_ptr(), n, 1, ms.data_ptr(), sws.data_ptr(), sws_b, st), a.reps)
     t_r = queued(lambda: lib.smaq_roundtrip(x.data_ptr(), y.data_ptr(), n, ms.data_ptr(), None, C.byref(params), st), a.reps)
     t_f = queued(lambda: lib.smaq_compress(x.data_ptr(), y.data_ptr(), n, None, C.byref(params), cws.data_ptr(), cws_b, st), a.reps)
-    ku = kernel_us(lambda: lib.smaq_compress(x.data_ptr(), y.data_ptr(), n, None, C.byref(params), cws.data_ptr(), cws_b, st), 20)
+    lay = packed_layout(n, 6, 8)
+    packed = torch.empty(lay.total_capacity_bytes, dtype=torch.uint8, device=dev)
+    pws = torch.empty(lay.workspace_bytes, dtype=torch.uint8, device=dev)
+    p8 = make_floatq_params(5, 2, fp.hparams)
+
+    def everything():
+        lib.smaq_compress(x.data_ptr(), y.data_ptr(), n, None, C.byref(params), cws.data_ptr(), cws_b, st)
+        lib.smaq_encode(x.data_ptr(), n, ms.data_ptr(), None, C.byref(params), packed.data_ptr(), packed.numel(),
+                        pws.data_ptr(), pws.numel(), st)
+        lib.smaq_decode(packed.data_ptr(), packed.numel(), n, 6, 8, 0, y.data_ptr(), st)
+        lib.smaq_float_quantize(x.data_ptr(), y.data_ptr(), n, None, C.byref(p8), st)
+
+    ku = kernel_us(everything, 20)
     print(f"{log2n:>5} {4 * n / 2**20:>8.2f} {t_s:>9.2f} {t_r:>9.2f} {t_f:>9.2f} {12.0 * n / t_f / 1e3:>20.0f}   " +
           "  ".join(f"{k} {v:.2f}" for k, v in sorted(ku.items())))
