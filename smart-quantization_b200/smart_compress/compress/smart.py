@@ -64,8 +64,19 @@ class SmartFP(CompressionAlgorithmBase):
         self._tls = threading.local()
         self._small_max = int(N.load().smaq_fused_small_max())
         self._call_ws = {}               # (device, stream) -> scratch of the fused statistics + round-trip call
+        self._lib = N.load()
+        self._ws_bytes = None
         self._desc_cache = {}            # compress_many: device descriptor arrays by (pointers, sizes)
         self._multi_ws = {}
+
+    def _lean_flags(self) -> bool:
+        """Whether the flags allow the lean path of __call__ (read per call: tests and callers mutate hparams)."""
+        hp = self.hparams
+        try:
+            return not (hp.use_sample_stats or hp.use_range_std_dev or hp.use_batch_norm
+                        or hp.measure_compression_ratio) and hp.min_size <= self._small_max
+        except AttributeError:  # a hand-made Namespace without every flag: the general path uses getattr defaults
+            return False
 
     # ------------------------------------------------------------------------------------------
     def _params(self, all_positive: bool, saturate: bool = False, offset: Optional[int] = None) -> N.CodecParams:
@@ -128,7 +139,6 @@ class SmartFP(CompressionAlgorithmBase):
                     "smaq_stats_full")
         return out
 
-    @torch.no_grad()
     def __call__(
         self,
         data: torch.Tensor,
@@ -137,11 +147,48 @@ class SmartFP(CompressionAlgorithmBase):
         batch_norm_stats: Union[Tuple[torch.Tensor, torch.Tensor], None] = None,
         **extra,
     ):
-        profiler = Globals.profiler
-        if profiler is not None:
-            with profiler.profile("smaq"):
-                return self._call(data, tag, all_positive, batch_norm_stats, extra)
-        return self._call(data, tag, all_positive, batch_norm_stats, extra)
+        # The call the training hooks make hundreds of times per step — default statistics, no size accounting,
+        # no test kwargs, a contiguous fp32 CUDA tensor above the single-block size — goes straight to
+        # smaq_compress: the small configs are bound by the host's cost per call, and the general path below
+        # spends 10 us of Python around 7 us of launches.  Nothing here records autograd history (a fresh
+        # output buffer and raw pointers), so it needs no no_grad scope.
+        if not extra and batch_norm_stats is None and Globals.profiler is None and self._lean_flags():
+            numel = data.numel()
+            if (numel > self._small_max and data.dtype is torch.float32 and data.is_cuda and data.is_contiguous()
+                    and not data.is_sparse):
+                device = data.device
+                stream = N.stream_ptr(device)
+                key = (device.index, stream)
+                ws = self._call_ws.get(key)
+                lib = self._lib
+                if ws is None or ws.numel() < self._ws_need(numel):
+                    ws = self._grow_ws(key, numel, device, stream)
+                out = torch.empty_like(data)
+                rc = lib.smaq_compress(data.data_ptr(), out.data_ptr(), numel, None,
+                                       C.byref(self._params(bool(all_positive))), ws.data_ptr(), ws.numel(), stream)
+                if rc:
+                    N.check(rc, "smaq_compress")
+                return out
+        with torch.no_grad():
+            profiler = Globals.profiler
+            if profiler is not None:
+                with profiler.profile("smaq"):
+                    return self._call(data, tag, all_positive, batch_norm_stats, extra)
+            return self._call(data, tag, all_positive, batch_norm_stats, extra)
+
+    def _ws_need(self, numel: int) -> int:
+        # smaq_compress_workspace_bytes does not depend on the element count (per-block partials of a capped
+        # grid): ask once
+        need = self._ws_bytes
+        if need is None:
+            need = self._ws_bytes = int(self._lib.smaq_compress_workspace_bytes(numel))
+        return need
+
+    def _grow_ws(self, key, numel, device, stream):
+        need = int(self._lib.smaq_compress_workspace_bytes(numel))
+        ws = self._call_ws[key] = torch.empty(need, dtype=torch.uint8, device=device)
+        N.check(self._lib.smaq_compress_workspace_init(N.ptr(ws), ws.numel(), stream), "smaq_compress_workspace_init")
+        return ws
 
     def _call(self, data, tag, all_positive, batch_norm_stats, extra):
         hp = self.hparams
@@ -175,10 +222,8 @@ class SmartFP(CompressionAlgorithmBase):
             # grow-only scratch buffer per (device, stream) — calls on one stream are ordered
             key = (data.device.index, stream)
             ws = self._call_ws.get(key)
-            need = lib.smaq_compress_workspace_bytes(numel)
-            if ws is None or ws.numel() < need:
-                ws = self._call_ws[key] = torch.empty(need, dtype=torch.uint8, device=data.device)
-                N.check(lib.smaq_compress_workspace_init(N.ptr(ws), ws.numel(), stream), "smaq_compress_workspace_init")
+            if ws is None or ws.numel() < lib.smaq_compress_workspace_bytes(numel):
+                ws = self._grow_ws(key, numel, data.device, stream)
             N.check(lib.smaq_compress(N.ptr(flat), N.ptr(out), numel, probs_ptr, C.byref(params), N.ptr(ws), ws.numel(),
                                       stream), "smaq_compress")
             return out
