@@ -235,6 +235,157 @@ __device__ __forceinline__ Acc block_combine(Acc acc, Acc* smem /* [warps] */) {
   return r;  // valid in every thread
 }
 
+// ---- one pass over a tensor, and the grid-level hand-over --------------------------------------------------
+// Shared by the statistics kernel (smaq_stats.cu) and the single-launch statistics + round trip kernel
+// (smaq_roundtrip.cu).  Workspace: an arrival ticket and one record of kPartialDoubles doubles per block.
+struct StatsWs {
+  unsigned int ticket;
+  unsigned int pad[3];
+  double partials[1];  // [grid][kPartialDoubles]
+};
+
+// Thread `tid` of `nthreads`: a strided walk over the tensor, 4 independent 128-bit loads in flight per thread
+// (each warp-level load is 512 contiguous bytes), 16 values per chunked-Welford update.
+template <int kKind, bool kAligned>
+__device__ __forceinline__ Acc accumulate_tensor(const float* __restrict__ x, int64_t n, int64_t tid, int64_t nthreads) {
+  Acc acc;
+  acc.m = Moments{0.0, 0.0, 0.0};
+  acc.hi = -INFINITY;
+  acc.lo = INFINITY;
+  LogSum ls = {0.0, 0};  // kind 2 only
+  if (kAligned) {
+    const float4* xv = reinterpret_cast<const float4*>(x);
+    const int64_t nvec = n >> 2;
+    int64_t v = tid;
+    // Software pipeline: the four loads of the NEXT 16-element chunk are issued before the current chunk is
+    // merged, and the up to three single vectors left at the end go out together, ahead of the last chunk's
+    // merge — a thread's pass is one memory round trip plus arithmetic, not one round trip per chunk (a
+    // 2^24-element tensor was ten dependent round trips per thread: 20 us for 64 MB).  Chunks are merged in the
+    // same order as a plain loop would merge them: same bits.
+    float4 a, b, c, d;
+    bool have = v + 3 * nthreads < nvec;
+    if (have) {
+      a = ldg_stream(xv + v), b = ldg_stream(xv + v + nthreads), c = ldg_stream(xv + v + 2 * nthreads),
+      d = ldg_stream(xv + v + 3 * nthreads);
+      v += 4 * nthreads;
+    }
+    while (have) {
+      const float r[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+      have = v + 3 * nthreads < nvec;
+      if (have) {
+        a = ldg_stream(xv + v), b = ldg_stream(xv + v + nthreads), c = ldg_stream(xv + v + 2 * nthreads),
+        d = ldg_stream(xv + v + 3 * nthreads);
+        v += 4 * nthreads;
+      } else {
+        // the last whole chunk: its merge overlaps the single vectors' flight
+        const bool h0 = v < nvec, h1 = v + nthreads < nvec, h2 = v + 2 * nthreads < nvec;
+        if (h0) a = ldg_stream(xv + v);
+        if (h1) b = ldg_stream(xv + v + nthreads);
+        if (h2) c = ldg_stream(xv + v + 2 * nthreads);
+        if (kKind == 2) log_chunk<16>(ls, acc.lo, acc.hi, r);
+        else merge_chunk<kKind, 16>(acc, r);
+        v = nvec;  // consumed below
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const bool ht = t == 0 ? h0 : t == 1 ? h1 : h2;
+          const float4 q = t == 0 ? a : t == 1 ? b : c;
+          if (ht) {
+            const float r4[4] = {q.x, q.y, q.z, q.w};
+            if (kKind == 2) log_chunk<4>(ls, acc.lo, acc.hi, r4);
+            else merge_chunk<kKind, 4>(acc, r4);
+          }
+        }
+        break;
+      }
+      if (kKind == 2) log_chunk<16>(ls, acc.lo, acc.hi, r);
+      else merge_chunk<kKind, 16>(acc, r);
+    }
+    // a thread with fewer than four vectors in all: they go out together
+    if (v < nvec) {
+      const bool h1 = v + nthreads < nvec, h2 = v + 2 * nthreads < nvec;
+      a = ldg_stream(xv + v);
+      if (h1) b = ldg_stream(xv + v + nthreads);
+      if (h2) c = ldg_stream(xv + v + 2 * nthreads);
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const bool ht = t == 0 ? true : t == 1 ? h1 : h2;
+        const float4 q = t == 0 ? a : t == 1 ? b : c;
+        if (ht) {
+          const float r4[4] = {q.x, q.y, q.z, q.w};
+          if (kKind == 2) log_chunk<4>(ls, acc.lo, acc.hi, r4);
+          else merge_chunk<kKind, 4>(acc, r4);
+        }
+      }
+    }
+    const int64_t tail = nvec << 2;
+    if (tid < n - tail) {
+      float raw[1] = {x[tail + tid]};
+      if (kKind == 2) log_chunk<1>(ls, acc.lo, acc.hi, raw);
+      else merge_one<kKind>(acc, raw[0]);
+    }
+  } else {
+    for (int64_t i = tid; i < n; i += nthreads) {
+      float raw[1] = {x[i]};
+      if (kKind == 2) log_chunk<1>(ls, acc.lo, acc.hi, raw);
+      else merge_one<kKind>(acc, raw[0]);
+    }
+  }
+  if (kKind == 2 && ls.count > 0) acc.m = Moments{(double)ls.count, ls.sum / (double)ls.count, 0.0};
+  return acc;
+}
+
+__device__ __forceinline__ void store_partial(StatsWs* ws, unsigned int block, const Acc& acc) {
+  double* p = ws->partials + (size_t)block * kPartialDoubles;
+  p[0] = acc.m.n; p[1] = acc.m.mean; p[2] = acc.m.m2; p[3] = (double)acc.lo; p[4] = (double)acc.hi;
+}
+
+// The per-block records of `count` blocks combined by one block, by the same two sums as block_combine; fixed
+// order, the result is valid in every thread.  The second sum needs the first's result: a thread keeps its first
+// three records in registers (every grid the statistics kernel launches: <= 3 per thread), so the records make ONE
+// trip from L2, and re-reads only what lies beyond.
+__device__ __forceinline__ Acc combine_partials(const StatsWs* ws, int count, Acc* smem) {
+  const double* parts = ws->partials;
+  constexpr int kHeld = 3;
+  Moments held[kHeld];
+  double tn = 0.0, s1 = 0.0;
+  float hi = -INFINITY, lo = INFINITY;
+  int slot = 0;
+  for (int b = threadIdx.x; b < count; b += blockDim.x, ++slot) {
+    const double* p = parts + (size_t)b * kPartialDoubles;
+    const Moments m{__ldcg(p), __ldcg(p + 1), __ldcg(p + 2)};
+#pragma unroll
+    for (int k = 0; k < kHeld; ++k)
+      if (slot == k) held[k] = m;
+    tn += m.n;
+    s1 += m.n == 0.0 ? 0.0 : m.n * m.mean;
+    lo = nanmin(lo, (float)__ldcg(p + 3));
+    hi = nanmax(hi, (float)__ldcg(p + 4));
+  }
+  block_sum2<true>(tn, s1, hi, lo, smem);
+  const double mean = weighted_mean(tn, s1);
+  double q = 0.0, unused = 0.0;
+  slot = 0;
+  for (int b = threadIdx.x; b < count; b += blockDim.x, ++slot) {
+    Moments m;
+    if (slot < kHeld) {
+#pragma unroll
+      for (int k = 0; k < kHeld; ++k)
+        if (slot == k) m = held[k];
+    } else {
+      const double* p = parts + (size_t)b * kPartialDoubles;
+      m = Moments{__ldcg(p), __ldcg(p + 1), __ldcg(p + 2)};
+    }
+    q += m2_about(m, mean);
+  }
+  float h2 = 0.f, l2 = 0.f;
+  block_sum2<false>(q, unused, h2, l2, smem);
+  Acc f;
+  f.m = Moments{tn, mean, q};
+  f.hi = hi;
+  f.lo = lo;
+  return f;
+}
+
 // Final scalar step shared by the grid kernel and the small-tensor kernels.
 template <int kKind>
 __device__ __forceinline__ void finalize(const Acc& a, int unbiased, float* out) {

@@ -10,6 +10,8 @@
 // (profiles/): the kernel is bound by instruction issue, so the element loop is written to
 // minimise issue slots — packed FADD2/FMUL2/FFMA2 arithmetic, three-instruction divisions
 // checked once per four elements, Philox round keys as constant-bank operands.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "moments.cuh"
 #include "params.cuh"
@@ -225,11 +227,38 @@ __device__ __forceinline__ f32x8 roundtrip_group8_hot(const f32x8& v, const f32x
 constexpr int kRtThreads = 256;
 constexpr int kRtUnroll = 2;  // independent 256-bit loads in flight per thread
 
+// The first loads of a thread's software pipeline.  They depend on nothing but the tensor, so the launch behind the
+// statistics kernel issues them BEFORE it waits for the statistics.
+struct RtFirst {
+  f32x8 x[kRtUnroll], p[kRtUnroll];
+};
+template <bool kWithProbs>
+__device__ __forceinline__ RtFirst roundtrip_first_loads(const float* x, const float* __restrict__ probs, int64_t n) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t ngroups = n >> 3;
+  RtFirst f;
+#pragma unroll
+  for (int u = 0; u < kRtUnroll; ++u) {
+    const int64_t gu = tid + u * nthreads;
+    f.x[u].a = f.x[u].b = make_float4(0.f, 0.f, 0.f, 0.f);
+    f.p[u] = f.x[u];
+    if (gu < ngroups) {
+      f.x[u] = ldg_stream8(x + 8 * gu);
+      if (kWithProbs) f.p[u] = ldg_stream8(probs + 8 * gu);
+    }
+  }
+  return f;
+}
+
 // kMode: 0 IEEE division everywhere; 1 three-instruction divisions (encode_pair / decode_pair); 2 the straight-line
-// path of roundtrip_group8_hot
-template <bool kStochastic, bool kHasProbs, bool kAllPos, bool kSaturate, int kMode>
+// path of roundtrip_group8_hot.  kPrefetched: the pipeline's first loads were issued by the caller (`first`);
+// otherwise they are issued here (the plain kernel: issuing them before the per-tensor scalars are set up cost it
+// 4 % at 2^30 elements).
+template <bool kStochastic, bool kHasProbs, bool kAllPos, bool kSaturate, int kMode, bool kPrefetched>
 __device__ __forceinline__ void roundtrip_body(const float* x, float* y, int64_t n, const float* __restrict__ probs,
-                                               const KernelParams& kp, const Scalars& s, const RtHot& h) {
+                                               const KernelParams& kp, const Scalars& s, const RtHot& h,
+                                               const RtFirst& first) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   const int64_t ngroups = n >> 3;
@@ -242,11 +271,16 @@ __device__ __forceinline__ void roundtrip_body(const float* x, float* y, int64_t
   f32x8 cur[kRtUnroll], curp[kRtUnroll];
 #pragma unroll
   for (int u = 0; u < kRtUnroll; ++u) {
-    const int64_t gu = g + u * nthreads;
-    cur[u] = curp[u] = zero8;
-    if (gu < ngroups) {
-      cur[u] = ldg_stream8(x + 8 * gu);
-      if (kStochastic && kHasProbs) curp[u] = ldg_stream8(probs + 8 * gu);
+    if (kPrefetched) {
+      cur[u] = first.x[u];
+      curp[u] = first.p[u];
+    } else {
+      const int64_t gu = g + u * nthreads;
+      cur[u] = curp[u] = zero8;
+      if (gu < ngroups) {
+        cur[u] = ldg_stream8(x + 8 * gu);
+        if (kStochastic && kHasProbs) curp[u] = ldg_stream8(probs + 8 * gu);
+      }
     }
   }
   while (g < ngroups) {
@@ -295,6 +329,21 @@ __device__ __forceinline__ float roundtrip_element(const float* x, const float* 
   return roundtrip_scalar<kStochastic>(x[i], p, s, kp.saturate != 0, kp.all_positive != 0);
 }
 
+// Everything after the statistics are known: the tensor-uniform choice of arithmetic, the vector loop, the tail.
+template <bool kStochastic, bool kHasProbs, bool kAllPos, bool kSaturate, bool kPrefetched>
+__device__ __forceinline__ void roundtrip_tensor(const float* x, float* y, int64_t n, const float* __restrict__ probs,
+                                                 const KernelParams& kp, const Scalars& s, const RtFirst& first) {
+  // uniform branch: the three-instruction division is valid for this tensor, or every division
+  // is the IEEE one (degenerate statistics: huge/tiny/NaN std, mean == -0)
+  const RtHot h = make_rt_hot(s);
+  if (h.ok) roundtrip_body<kStochastic, kHasProbs, kAllPos, kSaturate, 2, kPrefetched>(x, y, n, probs, kp, s, h, first);
+  else if (s.fast) roundtrip_body<kStochastic, kHasProbs, kAllPos, kSaturate, 1, kPrefetched>(x, y, n, probs, kp, s, h, first);
+  else roundtrip_body<kStochastic, kHasProbs, kAllPos, kSaturate, 0, kPrefetched>(x, y, n, probs, kp, s, h, first);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = ((n >> 3) << 3) + tid;
+  if (i < n) y[i] = roundtrip_element<kStochastic, kHasProbs>(x, probs, i, s, kp);
+}
+
 // 32-byte aligned tensors: 256-bit path for whole groups of 8, element path for the last n % 8.
 template <bool kStochastic, bool kHasProbs, bool kAllPos, bool kSaturate>
 __global__ void __launch_bounds__(kRtThreads, 3) roundtrip_kernel(const float* x, float* y, int64_t n,
@@ -302,15 +351,28 @@ __global__ void __launch_bounds__(kRtThreads, 3) roundtrip_kernel(const float* x
                                                                const float* __restrict__ probs,
                                                                const __grid_constant__ KernelParams kp) {
   const Scalars s = scalars_from(mean_std[0], mean_std[1], kp);
-  // uniform branch: the three-instruction division is valid for this tensor, or every division
-  // is the IEEE one (degenerate statistics: huge/tiny/NaN std, mean == -0)
-  const RtHot h = make_rt_hot(s);
-  if (h.ok) roundtrip_body<kStochastic, kHasProbs, kAllPos, kSaturate, 2>(x, y, n, probs, kp, s, h);
-  else if (s.fast) roundtrip_body<kStochastic, kHasProbs, kAllPos, kSaturate, 1>(x, y, n, probs, kp, s, h);
-  else roundtrip_body<kStochastic, kHasProbs, kAllPos, kSaturate, 0>(x, y, n, probs, kp, s, h);
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i = ((n >> 3) << 3) + tid;
-  if (i < n) y[i] = roundtrip_element<kStochastic, kHasProbs>(x, probs, i, s, kp);
+  RtFirst none;  // unused: the body issues its own first loads
+  roundtrip_tensor<kStochastic, kHasProbs, kAllPos, kSaturate, false>(x, y, n, probs, kp, s, none);
+}
+
+// The same kernel as smaq_compress launches it, right behind the statistics kernel on the same tensor, as a
+// PROGRAMMATIC DEPENDENT LAUNCH: its CTAs become resident while the statistics grid drains (stats_kernel signals
+// griddepcontrol.launch_dependents), issue their first loads of the tensor, and block in griddepcontrol.wait
+// until that grid has completed and the mean/std its last block wrote are visible.  The launch latency and the
+// first memory round trip of the second kernel overlap the tail of the first: 1-4 us of a hook call's ~10-45 us
+// on tensors up to 2^26 elements (tools/compress_ab.sh).
+template <bool kStochastic, bool kHasProbs, bool kAllPos>
+__global__ void __launch_bounds__(kRtThreads, 3) roundtrip_after_stats_kernel(const float* x, float* y, int64_t n,
+                                                                             const float* mean_std,
+                                                                             const float* __restrict__ probs,
+                                                                             const __grid_constant__ KernelParams kp) {
+  const RtFirst first = roundtrip_first_loads<kStochastic && kHasProbs>(x, probs, n);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  float mean, std_raw;  // not through the read-only path, not before the wait
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(mean) : "l"(mean_std) : "memory");
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(std_raw) : "l"(mean_std + 1) : "memory");
+  const Scalars s = scalars_from(mean, std_raw, kp);
+  roundtrip_tensor<kStochastic, kHasProbs, kAllPos, false, true>(x, y, n, probs, kp, s, first);
 }
 
 // Tensors whose pointers are not 32-byte aligned (views into larger buffers).
@@ -601,6 +663,51 @@ static void launch_aligned(int grid, cudaStream_t stream, const float* x, float*
 #undef SMAQ_RT
 }
 
+
+
+// ---- the round trip as smaq_compress launches it, right behind the statistics kernel -------------------
+// Development switch, read once: SMAQ_COMPRESS_MODE=0 keeps smaq_compress on two ordinary launches
+// (tools/compress_ab.sh measures one against the other).
+static bool compress_dependent_launch() {
+  static const bool on = [] { const char* e = getenv("SMAQ_COMPRESS_MODE"); return !e || atoi(e) != 0; }();
+  return on;
+}
+// Above this size the dependent launch measured slower than two ordinary ones (2^28 elements: 548 vs 530 us per
+// call; up to 2^27 it is faster or equal).
+constexpr int64_t kDependentLaunchMax = (int64_t)1 << 27;
+
+template <bool kStochastic, bool kHasProbs, bool kAllPos>
+static cudaError_t launch_after_stats(int grid, cudaStream_t stream, const float* x, float* y, int64_t n,
+                                      const float* mean_std, const float* probs, const KernelParams& kp) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kRtThreads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, roundtrip_after_stats_kernel<kStochastic, kHasProbs, kAllPos>, x, y, n, mean_std, probs,
+                            kp);
+}
+
+static int roundtrip_after_stats(const float* x, float* y, int64_t n, const float* mean_std, const float* probs,
+                                 const smaq_codec_params& params, cudaStream_t stream) {
+  const KernelParams kp = to_kernel_params(params);
+  const int grid = rt_grid(n);
+  const bool ap = params.all_positive != 0;
+  cudaError_t e;
+#define SMAQ_AS(S, P) (ap ? launch_after_stats<S, P, true>(grid, stream, x, y, n, mean_std, probs, kp) \
+                          : launch_after_stats<S, P, false>(grid, stream, x, y, n, mean_std, probs, kp))
+  if (!params.stochastic) e = SMAQ_AS(false, false);
+  else if (probs) e = SMAQ_AS(true, true);
+  else e = SMAQ_AS(true, false);
+#undef SMAQ_AS
+  SMAQ_CUDA_OK(e);
+  return SMAQ_OK;
+}
+
 }  // namespace smaq
 
 extern "C" {
@@ -669,7 +776,12 @@ int smaq_compress(const float* x, float* y, int64_t n, const float* probs, const
   const size_t sb = smaq_stats_workspace_bytes(n);
   if (!ws || ws_bytes < sb + 256) return fail(SMAQ_ERR_WORKSPACE, "compress: workspace too small (smaq_compress_workspace_bytes)");
   float* mean_std = (float*)((char*)ws + sb);
+  if (int rc = check_params(params)) return rc;
+  if (!x || !y || n <= 0) return fail(SMAQ_ERR_ARG, "compress: null pointer or n <= 0");
   if (int rc = stats_full_zeroed_ws(x, n, /*unbiased=*/1, mean_std, ws, sb, (cudaStream_t)stream)) return rc;
+  if (compress_dependent_launch() && n <= kDependentLaunchMax && !params->saturate && aligned32(x) && aligned32(y) &&
+      (!probs || aligned32(probs)))
+    return roundtrip_after_stats(x, y, n, mean_std, probs, *params, (cudaStream_t)stream);
   return smaq_roundtrip(x, y, n, mean_std, probs, params, stream);
 }
 

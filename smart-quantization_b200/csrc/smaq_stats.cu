@@ -17,64 +17,22 @@
 
 namespace smaq {
 
-struct StatsWs {
-  unsigned int ticket;
-  unsigned int pad[3];
-  double partials[1];  // [grid][kPartialDoubles]
-};
+// resident CTAs per SM the statistics kernel is compiled for (<= 64 registers) and its grid is capped at
+#ifndef SMAQ_STATS_CTAS_PER_SM
+#define SMAQ_STATS_CTAS_PER_SM 4
+#endif
 
 template <int kKind, bool kAligned>
-__global__ void __launch_bounds__(kStatsThreads) stats_kernel(const float* __restrict__ x, int64_t n, int unbiased,
+__global__ void __launch_bounds__(kStatsThreads, SMAQ_STATS_CTAS_PER_SM) stats_kernel(const float* __restrict__ x, int64_t n, int unbiased,
                                                               float* __restrict__ out, StatsWs* ws) {
   __shared__ Acc smem[kStatsThreads / 32];
   __shared__ bool is_last;
-  Acc acc;
-  acc.m = Moments{0.0, 0.0, 0.0};
-  acc.hi = -INFINITY;
-  acc.lo = INFINITY;
-  LogSum ls = {0.0, 0};  // kind 2 only
-
+  // a kernel launched behind this one as a programmatic dependent (smaq_compress's round trip) may become resident
+  // as soon as this grid's CTAs leave; it waits for this grid's completion before it reads mean/std
+  asm volatile("griddepcontrol.launch_dependents;");
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-
-  if (kAligned) {
-    const float4* xv = reinterpret_cast<const float4*>(x);
-    const int64_t nvec = n >> 2;
-    // 4 independent 128-bit loads in flight per thread; each warp-level load is 512 contiguous bytes
-    int64_t v = tid;
-    for (; v + 3 * nthreads < nvec; v += 4 * nthreads) {
-      float4 a = ldg_stream(xv + v), b = ldg_stream(xv + v + nthreads), c = ldg_stream(xv + v + 2 * nthreads),
-             d = ldg_stream(xv + v + 3 * nthreads);
-      float r[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
-      if (kKind == 2) {
-        log_chunk<16>(ls, acc.lo, acc.hi, r);
-        continue;
-      }
-      merge_chunk<kKind, 16>(acc, r);
-    }
-    for (; v < nvec; v += nthreads) {
-      float4 a = ldg_stream(xv + v);
-      float r[4] = {a.x, a.y, a.z, a.w};
-      if (kKind == 2) {
-        log_chunk<4>(ls, acc.lo, acc.hi, r);
-        continue;
-      }
-      merge_chunk<kKind, 4>(acc, r);
-    }
-    const int64_t tail = nvec << 2;
-    if (tid < n - tail) {
-      float raw[1] = {x[tail + tid]};
-      if (kKind == 2) log_chunk<1>(ls, acc.lo, acc.hi, raw);
-      else merge_one<kKind>(acc, raw[0]);
-    }
-  } else {
-    for (int64_t i = tid; i < n; i += nthreads) {
-      float raw[1] = {x[i]};
-      if (kKind == 2) log_chunk<1>(ls, acc.lo, acc.hi, raw);
-      else merge_one<kKind>(acc, raw[0]);
-    }
-  }
-  if (kKind == 2 && ls.count > 0) acc.m = Moments{(double)ls.count, ls.sum / (double)ls.count, 0.0};
+  Acc acc = accumulate_tensor<kKind, kAligned>(x, n, tid, nthreads);
 
   acc = block_combine<kKind>(acc, smem);
   if (gridDim.x == 1) {  // one block: nothing to hand over
@@ -82,8 +40,7 @@ __global__ void __launch_bounds__(kStatsThreads) stats_kernel(const float* __res
     return;
   }
   if (threadIdx.x == 0) {
-    double* p = ws->partials + (size_t)blockIdx.x * kPartialDoubles;
-    p[0] = acc.m.n; p[1] = acc.m.mean; p[2] = acc.m.m2; p[3] = (double)acc.lo; p[4] = (double)acc.hi;
+    store_partial(ws, blockIdx.x, acc);
     __threadfence();
     unsigned int t = atomicAdd(&ws->ticket, 1u);
     is_last = (t == gridDim.x - 1);
@@ -92,31 +49,8 @@ __global__ void __launch_bounds__(kStatsThreads) stats_kernel(const float* __res
   if (!is_last) return;
   __threadfence();
 
-  // last block: the per-block moments by the same two sums (moments.cuh), partials re-read for the second
-  const double* parts = ws->partials;
-  double tn = 0.0, s1 = 0.0;
-  float hi = -INFINITY, lo = INFINITY;
-  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
-    const double* p = parts + (size_t)b * kPartialDoubles;
-    const double pn = __ldcg(p), pm = __ldcg(p + 1);
-    tn += pn;
-    s1 += pn == 0.0 ? 0.0 : pn * pm;
-    lo = nanmin(lo, (float)__ldcg(p + 3));
-    hi = nanmax(hi, (float)__ldcg(p + 4));
-  }
-  block_sum2<true>(tn, s1, hi, lo, smem);
-  const double mean = weighted_mean(tn, s1);
-  double q = 0.0, unused = 0.0;
-  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
-    const double* p = parts + (size_t)b * kPartialDoubles;
-    q += m2_about(Moments{__ldcg(p), __ldcg(p + 1), __ldcg(p + 2)}, mean);
-  }
-  float h2 = 0.f, l2 = 0.f;
-  block_sum2<false>(q, unused, h2, l2, smem);
-  Acc f;
-  f.m = Moments{tn, mean, q};
-  f.hi = hi;
-  f.lo = lo;
+  // last block: the per-block moments by the same two sums (moments.cuh)
+  const Acc f = combine_partials(ws, (int)gridDim.x, smem);
   if (threadIdx.x == 0) {
     finalize<kKind>(f, unbiased, out);
     ws->ticket = 0;  // leave the workspace reusable
@@ -182,9 +116,6 @@ static int stats_grid(int64_t n) {
   // threads loop.  Measured over 2^16..2^30 elements (tools/midsize_bench.py): a second wave only starts late, and
   // 128 elements per thread made a 256 KB tensor wait out eight dependent memory round trips in two CTAs
   int64_t want = (n + (int64_t)kStatsThreads * SMAQ_STATS_EPT - 1) / ((int64_t)kStatsThreads * SMAQ_STATS_EPT);
-#ifndef SMAQ_STATS_CTAS_PER_SM
-#define SMAQ_STATS_CTAS_PER_SM 4
-#endif
   int64_t cap = (int64_t)sms * SMAQ_STATS_CTAS_PER_SM;
   if (want < 1) want = 1;
   return (int)(want < cap ? want : cap);

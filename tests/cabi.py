@@ -81,6 +81,21 @@ def roundtrip(x, mean_std, params, probs=None, out=None):
     return y
 
 
+def compress(x, params, probs=None, out=None, ws=None):
+    """smaq_compress (statistics + round trip behind one entry point) -> (y, the mean/std it used)."""
+    lib = N.load()
+    n = x.numel()
+    y = torch.empty_like(x) if out is None else out
+    need = lib.smaq_compress_workspace_bytes(n)
+    if ws is None:
+        ws = torch.full((need,), 0xA5, dtype=torch.uint8, device=x.device)   # dirty scratch
+        N.check(lib.smaq_compress_workspace_init(ws.data_ptr(), ws.numel(), N.stream_ptr(x.device)), "init")
+    N.check(lib.smaq_compress(x.data_ptr(), y.data_ptr(), n, None if probs is None else probs.data_ptr(),
+                              C.byref(params), ws.data_ptr(), ws.numel(), N.stream_ptr(x.device)), "compress")
+    sb = lib.smaq_stats_workspace_bytes(n)
+    return y, ws[sb:sb + 8].view(torch.float32).clone()
+
+
 def roundtrip_small(x, params, probs=None, want_stats=False):
     lib = N.load()
     y = torch.empty_like(x)

@@ -91,26 +91,95 @@ def test_saturation_counter_is_optional():
     assert abs(int((c.abs() > 63).sum()) - h_on.n_saturated) <= 2   # fp32 vs this fp32-ish recomputation
 
 
-@pytest.mark.parametrize("n", [40000, (1 << 20) + 5])
+# smaq_compress: the statistics kernel, then the round trip as a programmatic dependent launch that walks the
+# tensor back to front (saturating calls and pointers that are not 32-byte aligned: an ordinary launch).  Same
+# statistics kernel, element-indexed random numbers: the result must equal smaq_stats_full -> smaq_roundtrip bit
+# for bit at every size, across the grid-sizing thresholds and with ragged tails.
+FUSED_SIZES = [32769, 40000, 40003, (1 << 20) + 5, 909312, 909313 + 8, (1 << 22) + 1, 3 * (1 << 22) + 7]
+
+
+def _check_compress(xd, params, probs=None):
+    y, ms = cabi.compress(xd, params, probs=probs)
+    ref = cabi.stats_full(xd)
+    assert torch.equal(ms.view(torch.int32), ref.view(torch.int32)), (ms, ref)
+    want = cabi.roundtrip(xd, ms, params, probs=probs)
+    assert torch.equal(y.view(torch.int32), want.view(torch.int32))
+    return y, ms
+
+
+@pytest.mark.parametrize("n", FUSED_SIZES)
 def test_fused_entry_point_equals_stats_then_roundtrip(n):
     x, _ = make_outlier_tensor(n, seed=n)
     xd = x.to(DEV)
-    cfg = SmaqConfig()
     lib = N.load()
-    params = cabi.codec_params(cfg, seed=99, offset=3)
-    want = cabi.roundtrip(xd, cabi.stats_full(xd), params)
-    y = torch.empty_like(xd)
+    params = cabi.codec_params(SmaqConfig(), seed=99, offset=3)
+    y, ms = _check_compress(xd, params)
+    # reused scratch, twice: same bits, and in place
     need = lib.smaq_compress_workspace_bytes(n)
-    ws = torch.full((need + 4096,), 0xA5, dtype=torch.uint8, device=DEV)   # larger than needed, dirty: reused scratch
+    ws = torch.full((need + 4096,), 0xA5, dtype=torch.uint8, device=DEV)   # larger than needed, dirty
     N.check(lib.smaq_compress_workspace_init(ws.data_ptr(), ws.numel(), N.stream_ptr(xd.device)), "init")  # once
-    for _ in range(2):                                              # twice on the same scratch
-        N.check(lib.smaq_compress(xd.data_ptr(), y.data_ptr(), n, None, C.byref(params), ws.data_ptr(), ws.numel(),
-                                  N.stream_ptr(xd.device)), "compress")
-        assert torch.equal(y.view(torch.int32), want.view(torch.int32))
+    for _ in range(2):
+        y2, ms2 = cabi.compress(xd, params, ws=ws)
+        assert torch.equal(ms2.view(torch.int32), ms.view(torch.int32))
+        assert torch.equal(y2.view(torch.int32), y.view(torch.int32))
+    inplace = xd.clone()
+    cabi.compress(inplace, params, out=inplace, ws=ws)
+    assert torch.equal(inplace.view(torch.int32), y.view(torch.int32))
     small = torch.empty(16, dtype=torch.uint8, device=DEV)
     assert lib.smaq_compress(xd.data_ptr(), y.data_ptr(), n, None, C.byref(params), small.data_ptr(), 16,
                              N.stream_ptr(xd.device)) == 3          # SMAQ_ERR_WORKSPACE
     assert b"workspace" in lib.smaq_b200_last_error()
+
+
+@pytest.mark.parametrize("stochastic", [False, True])
+@pytest.mark.parametrize("all_positive", [False, True])
+def test_fused_entry_point_variants(stochastic, all_positive):
+    n = (1 << 20) + 3
+    x, _ = make_outlier_tensor(n, seed=5)
+    xd = x.to(DEV)
+    cfg = SmaqConfig(stochastic_rounding=stochastic)
+    params = cabi.codec_params(cfg, seed=7, offset=11, all_positive=all_positive)
+    _check_compress(xd, params)
+    if stochastic:   # explicit uniforms (parity mode) through the same launches
+        probs = torch.rand(n, generator=torch.Generator().manual_seed(3)).to(DEV)
+        _check_compress(xd, params, probs=probs)
+    # saturating calls and views that are not 32-byte aligned take the ordinary launch: same contract
+    _check_compress(xd, cabi.codec_params(cfg, seed=7, offset=11, all_positive=all_positive, saturate=True))
+    _check_compress(xd[1:], params)
+
+
+def test_fused_entry_point_beyond_the_dependent_launch_size():
+    """Above 2^27 elements smaq_compress takes two ordinary launches (measured faster there): same contract."""
+    n = (1 << 27) + 8
+    xd = torch.randn(n, device=DEV, generator=torch.Generator(device=DEV).manual_seed(2))
+    _check_compress(xd, cabi.codec_params(SmaqConfig(), seed=5, offset=1))
+
+
+def test_fused_entry_point_against_the_oracle():
+    """The whole call against the CPU oracle under the statistics it published, with explicit uniforms."""
+    n = 70000
+    x, _ = make_outlier_tensor(n, seed=17)
+    probs = torch.rand(n, generator=torch.Generator().manual_seed(4))
+    cfg = SmaqConfig()
+    y, ms = cabi.compress(x.to(DEV), cabi.codec_params(cfg), probs=probs.to(DEV))
+    msc = ms.cpu()
+    want = smaq_roundtrip(x, cfg, probs=probs, mean=msc[0], std=msc[1])
+    assert_bit_equal(y.cpu(), want.y, "smaq_compress vs oracle")
+
+
+def test_fused_entry_point_special_tensors():
+    params = cabi.codec_params(SmaqConfig(), seed=1)
+    n = 1 << 18
+    const = torch.full((n,), 3.25, device=DEV)                       # std 0 -> 1, codes 0 (smart.py:151-152)
+    y, ms = cabi.compress(const, params)
+    assert float(ms[1]) == 0.0 and torch.equal(y, const)
+    bad = torch.randn(n, device=DEV)
+    bad[n // 3] = float("nan")                                       # any NaN -> statistics NaN -> all NaN
+    y, ms = cabi.compress(bad, params)
+    assert torch.isnan(ms).all() and torch.isnan(y).all()
+    bad[n // 3] = float("inf")
+    y, ms = cabi.compress(bad, params)
+    assert torch.isnan(y).all()
 
 
 def test_plugin_scratch_reuse_across_sizes_and_threads():

@@ -23,6 +23,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--min", type=int, default=14)
 ap.add_argument("--max", type=int, default=26)
 ap.add_argument("--reps", type=int, default=50)
+ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel CUPTI durations")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 lib = N.load()
@@ -91,6 +92,6 @@ for log2n in range(a.min, a.max + 1):
         lib.smaq_decode(packed.data_ptr(), packed.numel(), n, 6, 8, 0, y.data_ptr(), st)
         lib.smaq_float_quantize(x.data_ptr(), y.data_ptr(), n, None, C.byref(p8), st)
 
-    ku = kernel_us(everything, 20)
+    ku = {} if a.no_kernels else kernel_us(everything, 20)
     print(f"{log2n:>5} {4 * n / 2**20:>8.2f} {t_s:>9.2f} {t_r:>9.2f} {t_f:>9.2f} {12.0 * n / t_f / 1e3:>20.0f}   " +
           "  ".join(f"{k} {v:.2f}" for k, v in sorted(ku.items())))
