@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 namespace smaq {
@@ -35,6 +36,18 @@ int sm_count() {
   }
   cache[dev].store(v, std::memory_order_relaxed);
   return v;
+}
+
+bool dependent_launch_enabled() {
+  static const bool on = [] { const char* e = getenv("SMAQ_DEPENDENT_LAUNCH"); return !e || atoi(e) != 0; }();
+  return on;
+}
+
+void set_dependent_launch(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr) {
+  attr->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr->val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = dependent_launch_enabled() ? 1 : 0;
 }
 
 }  // namespace smaq

@@ -15,6 +15,16 @@ char* last_error_buf();
 int fail(int code, const char* fmt, ...);
 int sm_count();  // cached per device, immutable once read
 
+// Programmatic dependent launch (sm_90+): a kernel that consumes the result of the kernel launched just before it
+// on the same stream is launched with this attribute; its CTAs become resident while the first grid drains — the
+// first kernel executes griddepcontrol.launch_dependents — and block in griddepcontrol.wait until that grid has
+// completed and its writes are visible.  Launch latency, CTA set-up and whatever the second kernel can do without
+// the first one's result overlap the first one's tail.  Used for statistics -> round trip (smaq_compress),
+// encode pass 1 -> pass 2 and S2FP8 statistics -> apply.  Development switch, read once:
+// SMAQ_DEPENDENT_LAUNCH=0 makes them ordinary launches (tools/compress_ab.sh).
+bool dependent_launch_enabled();
+void set_dependent_launch(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr);
+
 #define SMAQ_CUDA_OK(expr)                                                              \
   do {                                                                                  \
     cudaError_t _e = (expr);                                                            \

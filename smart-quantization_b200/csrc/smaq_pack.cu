@@ -534,6 +534,9 @@ __global__ void __launch_bounds__(kPackThreads, SMAQ_ENC_CTAS)
   __shared__ Hot s_hot;
   __shared__ bool s_last;
 
+  // pass 2 is launched behind this kernel as a programmatic dependent: its CTAs may become resident as this
+  // grid's leave; it waits for this grid's completion before it reads anything
+  asm volatile("griddepcontrol.launch_dependents;");
   const int lane = lane_id(), warp = warp_id();
   const uint32_t seg_addr = smem_u32(&s_seg[warp][0]);
   if (lane == 0) {
@@ -708,6 +711,9 @@ __global__ void __launch_bounds__(kPackThreads) encode_place_kernel(EncodeScratc
   constexpr int kSeg = seg_words(XB);
   constexpr int kPerThread = (kSeg + 7) / 8;
   __shared__ uint32_t s_off[kMaxRounds * kWarpsPerCta + 1];
+  // launched as a programmatic dependent of pass 1 (launch latency and CTA set-up overlap its tail): everything
+  // below reads what pass 1 wrote
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int lane = lane_id(), warp = warp_id();
   const long long group = blockIdx.x;
   const long long first_wt = group * rounds * kWarpsPerCta;
@@ -980,6 +986,13 @@ int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* p
   ha.count_saturated = cs ? 1 : 0;
   SMAQ_CUDA_OK(cudaMemsetAsync(sc.ticket, 0, (size_t)zero_bytes, stream));
 
+  cudaLaunchConfig_t place_cfg = {};
+  place_cfg.gridDim = dim3((unsigned)n_groups);
+  place_cfg.blockDim = dim3(kPackThreads);
+  place_cfg.stream = stream;
+  cudaLaunchAttribute place_attr[1];
+  set_dependent_launch(place_cfg, place_attr);
+
 #define SMAQ_ENC_LAUNCH(PM_, XB_, ST_, HP_)                                                                        \
   {                                                                                                                \
     auto kern = cs ? encode_kernel<PM_, XB_, ST_, HP_, true> : encode_kernel<PM_, XB_, ST_, HP_, false>;                                                                 \
@@ -987,9 +1000,8 @@ int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* p
     kern<<<grid, kPackThreads, kEncodeDynSmem, stream>>>(x, n, mean_std, probs, kp, planes, sc, l.n_cta_tiles,     \
                                                          rounds, gpc, n_groups, aligned, ha);                      \
     SMAQ_LAUNCH_OK();                                                                                              \
-    encode_place_kernel<XB_><<<(unsigned)n_groups, kPackThreads, 0, stream>>>(sc, table, extras, l.n_cta_tiles,    \
-                                                                              l.n_warp_tiles,                      \
-                                                                rounds);                                           \
+    SMAQ_CUDA_OK(cudaLaunchKernelEx(&place_cfg, encode_place_kernel<XB_>, sc, table, extras,                       \
+                                    (long long)l.n_cta_tiles, (long long)l.n_warp_tiles, rounds));                 \
   }
 #define SMAQ_ENC(PM_, XB_)                                                                                         \
   if (pm == PM_ && xb == XB_) {                                                                                    \

@@ -10,8 +10,6 @@
 // (profiles/): the kernel is bound by instruction issue, so the element loop is written to
 // minimise issue slots — packed FADD2/FMUL2/FFMA2 arithmetic, three-instruction divisions
 // checked once per four elements, Philox round keys as constant-bank operands.
-#include <cstdlib>
-
 #include "common.cuh"
 #include "moments.cuh"
 #include "params.cuh"
@@ -666,12 +664,6 @@ static void launch_aligned(int grid, cudaStream_t stream, const float* x, float*
 
 
 // ---- the round trip as smaq_compress launches it, right behind the statistics kernel -------------------
-// Development switch, read once: SMAQ_COMPRESS_MODE=0 keeps smaq_compress on two ordinary launches
-// (tools/compress_ab.sh measures one against the other).
-static bool compress_dependent_launch() {
-  static const bool on = [] { const char* e = getenv("SMAQ_COMPRESS_MODE"); return !e || atoi(e) != 0; }();
-  return on;
-}
 // Above this size the dependent launch measured slower than two ordinary ones (2^28 elements: 548 vs 530 us per
 // call; up to 2^27 it is faster or equal).
 constexpr int64_t kDependentLaunchMax = (int64_t)1 << 27;
@@ -684,10 +676,7 @@ static cudaError_t launch_after_stats(int grid, cudaStream_t stream, const float
   cfg.blockDim = dim3(kRtThreads);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  set_dependent_launch(cfg, attr);
   return cudaLaunchKernelEx(&cfg, roundtrip_after_stats_kernel<kStochastic, kHasProbs, kAllPos>, x, y, n, mean_std, probs,
                             kp);
 }
@@ -779,7 +768,7 @@ int smaq_compress(const float* x, float* y, int64_t n, const float* probs, const
   if (int rc = check_params(params)) return rc;
   if (!x || !y || n <= 0) return fail(SMAQ_ERR_ARG, "compress: null pointer or n <= 0");
   if (int rc = stats_full_zeroed_ws(x, n, /*unbiased=*/1, mean_std, ws, sb, (cudaStream_t)stream)) return rc;
-  if (compress_dependent_launch() && n <= kDependentLaunchMax && !params->saturate && aligned32(x) && aligned32(y) &&
+  if (dependent_launch_enabled() && n <= kDependentLaunchMax && !params->saturate && aligned32(x) && aligned32(y) &&
       (!probs || aligned32(probs)))
     return roundtrip_after_stats(x, y, n, mean_std, probs, *params, (cudaStream_t)stream);
   return smaq_roundtrip(x, y, n, mean_std, probs, params, stream);
