@@ -231,3 +231,54 @@ def test_other_thresholds_take_the_right_path(t_main, t_out, stochastic):
     ysat = cabi.roundtrip(x.to(DEV), ms, cabi.codec_params(cfg, saturate=True), probs=pd)
     assert_bit_equal(ysat.cpu(), smaq_roundtrip(x, cfg, probs=probs, saturate=True).y, "saturated round trip")
     encode_and_compare(x, cfg, probs, res.mean, res.std)
+
+
+def test_dependent_launches_inside_a_cuda_graph():
+    """The two-kernel calls are programmatic dependent launches; captured into a CUDA graph (programmatic edges)
+    and replayed they must give the bits of the eager calls — statistics + round trip, the packed encoder's two
+    passes + decode, and S2FP8's statistics + apply."""
+    n = (1 << 20) + 24
+    x, _ = make_outlier_tensor(n, seed=31)
+    xd = x.to(DEV)
+    cfg = SmaqConfig()
+    lib = N.load()
+    params = cabi.codec_params(cfg, seed=77, offset=5)
+    want_y, want_ms = cabi.compress(xd, params)
+    ms = cabi.stats_full(xd)
+    want_buf, lay = cabi_pack.encode(xd, ms, params, cfg)
+    want_dec = cabi_pack.decode(want_buf, lay)
+    p8 = cabi.floatq_params(5, 2, seed=9, offset=2)
+    want_s2 = cabi.s2fp8_apply(xd, cabi.s2fp8_stats(xd), p8)
+
+    y = torch.empty_like(xd)
+    dec = torch.empty_like(xd)
+    s2 = torch.empty_like(xd)
+    mm = torch.empty(2, dtype=torch.float32, device=DEV)
+    need = lib.smaq_compress_workspace_bytes(n)
+    ws = torch.zeros(need, dtype=torch.uint8, device=DEV)
+    sws_b = lib.smaq_stats_workspace_bytes(n)
+    sws = torch.zeros(sws_b, dtype=torch.uint8, device=DEV)
+    buf = torch.zeros(lay.total_capacity_bytes, dtype=torch.uint8, device=DEV)
+    pws = torch.zeros(lay.workspace_bytes, dtype=torch.uint8, device=DEV)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            st = N.stream_ptr(xd.device)
+            N.check(lib.smaq_compress(xd.data_ptr(), y.data_ptr(), n, None, C.byref(params), ws.data_ptr(), ws.numel(),
+                                      st), "compress")
+            N.check(lib.smaq_encode(xd.data_ptr(), n, ms.data_ptr(), None, C.byref(params), buf.data_ptr(), buf.numel(),
+                                    pws.data_ptr(), pws.numel(), st), "encode")
+            N.check(lib.smaq_decode(buf.data_ptr(), buf.numel(), n, cfg.num_bits_main, cfg.num_bits_outlier, 0,
+                                    dec.data_ptr(), st), "decode")
+            N.check(lib.smaq_s2fp8_stats(xd.data_ptr(), n, mm.data_ptr(), sws.data_ptr(), sws_b, st), "s2fp8_stats")
+            N.check(lib.smaq_s2fp8_apply(xd.data_ptr(), s2.data_ptr(), n, mm.data_ptr(), None, C.byref(p8), st),
+                    "s2fp8_apply")
+    for _ in range(3):
+        y.zero_(), dec.zero_(), s2.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(y.view(torch.int32), want_y.view(torch.int32))
+        assert torch.equal(dec.view(torch.int32), want_dec.view(torch.int32))
+        assert_bit_equal(s2, want_s2, "S2FP8 in a graph")
