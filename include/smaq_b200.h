@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SMAQ_B200_ABI_VERSION 2 /* 2: packed stream SQB2, count_saturated, smaq_compress, tensor_desc.stream */
+#define SMAQ_B200_ABI_VERSION 3 /* 2: packed stream SQB2, count_saturated, smaq_compress, tensor_desc.stream; 3: smaq_float_quantize_multi */
 
 typedef void* smaq_stream_t; /* cudaStream_t */
 
@@ -196,6 +196,15 @@ typedef struct smaq_floatq_params {
 } smaq_floatq_params;
 int smaq_float_quantize(const float* x, float* y, int64_t n, const int32_t* rand_bits,
                         const smaq_floatq_params* params, smaq_stream_t stream);
+
+/* float_quantize over MANY tensors in two launches — the loop OptimLP runs over every parameter, gradient and
+ * state tensor (smart_compress/util/pytorch/optimizer.py:69-127) with --compress fp8 | fp16 | bf16.  descs is a
+ * DEVICE array of `count` descriptors (x, y, n; all_positive is ignored); tensor i is rounded with the Philox
+ * stream params->offset + descs[i].stream, i.e. exactly as smaq_float_quantize would round it with that offset.
+ * In-kernel random numbers only (no rand_bits).  total_elems = sum of descs[i].n. */
+size_t smaq_floatq_multi_workspace_bytes(int32_t count);
+int smaq_float_quantize_multi(const smaq_tensor_desc* descs, int32_t count, int64_t total_elems,
+                              const smaq_floatq_params* params, void* ws, size_t ws_bytes, smaq_stream_t stream);
 
 /* S2FP8 (smart_compress/compress/s2fp8.py:31-48).  Pass 1: mu = mean(L), m = max(L) with
  * L = log2|x| and L := 0 where x == 0; writes mu_max[0..1].  Pass 2: alpha = 15/(m-mu),

@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libsmaq_b200.so")
 
 OK = 0
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class NativeLibraryError(RuntimeError):
@@ -135,6 +135,8 @@ _SIGNATURES = {
     "smaq_encode": (C.c_int, [_P, _I64, _P, _P, C.POINTER(CodecParams), _P, C.c_size_t, _P, C.c_size_t, _P]),
     "smaq_decode": (C.c_int, [_P, C.c_size_t, _I64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "smaq_float_quantize": (C.c_int, [_P, _P, _I64, _P, C.POINTER(FloatqParams), _P]),
+    "smaq_floatq_multi_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "smaq_float_quantize_multi": (C.c_int, [_P, C.c_int32, _I64, C.POINTER(FloatqParams), _P, C.c_size_t, _P]),
     "smaq_s2fp8_stats": (C.c_int, [_P, _I64, _P, _P, C.c_size_t, _P]),
     "smaq_s2fp8_apply": (C.c_int, [_P, _P, _I64, _P, _P, C.POINTER(FloatqParams), _P]),
     "smaq_selftest_pow": (C.c_int, [_P, _P, _P, _P, _I64, _P]),

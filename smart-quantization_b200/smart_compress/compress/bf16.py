@@ -4,7 +4,7 @@ from argparse import ArgumentParser, Namespace
 
 import torch
 
-from ..util.pytorch.quantization import add_float_quantize_args, float_quantize
+from ..util.pytorch.quantization import add_float_quantize_args, float_quantize, float_quantize_many
 from .base import CompressionAlgorithmBase, chain_parser
 
 
@@ -23,3 +23,11 @@ class BF16(CompressionAlgorithmBase):
         self.log_ratio(tag, tensor.numel(), 32, self.STORED_BITS)
         return float_quantize(tensor, exp=self.EXP_BITS, man=self.MAN_BITS, hparams=self.hparams,
                               rand_bits=extra.get("_rand_bits"))
+
+    @torch.no_grad()
+    def compress_many(self, tensors, kwargs_list=None, tag: str = None):
+        """The optimizer-side loop (OptimLP) in two launches; kwargs (``all_positive``) do not matter to this codec."""
+        if getattr(self.hparams, "measure_compression_ratio", False):
+            for t in tensors:
+                self.log_ratio(tag, t.numel(), 32, self.STORED_BITS)
+        return float_quantize_many(tensors, self.EXP_BITS, self.MAN_BITS, self.hparams)

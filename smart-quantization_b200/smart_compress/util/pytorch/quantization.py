@@ -105,3 +105,60 @@ def float_quantize(x: torch.Tensor, exp: int, man: int, hparams, rand_bits: torc
     N.check(lib.smaq_float_quantize(N.ptr(src), N.ptr(out), src.numel(), rb, C.byref(params),
                                     N.stream_ptr(src.device)), "smaq_float_quantize")
     return out.half() if is_16_bit else out
+
+
+_multi_cache = {}   # (device, tensors' pointers and sizes) -> device array of smaq_tensor_desc
+_multi_ws = {}      # device -> grow-only scratch
+
+
+def float_quantize_many(tensors, exp: int, man: int, hparams):
+    """``[float_quantize(t, exp, man, hparams) for t in tensors]`` in two launches (``smaq_float_quantize_multi``):
+    what OptimLP's loops over every parameter, gradient and state tensor (reference optimizer.py:69-127) cost with
+    --compress fp8 | fp16 | bf16 was one launch per tensor.  Philox streams are numbered as the per-tensor loop
+    numbers its calls, so every tensor gets the bits that loop would give it.  Contiguous fp32 CUDA tensors are
+    updated IN PLACE and returned as the same objects (the reference re-binds ``.data`` to a fresh tensor; nothing
+    else aliases optimizer tensors); anything else goes through ``float_quantize``."""
+    lib = N.load()
+    results = list(tensors)
+    is_16_bit = getattr(hparams, "precision", 32) == 16
+    batch = []
+    first = None
+    for i, t in enumerate(tensors):
+        if is_16_bit or not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()) or t.numel() == 0:
+            results[i] = float_quantize(t, exp, man, hparams)   # draws its own stream number
+            continue
+        no = next(_calls)
+        if first is None:
+            first = no
+        batch.append((i, t, no - first))
+    if not batch:
+        return results
+    device = batch[0][1].device
+    if any(t.device != device for _, t, _ in batch):
+        for i, t, _ in batch:
+            results[i] = float_quantize(t, exp, man, hparams)
+        return results
+    key = (device, tuple((t.data_ptr(), t.numel(), sn) for _, t, sn in batch))
+    descs = _multi_cache.get(key)
+    if descs is None:
+        host = (N.TensorDesc * len(batch))()
+        for j, (_, t, sn) in enumerate(batch):
+            host[j].x = host[j].y = t.data_ptr()
+            host[j].n = t.numel()
+            host[j].all_positive = 0
+            host[j].stream = sn
+        raw = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).pin_memory()
+        descs = raw.to(device, non_blocking=True)
+        if len(_multi_cache) > 64:
+            _multi_cache.clear()
+        _multi_cache[key] = descs
+    params = make_floatq_params(exp, man, hparams)
+    params.offset = first      # make_floatq_params drew one more number: harmless, the streams stay distinct
+    need = lib.smaq_floatq_multi_workspace_bytes(len(batch))
+    ws = _multi_ws.get(device)
+    if ws is None or ws.numel() < need:
+        ws = _multi_ws[device] = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
+    total = sum(t.numel() for _, t, _ in batch)
+    N.check(lib.smaq_float_quantize_multi(N.ptr(descs), len(batch), total, C.byref(params), N.ptr(ws), ws.numel(),
+                                          N.stream_ptr(device)), "smaq_float_quantize_multi")
+    return results

@@ -264,3 +264,64 @@ def test_s2fp8_fast_pow_declines_what_it_must():
     want = torch.pow(a, torch.tensor(1.5, device=DEV))
     same = (got.view(torch.int32) == want.view(torch.int32)) | (torch.isnan(got) & torch.isnan(want))
     assert bool(same.all())
+
+
+# ---- many tensors in two launches (the optimizer side with --compress fp8 | fp16 | bf16) ----------------------
+MANY_SIZES = [1, 7, 8, 513, 16384, 16385, 40003, 5, 100000, 16384 * 3]
+
+
+def _many_tensors(seed=0):
+    g = torch.Generator().manual_seed(seed)
+    ts = [(torch.randn(n, generator=g) * (10.0 ** ((i % 5) - 2))).to(DEV) for i, n in enumerate(MANY_SIZES)]
+    buf = (torch.randn(20001, generator=g)).to(DEV)
+    ts.append(buf[1:])            # contiguous, pointer not 32-byte aligned: element path
+    return ts
+
+
+@pytest.mark.parametrize("rounding", [1, 0])
+@pytest.mark.parametrize("exp,man", [(5, 2), (8, 7)])
+def test_float_quantize_multi_equals_the_per_tensor_calls(exp, man, rounding):
+    import ctypes as C
+    from smart_compress import _native as N
+    lib = N.load()
+    ts = _many_tensors(seed=exp * 10 + man)
+    base = 1000
+    want = []
+    for j, t in enumerate(ts):
+        want.append(cabi.float_quantize(t, cabi.floatq_params(exp, man, rounding=rounding, seed=11, offset=base + j)))
+    outs = [torch.full_like(t, float("nan")) for t in ts]
+    host = (N.TensorDesc * len(ts))()
+    for j, (t, o) in enumerate(zip(ts, outs)):
+        host[j].x, host[j].y, host[j].n, host[j].all_positive, host[j].stream = t.data_ptr(), o.data_ptr(), t.numel(), 0, j
+    descs = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).to(DEV)
+    need = lib.smaq_floatq_multi_workspace_bytes(len(ts))
+    ws = torch.full((need,), 0xA5, dtype=torch.uint8, device=DEV)
+    p = cabi.floatq_params(exp, man, rounding=rounding, seed=11, offset=base)
+    for _ in range(2):   # reused scratch
+        N.check(lib.smaq_float_quantize_multi(descs.data_ptr(), len(ts), sum(t.numel() for t in ts), C.byref(p),
+                                              ws.data_ptr(), ws.numel(), N.stream_ptr(DEV)), "float_quantize_multi")
+        for j, (o, w) in enumerate(zip(outs, want)):
+            assert_bit_equal(o, w, f"tensor {j} ({ts[j].numel()} elements)")
+    assert lib.smaq_float_quantize_multi(descs.data_ptr(), len(ts), 1, C.byref(p), ws.data_ptr(), 4, N.stream_ptr(DEV)) == 3
+    assert lib.smaq_float_quantize_multi(None, 0, 0, C.byref(p), None, 0, N.stream_ptr(DEV)) == 0
+
+
+def test_fp8_plugin_compress_many_equals_the_loop():
+    """FP8.compress_many (what OptimLP calls per phase) numbers its Philox streams like the per-tensor loop."""
+    import itertools
+    from argparse import ArgumentParser
+    from smart_compress.compress.fp8 import FP8
+    from smart_compress.util.pytorch import quantization as Q
+    hp = FP8.add_argparse_args(ArgumentParser()).parse_args([])
+    hp.precision = 32
+    fp = FP8(hp)
+    ts = _many_tensors(seed=3)
+    torch.manual_seed(5)
+    Q._calls = itertools.count(700)
+    want = [fp(t.clone(), tag="optimizer_grad") for t in ts]
+    Q._calls = itertools.count(700)
+    mine = [t.clone() for t in ts]
+    got = fp.compress_many(mine, None, tag="optimizer_grad")
+    for j, (g, w, m) in enumerate(zip(got, want, mine)):
+        assert g is m                                   # in place, same objects
+        assert_bit_equal(g, w, f"tensor {j}")
