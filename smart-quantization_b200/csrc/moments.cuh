@@ -141,7 +141,24 @@ __device__ __forceinline__ void merge_chunk(Acc& acc, const float (&v)[kCount]) 
   // use the exact fp32 sum for the mean so that no chunk-level rounding of s/kCount leaks in
   c.mean = (double)s * (1.0 / kCount);
   double corr = c.mean - (double)cm;  // M2 about cm -> M2 about c.mean
-  c.m2 = (double)m2 - (double)kCount * corr * corr;
+  double m2d = (double)m2;
+  // fp32 squares are only good between underflow and overflow: a chunk whose sum of squares is below
+  // 16 * FLT_MIN * 2^24 (deviations under ~1e-15: a tensor of 1e-30s would get std 0), huge or NaN is summed
+  // again in fp64 — one compare per chunk for ordinary data; an all-equal chunk (zeros) stops at the max
+  if (!(m2 >= 3.2e-30f && m2 <= 1e30f)) {
+    float amax = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kCount; ++i) amax = fmaxf(amax, fabsf(v[i] - cm));  // NaN-ignoring: NaN handled below
+    if (amax > 0.0f || !(m2 == m2)) {
+      m2d = 0.0;
+#pragma unroll
+      for (int i = 0; i < kCount; ++i) {
+        const double d = (double)v[i] - (double)cm;
+        m2d = fma(d, d, m2d);
+      }
+    }
+  }
+  c.m2 = m2d - (double)kCount * corr * corr;
   if (c.m2 < 0.0) c.m2 = 0.0;
   acc.m = merge(acc.m, c);
   if (kKind == 1) {

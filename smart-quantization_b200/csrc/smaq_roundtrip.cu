@@ -409,11 +409,10 @@ __device__ __forceinline__ int64_t small_groups(const float* x, float* y, int64_
 template <bool kStochastic, bool kHasProbs>
 __device__ __forceinline__ void small_body(const float* x, float* y, int64_t n, const float* probs,
                                            const KernelParams& kp, float* mean_std_out, Acc* smem, float* bcast) {
-  Acc acc;
-  acc.m = Moments{0.0, 0.0, 0.0};
-  acc.hi = -INFINITY;
-  acc.lo = INFINITY;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) merge_one<0>(acc, x[i]);
+  // the statistics kernel's chunked pass with the block as the whole grid: 16 values per fp64 merge (one merge per
+  // ELEMENT made a 32768-element tensor an 80 us block, and the multi-tensor launch lasts as long as its largest)
+  Acc acc = aligned16(x) ? accumulate_tensor<0, true>(x, n, threadIdx.x, blockDim.x)
+                         : accumulate_tensor<0, false>(x, n, threadIdx.x, blockDim.x);
   acc = block_combine<0>(acc, smem);
   if (threadIdx.x == 0) {
     finalize<0>(acc, /*unbiased=*/1, bcast);

@@ -315,3 +315,21 @@ def test_compression_ratio_logging():
     assert abs(seen["new_size_forward_autograd"] - want) <= 8 * 4  # stats differ in the last bit at most
     assert seen["orig_size"] == x.numel() * 32
     assert 4.0 < seen["compression_ratio"] < 5.4
+
+
+@pytest.mark.parametrize("scale", [1e-30, 1e-22, 1e-12, 1e12, 1e25])
+@pytest.mark.parametrize("n", [600, 32768, 100000, (1 << 20) + 3])
+def test_statistics_of_tiny_and_huge_magnitudes(n, scale):
+    """The chunked pass squares deviations in fp32; where those squares would underflow (|x| ~ 1e-30: gradients
+    late in training) or overflow it must fall back to fp64 — torch's CPU std accumulates in double."""
+    g = torch.Generator().manual_seed(n)
+    x = (torch.randn(n, generator=g) * scale + 0.25 * scale)
+    xd = x.to(DEV)
+    want_mean, want_std = x.double().mean().item(), x.double().std().item()
+    if n > 32768:
+        ms = cabi.stats_full(xd).cpu()
+    else:
+        _, ms = cabi.roundtrip_small(xd, cabi.codec_params(SmaqConfig(stochastic_rounding=False)), want_stats=True)
+        ms = ms.cpu()
+    assert rel(ms[0].item(), want_mean, max(abs(want_mean), want_std)) < 1e-6
+    assert rel(ms[1].item(), want_std) < 1e-6
