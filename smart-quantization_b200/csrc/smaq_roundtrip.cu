@@ -523,30 +523,9 @@ __global__ void __launch_bounds__(kStatsThreads) multi_stats_kernel(const smaq_t
   const int64_t start = (int64_t)(item - ws.prefix[t]) * kMultiChunk;
   const int64_t len = min(kMultiChunk, d.n - start);
   const float* x = d.x + start;
-  Acc acc;
-  acc.m = Moments{0.0, 0.0, 0.0};
-  acc.hi = -INFINITY;
-  acc.lo = INFINITY;
-  if (aligned16(x)) {
-    const float4* xv = reinterpret_cast<const float4*>(x);
-    const int64_t nvec = len >> 2;
-    int64_t v = threadIdx.x;
-    for (; v + 3 * kStatsThreads < nvec; v += 4 * kStatsThreads) {
-      const float4 a = ldg_stream(xv + v), b = ldg_stream(xv + v + kStatsThreads), c = ldg_stream(xv + v + 2 * kStatsThreads),
-                   e = ldg_stream(xv + v + 3 * kStatsThreads);
-      const float r[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, e.x, e.y, e.z, e.w};
-      merge_chunk<0, 16>(acc, r);
-    }
-    for (; v < nvec; v += kStatsThreads) {
-      const float4 a = ldg_stream(xv + v);
-      const float r[4] = {a.x, a.y, a.z, a.w};
-      merge_chunk<0, 4>(acc, r);
-    }
-    const int64_t tail = nvec << 2;
-    if (threadIdx.x < len - tail) merge_one<0>(acc, x[tail + threadIdx.x]);
-  } else {
-    for (int64_t i = threadIdx.x; i < len; i += kStatsThreads) merge_one<0>(acc, x[i]);
-  }
+  // the statistics kernel's chunked, software-pipelined pass with the block as the whole grid
+  Acc acc = aligned16(x) ? accumulate_tensor<0, true>(x, len, threadIdx.x, kStatsThreads)
+                         : accumulate_tensor<0, false>(x, len, threadIdx.x, kStatsThreads);
   acc = block_combine<0>(acc, smem);
   if (threadIdx.x == 0) {
     double* p = ws.partials + (size_t)item * 3;
@@ -584,23 +563,36 @@ template <bool kStochastic>
 __global__ void __launch_bounds__(kStatsThreads) multi_apply_kernel(const smaq_tensor_desc* __restrict__ descs, int count,
                                                                     MultiWs ws, const __grid_constant__ KernelParams kp) {
   __shared__ Acc smem[kStatsThreads / 32];
-  __shared__ float bcast[2];
   const int item = blockIdx.x;
   if (item >= ws.prefix[count]) return;
   const int t = multi_find(ws.prefix, count, item);
   const smaq_tensor_desc d = descs[t];
   const int first = ws.prefix[t], last = ws.prefix[t + 1];
-  Acc f;
-  f.m = Moments{0.0, 0.0, 0.0};
-  f.hi = -INFINITY;
-  f.lo = INFINITY;
+  // this tensor's item moments by the statistics kernel's two sums (N and sum n*mean, then M2 about the combined
+  // mean; the records come back from L1 for the second): fixed order, the same bits in every block of the tensor,
+  // no chain of Chan merges per thread
+  const double* parts = ws.partials;
+  double tn = 0.0, s1 = 0.0;
+  float hi = 0.f, lo = 0.f;
   for (int b = first + threadIdx.x; b < last; b += kStatsThreads) {
-    const double* p = ws.partials + (size_t)b * 3;
-    f.m = merge(f.m, Moments{p[0], p[1], p[2]});
+    const double* p = parts + (size_t)b * 3;
+    const double pn = p[0], pm = p[1];
+    tn += pn;
+    s1 += pn == 0.0 ? 0.0 : pn * pm;
   }
-  f = block_combine<0>(f, smem);
-  if (threadIdx.x == 0) finalize<0>(f, /*unbiased=*/1, bcast);
-  __syncthreads();
+  block_sum2<false>(tn, s1, hi, lo, smem);
+  const double mean = weighted_mean(tn, s1);
+  double q = 0.0, unused = 0.0;
+  for (int b = first + threadIdx.x; b < last; b += kStatsThreads) {
+    const double* p = parts + (size_t)b * 3;
+    q += m2_about(Moments{p[0], p[1], p[2]}, mean);
+  }
+  block_sum2<false>(q, unused, hi, lo, smem);
+  Acc f;
+  f.m = Moments{tn, mean, q};
+  f.hi = f.lo = 0.f;
+  float bcast[2];
+  finalize<0>(f, /*unbiased=*/1, bcast);  // every thread holds the sums
   KernelParams k = kp;
   k.all_positive = d.all_positive;
   k.saturate = 0;
