@@ -73,3 +73,19 @@ def test_cpu_tensors_are_refused_not_emulated():
         args.precision = 32
         with pytest.raises(NativeLibraryError):
             cls(args)(torch.randn(64))
+
+
+def test_batched_entry_points_refuse_cpu_tensors_too():
+    """compress_many (what OptimLP calls per phase) must fail as loudly as the per-tensor call: no CPU emulation."""
+    import pytest
+    import torch
+    from argparse import ArgumentParser
+
+    from smart_compress._native import NativeLibraryError
+    from smart_compress.compress import BF16, FP8, FP16, SmartFP
+
+    for cls in (SmartFP, FP8, FP16, BF16):
+        args = cls.add_argparse_args(ArgumentParser()).parse_args([])
+        args.precision = 32
+        with pytest.raises(NativeLibraryError):
+            cls(args).compress_many([torch.randn(64), torch.randn(100)], None, tag="optimizer_grad")
