@@ -27,7 +27,8 @@
 extern "C" {
 #endif
 
-#define SMAQ_B200_ABI_VERSION 3 /* 2: packed stream SQB2, count_saturated, smaq_compress, tensor_desc.stream; 3: smaq_float_quantize_multi */
+#define SMAQ_B200_ABI_VERSION 4 /* 2: packed stream SQB2, count_saturated, smaq_compress, tensor_desc.stream; 3: smaq_float_quantize_multi;
+                                    4: smaq_roundtrip_bn, smaq_roundtrip_multi(mean_std_out), range_std in the sampled statistics */
 
 typedef void* smaq_stream_t; /* cudaStream_t */
 
@@ -54,8 +55,8 @@ typedef struct smaq_codec_params {
   float range_outlier;  /* fp32(range_outlier)  smart.py:75-77 */
   float clamp_lo;       /* clamped_range        smart.py:82-84 */
   float clamp_hi;
-  int32_t bits_main;    /* --num_bits_main    (3..16) */
-  int32_t bits_outlier; /* --num_bits_outlier (bits_main..17) */
+  int32_t bits_main;    /* --num_bits_main    (2..32; the packed stream: 4..8) */
+  int32_t bits_outlier; /* --num_bits_outlier (2..32; the packed stream: bits_main + 0..4) */
   int32_t stochastic;   /* 0: trunc (smart.py:169); 1: stochastic rounding (smart.py:93-98) */
   int32_t all_positive; /* clamp_min(0) at the end (smart.py:181-182) */
   int32_t saturate;     /* round trip only: clamp codes to what the packed format holds (not in
@@ -80,12 +81,13 @@ int smaq_stats_range(const float* x, int64_t n, float* mean_std, void* ws, size_
                      smaq_stream_t stream);
 
 /* --use_sample_stats (smart.py:86-91): mean and BIASED std of x[idx[0..k)].  idx is a device
- * array of int64 indices (the caller's permutation prefix), k <= 1024. */
-int smaq_stats_sampled(const float* x, int64_t n, const int64_t* idx, int32_t k, float* mean_std,
+ * array of int64 indices (the caller's permutation prefix).  range_std != 0: --use_range_std_dev as well, i.e.
+ * std = (max - min) / sqrt(2 ln k) over the k samples (smart.py:91 calls _get_std on the sample, :100-106). */
+int smaq_stats_sampled(const float* x, int64_t n, const int64_t* idx, int32_t k, int32_t range_std, float* mean_std,
                        smaq_stream_t stream);
 /* Same, but the k distinct indices are drawn on the device (Philox + Floyd's algorithm): a
  * uniform k-subset, the law of randperm(n)[:k], without materialising an n-element permutation. */
-int smaq_stats_sampled_draw(const float* x, int64_t n, int32_t k, uint64_t seed, uint64_t offset,
+int smaq_stats_sampled_draw(const float* x, int64_t n, int32_t k, int32_t range_std, uint64_t seed, uint64_t offset,
                             float* mean_std, smaq_stream_t stream);
 
 /* Fused fake-quantisation round trip — replaces smart.py:151-182 (~26 elementwise kernels, a
@@ -95,6 +97,16 @@ int smaq_stats_sampled_draw(const float* x, int64_t n, int32_t k, uint64_t seed,
  * y may alias x. */
 int smaq_roundtrip(const float* x, float* y, int64_t n, const float* mean_std, const float* probs,
                    const smaq_codec_params* params, smaq_stream_t stream);
+
+/* --use_batch_norm (smart.py:121,136-149,174-179; the hook passes the producing BatchNorm2d's weight and bias,
+ * util/pytorch/autograd.py:64-72): x is an NCHW feature map, element i belongs to channel (i / inner) % channels
+ * (inner = H * W).  Per element: x' = (x - beta_c) / gamma_c, the round trip of x' under mean_std (statistics of
+ * x itself: the reference takes them BEFORE the un-affine), y = y' * gamma_c + beta_c, then clamp_min(0) if
+ * params->all_positive.  --bn_scalar_params: pass the two means as 1-element arrays with channels = 1.
+ * Replaces four permute+clone copies and four elementwise passes around the chain.  y may alias x. */
+int smaq_roundtrip_bn(const float* x, float* y, int64_t n, const float* mean_std, const float* probs, const float* gamma,
+                      const float* beta, int64_t channels, int64_t inner, const smaq_codec_params* params,
+                      smaq_stream_t stream);
 
 /* The whole default call in one entry point — full-tensor unbiased statistics, then the round trip
  * (smart.py:130-182 with the reference's default flags): what the training hooks issue hundreds of
@@ -134,9 +146,12 @@ typedef struct smaq_tensor_desc {
   int32_t stream;       /* Philox stream of this tensor = params->offset + stream */
 } smaq_tensor_desc;
 size_t smaq_multi_workspace_bytes(int32_t count, int64_t total_elems);
+/* mean_std_out: optional device float[count][2]; entry i receives the (mean, std) tensor i was quantised with
+ * (untouched for tensors below min_size), so a caller — the parity tests — can check the codes against the
+ * reference given those statistics. */
 int smaq_roundtrip_multi(const smaq_tensor_desc* descs, int32_t count, int64_t max_n, int64_t total_elems,
                          const smaq_codec_params* params, int64_t min_size, void* ws, size_t ws_bytes,
-                         smaq_stream_t stream);
+                         float* mean_std_out, smaq_stream_t stream);
 
 /* ---- packed SmaQ stream ------------------------------------------------------------------ */
 

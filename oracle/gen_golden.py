@@ -51,6 +51,8 @@ def make_input(kind: str, n: int, seed: int) -> torch.Tensor:
         return torch.randn(n, generator=g) * 1e-30
     if kind == "image":  # a 4-D feature map, as the autograd hook sees it
         return torch.randn(n, generator=g).view(2, -1, 4, 4).relu()
+    if kind == "image3":  # batch of 3 (N != W != C, so a wrong permutation cannot pass by accident)
+        return (torch.randn(n, generator=g) + 0.3).view(3, -1, 2, 8)
     raise ValueError(kind)
 
 
@@ -79,6 +81,15 @@ CASES = [
     ("range_std_sr", "normal", 3000, 18, ["--use_range_std_dev"], {}, 32),
     ("prec16_clamp", "tiny", 600, 19, [], {}, 16),
     ("image_sr", "image", 2 * 5 * 16, 20, [], {}, 32),
+    ("sampled_range_sr", "outliers", 3000, 26, ["--use_sample_stats", "--use_range_std_dev"], {}, 32),
+    # --use_batch_norm (smart.py:121,136-149,174-179): an NCHW feature map with the layer's gamma / beta; the
+    # marker "bn" is replaced by seeded (gamma, beta) of C entries, stored next to the case
+    ("bn_sr", "image", 2 * 5 * 16, 21, ["--use_batch_norm"], {"batch_norm_stats": "bn"}, 32),
+    ("bn_scalar_sr", "image", 2 * 5 * 16, 22, ["--use_batch_norm", "--bn_scalar_params"], {"batch_norm_stats": "bn"}, 32),
+    ("bn_allpos_trunc", "image3", 3 * 7 * 16, 23, ["--use_batch_norm", "--no_stochastic_rounding"],
+     {"batch_norm_stats": "bn", "all_positive": True}, 32),
+    ("bn_flag_without_stats_sr", "image", 2 * 5 * 16, 24, ["--use_batch_norm"], {}, 32),
+    ("bn_stats_without_flag_sr", "image", 2 * 5 * 16, 25, [], {"batch_norm_stats": "bn"}, 32),
 ]
 
 
@@ -88,6 +99,12 @@ def run_case(name, kind, n, seed, argv, kwargs, precision):
     probs = torch.rand(x.shape, generator=g)
     perm = torch.randperm(x.numel(), generator=g)
     fp = refload.load_reference_smartfp(argv, precision=precision)
+    kwargs = dict(kwargs)
+    bn = None
+    if kwargs.get("batch_norm_stats") == "bn":  # per-channel affine parameters of the producing BatchNorm2d
+        channels = x.shape[1]
+        bn = (torch.rand(channels, generator=g) + 0.5, torch.randn(channels, generator=g) * 0.1)
+        kwargs["batch_norm_stats"] = bn
 
     real_rand_like, real_randperm = torch.rand_like, torch.randperm
     used = {"probs": False, "perm": False}
@@ -114,7 +131,7 @@ def run_case(name, kind, n, seed, argv, kwargs, precision):
         f"{name}/x": x.numpy(),
         f"{name}/y": y.numpy(),
         f"{name}/argv": np.array(" ".join(argv)),
-        f"{name}/kwargs": np.array(repr(kwargs)),
+        f"{name}/kwargs": np.array(repr({k: v for k, v in kwargs.items() if k != "batch_norm_stats"})),
         f"{name}/precision": np.array(precision),
         f"{name}/same_object": np.array(y is xin),
     }
@@ -122,6 +139,8 @@ def run_case(name, kind, n, seed, argv, kwargs, precision):
         out[f"{name}/probs"] = probs.numpy()
     if used["perm"]:
         out[f"{name}/idx"] = perm[:k].numpy()
+    if bn is not None:
+        out[f"{name}/gamma"], out[f"{name}/beta"] = bn[0].numpy(), bn[1].numpy()
     return out
 
 

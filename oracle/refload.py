@@ -37,6 +37,47 @@ class _NullProfiler:
         yield
 
 
+class ParsedArgs(Exception):
+    """Raised by the stand-in Trainer to hand the reference's fully parsed Namespace back to the caller."""
+
+    def __init__(self, args):
+        super().__init__("parsed")
+        self.parsed = args
+
+
+class _CapturingTrainer:
+    """Stands in for pytorch_lightning.Trainer in util/train.py: contributes the one Trainer flag the codecs read
+    (--precision) and stops ``init_model_from_args`` right after its two-phase parse (train.py:191)."""
+
+    @staticmethod
+    def add_argparse_args(parser):
+        parser.add_argument("--precision", type=int, default=32)
+        parser.add_argument("--terminate_on_nan", action="store_true")
+        return parser
+
+    @staticmethod
+    def from_argparse_args(args, **kwargs):
+        raise ParsedArgs(args)
+
+
+def _mapping_action(mapping):
+    """argparse_utils.mapping_action: store mapping[value]; a string default is mapped as well (the reference
+    asserts that ``compression_cls`` is a class even when --compress is absent, util/train.py:58)."""
+    import argparse
+
+    class MappingAction(argparse.Action):
+        def __init__(self, option_strings, dest, default=None, **kwargs):
+            kwargs.pop("choices", None)
+            if isinstance(default, str):
+                default = mapping[default]
+            super().__init__(option_strings, dest, default=default, choices=list(mapping), **kwargs)
+
+        def __call__(self, parser, namespace, values, option_string=None):
+            setattr(namespace, self.dest, mapping[values])
+
+    return MappingAction
+
+
 def _install_stubs(float_quantize_impl=None):
     import torch.nn as nn
 
@@ -45,9 +86,17 @@ def _install_stubs(float_quantize_impl=None):
     prof = types.ModuleType("pytorch_lightning.profiler")
     base = types.ModuleType("pytorch_lightning.profiler.base")
     base.BaseProfiler = _NullProfiler
+    pl.LightningDataModule = type("LightningDataModule", (), {"__init__": lambda self, *a, **k: None})
+    pl.Trainer = _CapturingTrainer
+    loggers = types.ModuleType("pytorch_lightning.loggers")
+    tt = types.ModuleType("pytorch_lightning.loggers.test_tube")
+    tt.TestTubeLogger = lambda *a, **k: None
+    plugins = types.ModuleType("pytorch_lightning.plugins")
+    ttype = types.ModuleType("pytorch_lightning.plugins.training_type")
+    ttype.DDPPlugin = type("DDPPlugin", (), {})
     au = types.ModuleType("argparse_utils")
     aum = types.ModuleType("argparse_utils.mapping")
-    au.mapping_action = aum.mapping_action = lambda *a, **k: None
+    au.mapping_action = aum.mapping_action = _mapping_action
     qt = types.ModuleType("qtorch")
     qtq = types.ModuleType("qtorch.quant")
     qtf = types.ModuleType("qtorch.quant.quant_function")
@@ -60,6 +109,10 @@ def _install_stubs(float_quantize_impl=None):
         "pytorch_lightning": pl,
         "pytorch_lightning.profiler": prof,
         "pytorch_lightning.profiler.base": base,
+        "pytorch_lightning.loggers": loggers,
+        "pytorch_lightning.loggers.test_tube": tt,
+        "pytorch_lightning.plugins": plugins,
+        "pytorch_lightning.plugins.training_type": ttype,
         "argparse_utils": au,
         "argparse_utils.mapping": aum,
         "qtorch": qt,
@@ -103,3 +156,31 @@ def load_reference_smartfp(argv=(), precision=32):
         args = SmartFP.add_argparse_args(ArgumentParser()).parse_args(list(argv))
         args.precision = precision
         return SmartFP(args)
+
+
+def reference_parse_args(argv):
+    """Run the reference's own ``init_model_from_args`` (smart_compress/util/train.py:74-184) up to the end of
+    its two-phase parse and return (Namespace, {name: value}) of what it parsed.  Classes and functions are
+    reported by name (the reference's objects do not outlive the import context)."""
+    import importlib
+
+    with reference_modules():
+        for optional in ("torchmetrics", "torchmetrics.functional", "datasets"):
+            try:
+                importlib.import_module(optional)
+            except Exception:
+                stub = types.ModuleType(optional)
+                stub.load_dataset = stub.load_metric = lambda *a, **k: None
+                sys.modules[optional] = stub
+        from smart_compress.util.train import init_model_from_args
+
+        try:
+            init_model_from_args(list(argv))
+        except ParsedArgs as e:
+            args = e.parsed
+        else:  # pragma: no cover
+            raise RuntimeError("the stand-in Trainer did not stop init_model_from_args")
+        flat = {}
+        for k, v in vars(args).items():
+            flat[k] = getattr(v, "__name__", v) if (isinstance(v, type) or callable(v)) else v
+        return args, flat

@@ -37,6 +37,8 @@ class SmaqConfig:
     outlier_std_dev_threshold: float = 2.5
     min_size: int = 8
     use_range_std_dev: bool = False
+    use_batch_norm: bool = False
+    bn_scalar_params: bool = False
     precision: int = 32
 
     # smart.py:75-80
@@ -115,9 +117,14 @@ def smaq_roundtrip(
     std: Optional[torch.Tensor] = None,
     all_positive: bool = False,
     saturate: bool = False,
+    batch_norm_stats=None,
 ) -> SmaqResult:
-    """The whole fake-quantisation call, smart.py:123-190 (batch-norm mode excluded).
+    """The whole fake-quantisation call, smart.py:121-190.
 
+    ``batch_norm_stats`` (gamma, beta) of the producing BatchNorm2d; honoured only under
+                 --use_batch_norm (smart.py:121): the NCHW map is un-affined per channel AFTER the
+                 statistics were taken (smart.py:136-149) and re-affined before ``all_positive``
+                 (smart.py:174-182).
     ``probs``   uniform [0,1) numbers, same shape as data (needed when stochastic_rounding)
     ``idx``     sample indices for --use_sample_stats (the first k entries of the permutation)
     ``mean/std`` override the statistics step (used to feed a kernel's stats back in)
@@ -138,6 +145,13 @@ def smaq_roundtrip(
             mean, std = full_mean_std(data, cfg)  # smart.py:131
     mean = torch.as_tensor(mean, dtype=data.dtype)
     std_raw = torch.as_tensor(std, dtype=data.dtype)
+
+    use_bn = cfg.use_batch_norm and batch_norm_stats is not None  # smart.py:121
+    if use_bn:  # smart.py:136-149
+        gamma, beta = batch_norm_stats
+        if cfg.bn_scalar_params:
+            gamma, beta = gamma.mean(), beta.mean()
+        data = ((data.permute(0, 3, 2, 1).clone() - beta) / gamma).permute(0, 3, 2, 1).clone()
 
     std_dev = std_raw
     if std_dev == 0:  # smart.py:151-152
@@ -165,6 +179,8 @@ def smaq_roundtrip(
 
     y = (code / ranges) - scalars  # smart.py:171
     y = (y * std_dev) + mean  # smart.py:172
+    if use_bn:  # smart.py:174-179
+        y = ((y.permute(0, 3, 2, 1).clone() * gamma) + beta).permute(0, 3, 2, 1).clone()
     if all_positive:  # smart.py:181-182
         y = y.clamp_min(0.0)
 

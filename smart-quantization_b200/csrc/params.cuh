@@ -38,8 +38,11 @@ __device__ __forceinline__ Scalars scalars_from(float mean, float std_raw, const
 inline int check_params(const smaq_codec_params* p) {
   if (!p) return fail(SMAQ_ERR_ARG, "params is NULL");
   if (!(p->threshold > 0.0f)) return fail(SMAQ_ERR_ARG, "threshold must be > 0");
-  if (p->bits_main < 3 || p->bits_main > 16 || p->bits_outlier < p->bits_main || p->bits_outlier > 17)
-    return fail(SMAQ_ERR_ARG, "unsupported bit widths main=%d outlier=%d", p->bits_main, p->bits_outlier);
+  // the fake-quantisation round trip needs the widths only for the optional saturation limit 2^(bits-2)-1 (the
+  // reference never checks them; its ranges are derived on the host): anything that limit can be formed for is
+  // accepted here.  The packed encoder has its own, narrower, list (smaq_packed_layout_for).
+  if (p->bits_main < 2 || p->bits_main > 32 || p->bits_outlier < 2 || p->bits_outlier > 32)
+    return fail(SMAQ_ERR_ARG, "unsupported bit widths main=%d outlier=%d (2..32)", p->bits_main, p->bits_outlier);
   return SMAQ_OK;
 }
 

@@ -384,6 +384,36 @@ __global__ void __launch_bounds__(kRtThreads) roundtrip_unaligned_kernel(const f
     y[i] = roundtrip_element<kStochastic, kHasProbs>(x, probs, i, s, kp);
 }
 
+// --use_batch_norm (smart.py:121,136-149,174-179): the feature map of a BatchNorm2d is un-affined per channel
+// before the z-score — x' = (x - beta_c) / gamma_c, AFTER the statistics were taken on x itself — and re-affined
+// after the inverse, y = y' * gamma_c + beta_c, then clamp_min(0) if all_positive.  The reference does it with four
+// permute+clone copies and four elementwise passes around its chain; here it is the element path of the round trip
+// with the channel looked up from the NCHW index: one read and one write.  Off by default in the reference, so the
+// kernel is the plain one-element-per-thread form (IEEE division), not the packed 256-bit one.
+template <bool kStochastic, bool kHasProbs>
+__global__ void __launch_bounds__(kRtThreads) roundtrip_bn_kernel(const float* x, float* y, int64_t n,
+                                                                  const float* __restrict__ mean_std,
+                                                                  const float* __restrict__ probs,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, int64_t channels,
+                                                                  int64_t inner, const __grid_constant__ KernelParams kp) {
+  const Scalars s = scalars_from(mean_std[0], mean_std[1], kp);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = channels == 1 ? 0 : (i / inner) % channels;
+    const float g = gamma[c], b = beta[c];
+    float p = 0.f;
+    if (kStochastic)
+      p = kHasProbs ? probs[i]
+                    : uniform16(philox_word(philox_group(kp.keys, (uint64_t)(i >> 3), kp.offset), (int)((i & 7) >> 1)),
+                                (int)(i & 1));
+    const float xu = true_div(sub_rn(x[i], b), g);                                     // smart.py:144-149
+    float v = roundtrip_scalar<kStochastic>(xu, p, s, kp.saturate != 0, /*all_positive=*/false);
+    v = add_rn(mul_rn(v, g), b);                                                       // smart.py:174-179
+    if (kp.all_positive) v = (v < 0.0f) ? 0.0f : v;                                    // smart.py:181-182
+    y[i] = v;
+  }
+}
+
 // ---- small tensors: statistics + round trip in one block, one launch ---------------------------
 // The optimizer-side tensors of the reference workloads are tiny (median 512 elements for
 // ResNet-18); two launches per call would be pure launch latency.
@@ -443,7 +473,8 @@ __global__ void __launch_bounds__(kStatsThreads) roundtrip_small_kernel(const fl
 template <bool kStochastic>
 __global__ void __launch_bounds__(kStatsThreads) multi_small_kernel(const smaq_tensor_desc* __restrict__ descs,
                                                                     int count, int64_t min_size,
-                                                                    const __grid_constant__ KernelParams kp) {
+                                                                    const __grid_constant__ KernelParams kp,
+                                                                    float* __restrict__ mean_std_out) {
   __shared__ Acc smem[kStatsThreads / 32];
   __shared__ float bcast[2];
   for (int t = blockIdx.x; t < count; t += gridDim.x) {
@@ -457,7 +488,8 @@ __global__ void __launch_bounds__(kStatsThreads) multi_small_kernel(const smaq_t
     KernelParams k = kp;
     k.all_positive = d.all_positive;
     k.offset = kp.offset + (uint64_t)(uint32_t)d.stream;  // one Philox stream per tensor
-    small_body<kStochastic, false>(d.x, d.y, d.n, nullptr, k, nullptr, smem, bcast);
+    small_body<kStochastic, false>(d.x, d.y, d.n, nullptr, k, mean_std_out ? mean_std_out + 2 * (size_t)t : nullptr, smem,
+                                   bcast);
   }
 }
 
@@ -561,7 +593,8 @@ __device__ __forceinline__ void multi_apply_chunk(const float* x, float* y, int6
 
 template <bool kStochastic>
 __global__ void __launch_bounds__(kStatsThreads) multi_apply_kernel(const smaq_tensor_desc* __restrict__ descs, int count,
-                                                                    MultiWs ws, const __grid_constant__ KernelParams kp) {
+                                                                    MultiWs ws, const __grid_constant__ KernelParams kp,
+                                                                    float* __restrict__ mean_std_out) {
   __shared__ Acc smem[kStatsThreads / 32];
   const int item = blockIdx.x;
   if (item >= ws.prefix[count]) return;
@@ -593,6 +626,10 @@ __global__ void __launch_bounds__(kStatsThreads) multi_apply_kernel(const smaq_t
   f.hi = f.lo = 0.f;
   float bcast[2];
   finalize<0>(f, /*unbiased=*/1, bcast);  // every thread holds the sums
+  if (mean_std_out && item == first && threadIdx.x == 0) {  // the statistics every block of this tensor used
+    mean_std_out[2 * (size_t)t] = bcast[0];
+    mean_std_out[2 * (size_t)t + 1] = bcast[1];
+  }
   KernelParams k = kp;
   k.all_positive = d.all_positive;
   k.saturate = 0;
@@ -716,6 +753,29 @@ int smaq_roundtrip(const float* x, float* y, int64_t n, const float* mean_std, c
   return SMAQ_OK;
 }
 
+int smaq_roundtrip_bn(const float* x, float* y, int64_t n, const float* mean_std, const float* probs, const float* gamma,
+                      const float* beta, int64_t channels, int64_t inner, const smaq_codec_params* params,
+                      smaq_stream_t stream_) {
+  using namespace smaq;
+  if (int rc = check_params(params)) return rc;
+  if (!x || !y || !mean_std || !gamma || !beta || n < 0 || channels < 1 || inner < 1)
+    return fail(SMAQ_ERR_ARG, "roundtrip_bn: null pointer, n < 0, channels < 1 or inner < 1");
+  if (n == 0) return SMAQ_OK;
+  if (channels > 1 && n % (channels * inner) != 0)
+    return fail(SMAQ_ERR_ARG, "roundtrip_bn: n is not a multiple of channels * inner (NCHW layout expected)");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const KernelParams kp = to_kernel_params(*params);
+  const int grid = rt_grid(n);
+  if (!params->stochastic)
+    roundtrip_bn_kernel<false, false><<<grid, kRtThreads, 0, stream>>>(x, y, n, mean_std, probs, gamma, beta, channels, inner, kp);
+  else if (probs)
+    roundtrip_bn_kernel<true, true><<<grid, kRtThreads, 0, stream>>>(x, y, n, mean_std, probs, gamma, beta, channels, inner, kp);
+  else
+    roundtrip_bn_kernel<true, false><<<grid, kRtThreads, 0, stream>>>(x, y, n, mean_std, probs, gamma, beta, channels, inner, kp);
+  SMAQ_LAUNCH_OK();
+  return SMAQ_OK;
+}
+
 int smaq_count_outliers(const float* x, int64_t n, const float* mean_std, const smaq_codec_params* params,
                         unsigned long long* counter, smaq_stream_t stream_) {
   using namespace smaq;
@@ -783,7 +843,7 @@ size_t smaq_multi_workspace_bytes(int32_t count, int64_t total_elems) {
 
 int smaq_roundtrip_multi(const smaq_tensor_desc* descs, int32_t count, int64_t max_n, int64_t total_elems,
                          const smaq_codec_params* params, int64_t min_size, void* ws, size_t ws_bytes,
-                         smaq_stream_t stream_) {
+                         float* mean_std_out, smaq_stream_t stream_) {
   using namespace smaq;
   if (int rc = check_params(params)) return rc;
   if (!descs || count < 0) return fail(SMAQ_ERR_ARG, "roundtrip_multi: bad argument");
@@ -794,8 +854,8 @@ int smaq_roundtrip_multi(const smaq_tensor_desc* descs, int32_t count, int64_t m
   if (sms <= 0) sms = 148;
   // tensors of at most kSmallMax elements: statistics + round trip in one block each, one launch
   int grid = count < sms * 8 ? count : sms * 8;
-  if (params->stochastic) multi_small_kernel<true><<<grid, kStatsThreads, 0, stream>>>(descs, count, min_size, kp);
-  else multi_small_kernel<false><<<grid, kStatsThreads, 0, stream>>>(descs, count, min_size, kp);
+  if (params->stochastic) multi_small_kernel<true><<<grid, kStatsThreads, 0, stream>>>(descs, count, min_size, kp, mean_std_out);
+  else multi_small_kernel<false><<<grid, kStatsThreads, 0, stream>>>(descs, count, min_size, kp, mean_std_out);
   SMAQ_LAUNCH_OK();
   if (max_n <= kSmallMax) return SMAQ_OK;
   // the larger ones: work items of kMultiChunk elements
@@ -808,8 +868,8 @@ int smaq_roundtrip_multi(const smaq_tensor_desc* descs, int32_t count, int64_t m
   if (items > 0x7fffffff) return fail(SMAQ_ERR_UNSUPPORTED, "roundtrip_multi: too many work items");
   multi_setup_kernel<<<1, kStatsThreads, 0, stream>>>(descs, count, mw.prefix);
   multi_stats_kernel<<<(unsigned)items, kStatsThreads, 0, stream>>>(descs, count, mw);
-  if (params->stochastic) multi_apply_kernel<true><<<(unsigned)items, kStatsThreads, 0, stream>>>(descs, count, mw, kp);
-  else multi_apply_kernel<false><<<(unsigned)items, kStatsThreads, 0, stream>>>(descs, count, mw, kp);
+  if (params->stochastic) multi_apply_kernel<true><<<(unsigned)items, kStatsThreads, 0, stream>>>(descs, count, mw, kp, mean_std_out);
+  else multi_apply_kernel<false><<<(unsigned)items, kStatsThreads, 0, stream>>>(descs, count, mw, kp, mean_std_out);
   SMAQ_LAUNCH_OK();
   return SMAQ_OK;
 }

@@ -14,6 +14,7 @@
 // HBM roofline: 4 bytes read per element, nothing written.
 #include "common.cuh"
 #include "moments.cuh"
+#include "smaq_math.cuh"
 
 namespace smaq {
 
@@ -57,7 +58,9 @@ __global__ void __launch_bounds__(kStatsThreads, SMAQ_STATS_CTAS_PER_SM) stats_k
   }
 }
 
-// --use_sample_stats: k gathered values, one block.
+// --use_sample_stats: k gathered values, one block.  kKind 1: --use_range_std_dev as well — the reference's
+// _get_sample_mean_std calls _get_std(sample), i.e. (max - min) / sqrt(2 ln k) over the k samples (smart.py:86-108).
+template <int kKind>
 __global__ void __launch_bounds__(kStatsThreads) sampled_stats_kernel(const float* __restrict__ x, int64_t n,
                                                                       const int64_t* __restrict__ idx, int k,
                                                                       float* __restrict__ out) {
@@ -68,14 +71,15 @@ __global__ void __launch_bounds__(kStatsThreads) sampled_stats_kernel(const floa
   acc.lo = INFINITY;
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     int64_t j = idx[i];
-    if (j >= 0 && j < n) merge_one<0>(acc, x[j]);
+    if (j >= 0 && j < n) merge_one<kKind>(acc, x[j]);
   }
-  acc = block_combine<0>(acc, smem);
-  if (threadIdx.x == 0) finalize<0>(acc, /*unbiased=*/0, out);  // smart.py:91: unbiased=False
+  acc = block_combine<kKind>(acc, smem);
+  if (threadIdx.x == 0) finalize<kKind>(acc, /*unbiased=*/0, out);  // smart.py:91: unbiased=False
 }
 
 // Same, drawing the k distinct indices on the device with Floyd's algorithm (a uniform k-subset,
 // which is the law of randperm(n)[:k]; mean and std do not depend on the order).
+template <int kKind>
 __global__ void __launch_bounds__(32) sampled_draw_stats_kernel(const float* __restrict__ x, int64_t n, int k,
                                                                 uint64_t seed, uint64_t offset,
                                                                 float* __restrict__ out) {
@@ -97,13 +101,17 @@ __global__ void __launch_bounds__(32) sampled_draw_stats_kernel(const float* __r
   acc.m = Moments{0.0, 0.0, 0.0};
   acc.hi = -INFINITY;
   acc.lo = INFINITY;
-  for (int i = lane; i < k; i += 32) merge_one<0>(acc, x[chosen[i]]);
+  for (int i = lane; i < k; i += 32) merge_one<kKind>(acc, x[chosen[i]]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     Moments other = shfl_xor(acc.m, o);
     acc.m = (lane & o) ? merge(other, acc.m) : merge(acc.m, other);
+    if (kKind == 1) {  // NaN-propagating like torch's max / min
+      acc.hi = max_nan(acc.hi, __shfl_xor_sync(0xffffffffu, acc.hi, o));
+      acc.lo = min_nan(acc.lo, __shfl_xor_sync(0xffffffffu, acc.lo, o));
+    }
   }
-  if (lane == 0) finalize<0>(acc, 0, out);
+  if (lane == 0) finalize<kKind>(acc, 0, out);
 }
 
 static int stats_grid(int64_t n) {
@@ -167,20 +175,22 @@ int smaq_s2fp8_stats(const float* x, int64_t n, float* mu_max, void* ws, size_t 
   return smaq::launch_stats<2>(x, n, 0, mu_max, ws, ws_bytes, (cudaStream_t)stream);
 }
 
-int smaq_stats_sampled(const float* x, int64_t n, const int64_t* idx, int32_t k, float* mean_std,
+int smaq_stats_sampled(const float* x, int64_t n, const int64_t* idx, int32_t k, int32_t range_std, float* mean_std,
                        smaq_stream_t stream) {
   if (!x || !idx || !mean_std || n <= 0 || k <= 0) return smaq::fail(SMAQ_ERR_ARG, "stats_sampled: bad argument");
-  smaq::sampled_stats_kernel<<<1, smaq::kStatsThreads, 0, (cudaStream_t)stream>>>(x, n, idx, k, mean_std);
+  if (range_std) smaq::sampled_stats_kernel<1><<<1, smaq::kStatsThreads, 0, (cudaStream_t)stream>>>(x, n, idx, k, mean_std);
+  else smaq::sampled_stats_kernel<0><<<1, smaq::kStatsThreads, 0, (cudaStream_t)stream>>>(x, n, idx, k, mean_std);
   SMAQ_LAUNCH_OK();
   return SMAQ_OK;
 }
 
-int smaq_stats_sampled_draw(const float* x, int64_t n, int32_t k, uint64_t seed, uint64_t offset, float* mean_std,
-                            smaq_stream_t stream) {
+int smaq_stats_sampled_draw(const float* x, int64_t n, int32_t k, int32_t range_std, uint64_t seed, uint64_t offset,
+                            float* mean_std, smaq_stream_t stream) {
   if (!x || !mean_std || n <= 0 || k <= 0) return smaq::fail(SMAQ_ERR_ARG, "stats_sampled_draw: bad argument");
   if (k > 1024) return smaq::fail(SMAQ_ERR_UNSUPPORTED, "stats_sampled_draw: k > 1024");
   if (k > n) k = (int32_t)n;
-  smaq::sampled_draw_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(x, n, k, seed, offset, mean_std);
+  if (range_std) smaq::sampled_draw_stats_kernel<1><<<1, 32, 0, (cudaStream_t)stream>>>(x, n, k, seed, offset, mean_std);
+  else smaq::sampled_draw_stats_kernel<0><<<1, 32, 0, (cudaStream_t)stream>>>(x, n, k, seed, offset, mean_std);
   SMAQ_LAUNCH_OK();
   return SMAQ_OK;
 }

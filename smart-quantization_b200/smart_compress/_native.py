@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libsmaq_b200.so")
 
 OK = 0
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class NativeLibraryError(RuntimeError):
@@ -120,8 +120,8 @@ _SIGNATURES = {
     "smaq_stats_workspace_bytes": (C.c_size_t, [_I64]),
     "smaq_stats_full": (C.c_int, [_P, _I64, C.c_int, _P, _P, C.c_size_t, _P]),
     "smaq_stats_range": (C.c_int, [_P, _I64, _P, _P, C.c_size_t, _P]),
-    "smaq_stats_sampled": (C.c_int, [_P, _I64, _P, C.c_int32, _P, _P]),
-    "smaq_stats_sampled_draw": (C.c_int, [_P, _I64, C.c_int32, C.c_uint64, C.c_uint64, _P, _P]),
+    "smaq_stats_sampled": (C.c_int, [_P, _I64, _P, C.c_int32, C.c_int32, _P, _P]),
+    "smaq_stats_sampled_draw": (C.c_int, [_P, _I64, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, _P, _P]),
     "smaq_roundtrip": (C.c_int, [_P, _P, _I64, _P, _P, C.POINTER(CodecParams), _P]),
     "smaq_compress_workspace_bytes": (C.c_size_t, [_I64]),
     "smaq_compress_workspace_init": (C.c_int, [_P, C.c_size_t, _P]),
@@ -130,7 +130,8 @@ _SIGNATURES = {
     "smaq_fused_small_max": (_I64, []),
     "smaq_roundtrip_small": (C.c_int, [_P, _P, _I64, _P, C.POINTER(CodecParams), _P, _P]),
     "smaq_multi_workspace_bytes": (C.c_size_t, [C.c_int32, _I64]),
-    "smaq_roundtrip_multi": (C.c_int, [_P, C.c_int32, _I64, _I64, C.POINTER(CodecParams), _I64, _P, C.c_size_t, _P]),
+    "smaq_roundtrip_multi": (C.c_int, [_P, C.c_int32, _I64, _I64, C.POINTER(CodecParams), _I64, _P, C.c_size_t, _P, _P]),
+    "smaq_roundtrip_bn": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _I64, _I64, C.POINTER(CodecParams), _P]),
     "smaq_packed_layout_for": (C.c_int, [_I64, C.c_int32, C.c_int32, C.POINTER(PackedLayout)]),
     "smaq_encode": (C.c_int, [_P, _I64, _P, _P, C.POINTER(CodecParams), _P, C.c_size_t, _P, C.c_size_t, _P]),
     "smaq_decode": (C.c_int, [_P, C.c_size_t, _I64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
@@ -198,6 +199,36 @@ def stream_ptr(device=None) -> int:
             index = device.index if device.index is not None else torch.cuda.current_device()
         return _raw_stream(index)
     return torch.cuda.current_stream(device).cuda_stream
+
+
+_get_device = getattr(torch._C, "_cuda_getDevice", None) or torch.cuda.current_device
+
+
+class _NoSwitch:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def on_device_of(t: torch.Tensor):
+    """Context in which the current CUDA device is ``t``'s.  The C entry points launch on the CURRENT device and
+    size their grids from it; a tensor on cuda:1 while cuda:0 is current (``model.to("cuda:1")`` without
+    ``set_device``) would otherwise be launched on the wrong GPU.  The reference's eager operators work on any
+    device.  Free when the devices already agree (one integer compare); a device switch otherwise."""
+    index = t.device.index
+    if index is None or index == _get_device():
+        return _NO_SWITCH
+    return torch.cuda.device(index)
+
+
+def wrong_device(t: torch.Tensor) -> bool:
+    index = t.device.index
+    return index is not None and index != _get_device()
 
 
 def ptr(t: torch.Tensor) -> int:

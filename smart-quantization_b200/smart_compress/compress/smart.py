@@ -53,13 +53,7 @@ class SmartFP(CompressionAlgorithmBase):
 
     def __init__(self, hparams: Namespace):
         super().__init__(hparams)
-        hp = self.hparams
-        # smart.py:75-84, evaluated in Python floats exactly as there
-        self.range_outlier = ((2 ** (hp.num_bits_outlier - 2)) - 1) / (
-            hp.outlier_std_dev_threshold - hp.main_std_dev_threshold
-        )
-        self.range_normal = ((2 ** (hp.num_bits_main - 2)) - 1) / hp.main_std_dev_threshold
-        self.clamped_range = (1e-4, 1e4) if getattr(hp, "precision", 32) == 16 else (1e-38, 1e38)
+        self._derive(self.hparams)
         self._calls = itertools.count()  # Philox stream offset: one stream per call
         self._tls = threading.local()
         self._small_max = int(N.load().smaq_fused_small_max())
@@ -68,6 +62,14 @@ class SmartFP(CompressionAlgorithmBase):
         self._ws_bytes = None
         self._desc_cache = {}            # compress_many: device descriptor arrays by (pointers, sizes)
         self._multi_ws = {}
+
+    def _derive(self, hp):
+        # smart.py:75-84, evaluated in Python floats exactly as there
+        self.range_outlier = ((2 ** (hp.num_bits_outlier - 2)) - 1) / (
+            hp.outlier_std_dev_threshold - hp.main_std_dev_threshold
+        )
+        self.range_normal = ((2 ** (hp.num_bits_main - 2)) - 1) / hp.main_std_dev_threshold
+        self.clamped_range = (1e-4, 1e4) if getattr(hp, "precision", 32) == 16 else (1e-38, 1e38)
 
     def _lean_flags(self) -> bool:
         """Whether the flags allow the lean path of __call__ (read per call: tests and callers mutate hparams)."""
@@ -83,18 +85,20 @@ class SmartFP(CompressionAlgorithmBase):
         """The per-call constants (smart.py:72-84 + the call's kwargs).  The flag-derived part is filled once
         per thread (forward calls come from the main thread, backward calls from autograd's worker); a call
         only stamps its own kwargs, the seed and its Philox stream number."""
+        hp = self.hparams
         p = getattr(self._tls, "params", None)
         if p is None:
-            hp = self.hparams
             p = N.CodecParams()
-            p.threshold = hp.main_std_dev_threshold
+            # like the reference: the ranges and the clamp are derived ONCE, in __init__ (smart.py:75-84) ...
             p.range_main = self.range_normal
             p.range_outlier = self.range_outlier
             p.clamp_lo, p.clamp_hi = self.clamped_range
-            p.bits_main = hp.num_bits_main
-            p.bits_outlier = hp.num_bits_outlier
             self._tls.params = p
-        hp = self.hparams
+        # ... while the threshold (smart.py:155-160) and the widths (smart.py:184-187) are read from hparams on
+        # every call, so update_hparams() or an in-place edit acts exactly as it does there
+        p.threshold = hp.main_std_dev_threshold
+        p.bits_main = hp.num_bits_main
+        p.bits_outlier = hp.num_bits_outlier
         p.stochastic = 1 if hp.stochastic_rounding else 0
         p.all_positive = 1 if all_positive else 0
         p.saturate = 1 if saturate else 0
@@ -115,20 +119,19 @@ class SmartFP(CompressionAlgorithmBase):
         stream = N.stream_ptr(flat.device)
         if hp.use_sample_stats:
             k = min(n, hp.num_samples)
+            rng = 1 if hp.use_range_std_dev else 0  # _get_std(sample): the range estimate over the k samples
             if sample_idx is not None:
                 idx = sample_idx.to(device=flat.device, dtype=torch.int64).contiguous()
-                N.check(lib.smaq_stats_sampled(N.ptr(flat), n, N.ptr(idx), int(idx.numel()), N.ptr(out), stream),
+                N.check(lib.smaq_stats_sampled(N.ptr(flat), n, N.ptr(idx), int(idx.numel()), rng, N.ptr(out), stream),
                         "smaq_stats_sampled")
             elif k <= 1024:
-                N.check(lib.smaq_stats_sampled_draw(N.ptr(flat), n, k, torch.initial_seed() & (2**64 - 1),
+                N.check(lib.smaq_stats_sampled_draw(N.ptr(flat), n, k, rng, torch.initial_seed() & (2**64 - 1),
                                                     (1 << 62) + next(self._calls), N.ptr(out), stream),
                         "smaq_stats_sampled_draw")
             else:
                 idx = torch.randperm(n, device=flat.device)[:k]
-                N.check(lib.smaq_stats_sampled(N.ptr(flat), n, N.ptr(idx), k, N.ptr(out), stream),
+                N.check(lib.smaq_stats_sampled(N.ptr(flat), n, N.ptr(idx), k, rng, N.ptr(out), stream),
                         "smaq_stats_sampled")
-            if hp.use_range_std_dev:
-                raise NotImplementedError("--use_sample_stats together with --use_range_std_dev")
             return out
         ws_bytes = lib.smaq_stats_workspace_bytes(n)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=flat.device)
@@ -155,7 +158,7 @@ class SmartFP(CompressionAlgorithmBase):
         if not extra and batch_norm_stats is None and Globals.profiler is None and self._lean_flags():
             numel = data.numel()
             if (numel > self._small_max and data.dtype is torch.float32 and data.is_cuda and data.is_contiguous()
-                    and not data.is_sparse):
+                    and not data.is_sparse and data.device.index == N._get_device()):
                 device = data.device
                 stream = N.stream_ptr(device)
                 key = (device.index, stream)
@@ -169,7 +172,7 @@ class SmartFP(CompressionAlgorithmBase):
                 if rc:
                     N.check(rc, "smaq_compress")
                 return out
-        with torch.no_grad():
+        with torch.no_grad(), (N.on_device_of(data) if data.is_cuda else N._NO_SWITCH):
             profiler = Globals.profiler
             if profiler is not None:
                 with profiler.profile("smaq"):
@@ -208,7 +211,7 @@ class SmartFP(CompressionAlgorithmBase):
         flat = src.view(-1)
         out = torch.empty_like(src)
         stream = N.stream_ptr(data.device)
-        params = self._params(all_positive and not use_bn, offset=extra.get("_offset"))
+        params = self._params(all_positive, offset=extra.get("_offset"))
         probs_ptr = None
         if probs is not None:
             probs = probs.to(device=data.device, dtype=torch.float32).contiguous()
@@ -238,15 +241,18 @@ class SmartFP(CompressionAlgorithmBase):
         else:
             mean_std = self.statistics(flat, sample_idx)  # statistics precede the BN un-affine (smart.py:130-149)
             if use_bn:
-                flat = self._bn_unaffine(src, batch_norm_stats).view(-1)
-            N.check(
-                lib.smaq_roundtrip(N.ptr(flat), N.ptr(out), numel, N.ptr(mean_std), probs_ptr, C.byref(params), stream),
-                "smaq_roundtrip",
-            )
-            if use_bn:
-                out = self._bn_reaffine(out, batch_norm_stats)
-                if all_positive:
-                    out = out.clamp_min_(0.0)
+                gamma, beta, channels, inner = self._bn_affine_params(src, batch_norm_stats)
+                N.check(
+                    lib.smaq_roundtrip_bn(N.ptr(flat), N.ptr(out), numel, N.ptr(mean_std), probs_ptr, N.ptr(gamma),
+                                          N.ptr(beta), channels, inner, C.byref(params), stream),
+                    "smaq_roundtrip_bn",
+                )
+            else:
+                N.check(
+                    lib.smaq_roundtrip(N.ptr(flat), N.ptr(out), numel, N.ptr(mean_std), probs_ptr, C.byref(params),
+                                       stream),
+                    "smaq_roundtrip",
+                )
 
         if hp.measure_compression_ratio:
             self.log_size(tag, orig_size, lambda: self._compressed_bits(flat, mean_std, params))
@@ -254,7 +260,7 @@ class SmartFP(CompressionAlgorithmBase):
 
     # -- many tensors, one launch (the optimizer side) ------------------------------------------
     @torch.no_grad()
-    def compress_many(self, tensors, kwargs_list=None, tag: str = None):
+    def compress_many(self, tensors, kwargs_list=None, tag: str = None, stats_out: Optional[dict] = None):
         """``[self(t, tag=tag, **kw) for t, kw in zip(tensors, kwargs_list)]`` in at most four launches
         (``smaq_roundtrip_multi``: per-tensor full statistics + round trip, one Philox stream per tensor;
         tensors up to ``smaq_fused_small_max()`` elements take one block each, larger ones are cut into
@@ -262,7 +268,9 @@ class SmartFP(CompressionAlgorithmBase):
         parameter, gradient and state tensor (reference optimizer.py:69-127); most of them are tiny
         (median 512 elements for ResNet-18), so per-tensor launches are pure latency.  The batched
         tensors are updated IN PLACE and returned as the same objects (the reference re-binds ``.data``
-        to a fresh tensor; nothing else aliases optimizer tensors, so the effect is the same)."""
+        to a fresh tensor; nothing else aliases optimizer tensors, so the effect is the same).
+        ``stats_out`` (a dict, parity tests): receives ``{index: device float[2]}`` with the (mean, std)
+        each batched tensor was quantised with."""
         hp = self.hparams
         lib = N.load()
         small_max = lib.smaq_fused_small_max()
@@ -294,7 +302,17 @@ class SmartFP(CompressionAlgorithmBase):
                 results[i] = self(t, tag=tag, _offset=first + stream_no, **kw)
         if not batch:
             return results
-        device = batch[0][1].device
+        by_device = {}
+        for item in batch:  # an optimizer whose parameters span GPUs: one launch set per device
+            by_device.setdefault(item[1].device, []).append(item)
+        for device, items in by_device.items():
+            with N.on_device_of(items[0][1]):
+                self._launch_many(device, items, first, stats_out)
+        return results
+
+    def _launch_many(self, device, batch, first, stats_out=None):
+        hp = self.hparams
+        lib = self._lib
         key = (device, tuple((t.data_ptr(), t.numel(), ap, sn) for _, t, ap, sn in batch))
         descs = self._desc_cache.get(key)
         if descs is None:
@@ -312,15 +330,22 @@ class SmartFP(CompressionAlgorithmBase):
         params = self._params(all_positive=False, offset=first)
         total = sum(t.numel() for _, t, _, _ in batch)
         need = lib.smaq_multi_workspace_bytes(len(batch), total)
-        ws = self._multi_ws.get(device)
+        stream = N.stream_ptr(device)
+        ws_key = (device, stream)
+        ws = self._multi_ws.get(ws_key)
         if ws is None or ws.numel() < need:  # grow-only scratch; calls on one stream are ordered
-            ws = self._multi_ws[device] = torch.empty(need, dtype=torch.uint8, device=device)
+            ws = self._multi_ws[ws_key] = torch.empty(need, dtype=torch.uint8, device=device)
+        ms = None
+        if stats_out is not None:  # parity tests: the (mean, std) each tensor was quantised with
+            ms = torch.zeros(len(batch), 2, dtype=torch.float32, device=device)
+            for j, (i, _, _, _) in enumerate(batch):
+                stats_out[i] = ms[j]
         N.check(
             lib.smaq_roundtrip_multi(N.ptr(descs), len(batch), max(t.numel() for _, t, _, _ in batch), total,
-                                     C.byref(params), int(hp.min_size), N.ptr(ws), ws.numel(), N.stream_ptr(device)),
+                                     C.byref(params), int(hp.min_size), N.ptr(ws), ws.numel(),
+                                     None if ms is None else N.ptr(ms), stream),
             "smaq_roundtrip_multi",
         )
-        return results
 
     # -- materialised stream: encode / decode ---------------------------------------------------
     @torch.no_grad()
@@ -330,6 +355,9 @@ class SmartFP(CompressionAlgorithmBase):
         from .packed import PackedSmaq, packed_layout
 
         N.require_cuda_f32(data, "SmartFP.encode")
+        if N.wrong_device(data):
+            with N.on_device_of(data):
+                return self.encode(data, mean_std, **extra)
         lib = N.load()
         hp = self.hparams
         src = data if data.is_contiguous() else data.contiguous()
@@ -355,6 +383,9 @@ class SmartFP(CompressionAlgorithmBase):
 
     @torch.no_grad()
     def decode(self, packed, all_positive: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if N.wrong_device(packed.buffer):
+            with N.on_device_of(packed.buffer):
+                return self.decode(packed, all_positive, out)
         lib = N.load()
         lay = packed.layout
         y = out if out is not None else torch.empty(packed.shape, dtype=torch.float32, device=packed.buffer.device)
@@ -365,21 +396,23 @@ class SmartFP(CompressionAlgorithmBase):
         )
         return y
 
-    # -- --use_batch_norm (smart.py:136-149,174-179): off by default, not on the hot path --------
-    def _bn_affine_params(self, stats):
+    # -- --use_batch_norm (smart.py:136-149,174-179): off by default -----------------------------
+    def _bn_affine_params(self, x, stats):
+        """(gamma, beta, channels, inner) for ``smaq_roundtrip_bn``.  The reference broadcasts gamma / beta over the
+        LAST axis of ``x.permute(0, 3, 2, 1)``, i.e. over axis 1 of a 4-D map: per channel of an NCHW tensor;
+        with --bn_scalar_params both are replaced by their means (smart.py:140-142)."""
         gamma, beta = stats
+        if x.dim() != 4:
+            raise RuntimeError(f"--use_batch_norm expects a 4-D (N, C, H, W) feature map, got {tuple(x.shape)} "
+                               "(the reference's permute(0, 3, 2, 1) raises on anything else)")
+        gamma = gamma.detach().to(device=x.device, dtype=torch.float32)
+        beta = beta.detach().to(device=x.device, dtype=torch.float32)
         if self.hparams.bn_scalar_params:
-            gamma, beta = gamma.mean(), beta.mean()
-        return gamma, beta
-
-    def _bn_unaffine(self, x, stats):
-        gamma, beta = self._bn_affine_params(stats)
-        # the reference broadcasts over the LAST axis of an (N, W, H, C) view (permute(0,3,2,1))
-        return ((x.permute(0, 3, 2, 1).clone() - beta) / gamma).permute(0, 3, 2, 1).clone()
-
-    def _bn_reaffine(self, y, stats):
-        gamma, beta = self._bn_affine_params(stats)
-        return ((y.permute(0, 3, 2, 1).clone() * gamma) + beta).permute(0, 3, 2, 1).clone()
+            return gamma.mean().reshape(1), beta.mean().reshape(1), 1, x.numel()
+        channels = x.shape[1]
+        if gamma.numel() != channels or beta.numel() != channels:
+            raise RuntimeError(f"batch_norm_stats of {gamma.numel()} / {beta.numel()} entries for {channels} channels")
+        return gamma.contiguous().view(-1), beta.contiguous().view(-1), channels, x.shape[2] * x.shape[3]
 
     # -- size accounting (smart.py:184-187) ------------------------------------------------------
     def _compressed_bits(self, flat, mean_std, params) -> float:

@@ -34,9 +34,11 @@ class ResidualBlock(nn.Module):
                                             nn.BatchNorm2d(cout))
 
     def forward(self, x):
-        skip = x if self.downsample is None else self.downsample(x)
         y = self.relu(self.bn1(self.conv1(x)))
         y = self.bn2(self.conv2(y))
+        # the projection runs AFTER the residual branch, as in the reference (pytorch/resnet.py:59-74): the order
+        # of the hooked calls is part of the boundary (tests/test_hooks_vs_reference.py)
+        skip = x if self.downsample is None else self.downsample(x)
         return self.relu(y + skip)
 
 

@@ -46,19 +46,19 @@ def stats_range(x):
     return out
 
 
-def stats_sampled(x, idx):
+def stats_sampled(x, idx, range_std=False):
     lib = N.load()
     out = torch.empty(2, dtype=torch.float32, device=x.device)
     idx = idx.to(x.device, torch.int64).contiguous()
-    N.check(lib.smaq_stats_sampled(x.data_ptr(), x.numel(), idx.data_ptr(), idx.numel(), out.data_ptr(),
+    N.check(lib.smaq_stats_sampled(x.data_ptr(), x.numel(), idx.data_ptr(), idx.numel(), int(range_std), out.data_ptr(),
                                    N.stream_ptr(x.device)), "stats_sampled")
     return out
 
 
-def stats_sampled_draw(x, k, seed, offset=0):
+def stats_sampled_draw(x, k, seed, offset=0, range_std=False):
     lib = N.load()
     out = torch.empty(2, dtype=torch.float32, device=x.device)
-    N.check(lib.smaq_stats_sampled_draw(x.data_ptr(), x.numel(), k, seed, offset, out.data_ptr(),
+    N.check(lib.smaq_stats_sampled_draw(x.data_ptr(), x.numel(), k, int(range_std), seed, offset, out.data_ptr(),
                                         N.stream_ptr(x.device)), "stats_sampled_draw")
     return out
 

@@ -23,6 +23,10 @@ def parse_argv(argv: str):
             kw["use_sample_stats"] = True
         elif t == "--use_range_std_dev":
             kw["use_range_std_dev"] = True
+        elif t == "--use_batch_norm":
+            kw["use_batch_norm"] = True
+        elif t == "--bn_scalar_params":
+            kw["bn_scalar_params"] = True
         elif t in ("--num_samples", "--num_bits_main", "--num_bits_outlier", "--min_size"):
             kw[t[2:]] = int(toks[i + 1])
             i += 1
@@ -46,6 +50,8 @@ def load_golden():
             c[f] = torch.from_numpy(z[key].copy()) if key in z.files else None
         c["argv"] = str(z[f"{n}/argv"])
         c["kwargs"] = ast.literal_eval(str(z[f"{n}/kwargs"]))
+        if f"{n}/gamma" in z.files:  # --use_batch_norm cases: the BatchNorm2d affine parameters
+            c["kwargs"]["batch_norm_stats"] = (torch.from_numpy(z[f"{n}/gamma"].copy()), torch.from_numpy(z[f"{n}/beta"].copy()))
         c["precision"] = int(z[f"{n}/precision"])
         c["same_object"] = bool(z[f"{n}/same_object"])
         cfg = parse_argv(c["argv"])
@@ -53,6 +59,11 @@ def load_golden():
         c["cfg"] = cfg
         cases[n] = c
     return cases
+
+
+def uses_bn(case) -> bool:
+    """The case exercises --use_batch_norm (flag AND the layer's gamma / beta present, smart.py:121)."""
+    return bool(case["cfg"].use_batch_norm and case["kwargs"].get("batch_norm_stats") is not None)
 
 
 def bits(t: torch.Tensor) -> torch.Tensor:

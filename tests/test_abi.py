@@ -31,7 +31,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared_functions():
         assert hasattr(raw, name), f"{name} declared in smaq_b200.h but not exported"
         assert name in _native.EXPORTED_SYMBOLS, f"{name} has no ctypes signature"
-    assert lib.smaq_b200_abi_version() == _native.ABI_VERSION == 3
+    assert lib.smaq_b200_abi_version() == _native.ABI_VERSION == 4
     assert set(_native.EXPORTED_SYMBOLS) <= set(declared_functions())
 
 
