@@ -204,10 +204,10 @@ class Pipeline:
         self.stats_ws_bytes = self.lib.smaq_stats_workspace_bytes(n)
         self.stats_ws = torch.empty(self.stats_ws_bytes, dtype=torch.uint8, device=device)
         self.packed = torch.empty(self.lay.total_capacity_bytes, dtype=torch.uint8, device=device)
-        self.enc_ws = torch.empty(self.lay.workspace_bytes, dtype=torch.uint8, device=device)
+        self.enc_ws = torch.zeros(self.lay.workspace_bytes, dtype=torch.uint8, device=device)  # zeroed once; every call leaves it zero
         self.y = torch.empty(n, dtype=torch.float32, device=device)
-        # stats; encode = quantise+pack (its last CTA scans the per-group counts), placement of the extras; decode
-        self.launches_per_step = 4
+        # statistics; encode (one pass: quantise + pack); decode
+        self.launches_per_step = 3
         self.step_index = 0
 
     def stats(self, x):
@@ -475,7 +475,7 @@ def sweep(args, device, peak):
         params = fp._params(all_positive=False)
         lay = packed_layout(n, 6, 8)
         packed = torch.empty(lay.total_capacity_bytes, dtype=torch.uint8, device=device)
-        ws = torch.empty(lay.workspace_bytes, dtype=torch.uint8, device=device)
+        ws = torch.zeros(lay.workspace_bytes, dtype=torch.uint8, device=device)
         sws_b = lib.smaq_stats_workspace_bytes(n)
         sws = torch.empty(sws_b, dtype=torch.uint8, device=device)
         st = N.stream_ptr(device)

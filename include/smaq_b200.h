@@ -28,7 +28,8 @@ extern "C" {
 #endif
 
 #define SMAQ_B200_ABI_VERSION 4 /* 2: packed stream SQB2, count_saturated, smaq_compress, tensor_desc.stream; 3: smaq_float_quantize_multi;
-                                    4: smaq_roundtrip_bn, smaq_roundtrip_multi(mean_std_out), range_std in the sampled statistics */
+                                    4: smaq_roundtrip_bn, smaq_roundtrip_multi(mean_std_out), range_std in the sampled statistics,
+                                       packed stream SQB3 (one-pass encoder, smaq_encode_workspace_init) */
 
 typedef void* smaq_stream_t; /* cudaStream_t */
 
@@ -155,23 +156,24 @@ int smaq_roundtrip_multi(const smaq_tensor_desc* descs, int32_t count, int64_t m
 
 /* ---- packed SmaQ stream ------------------------------------------------------------------ */
 
-/* Byte offsets of the sections of one packed tensor (see DESIGN.md "Packed layout"). */
+/* Byte offsets of the sections of one packed tensor (stream "SQB3", DESIGN.md "Packed stream"). */
 typedef struct smaq_packed_layout {
   int64_t n;
   int32_t bits_main, bits_outlier;
   int64_t n_warp_tiles;    /* ceil(n / 1024) */
   int64_t n_cta_tiles;     /* ceil(n_warp_tiles / 8) */
   int64_t header_off, header_bytes;   /* smaq_packed_header */
-  int64_t table_off, table_bytes;     /* uint32 extras word offset per CTA tile (+1 sentinel) */
   int64_t planes_off, planes_bytes;   /* tag word + (bits_main-1) base words per lane, per warp tile */
-  int64_t extras_off, extras_capacity_bytes; /* dense (bits_outlier-bits_main) bits per outlier */
+  int64_t extras_off;                 /* (bits_outlier-bits_main) bits per outlier, dense inside a warp tile */
+  int64_t extras_stride_bytes;        /* warp tile t's segment starts at extras_off + t * extras_stride_bytes */
+  int64_t extras_capacity_bytes;
   int64_t total_capacity_bytes;       /* what the caller must allocate */
-  int64_t workspace_bytes;            /* scratch for smaq_encode */
+  int64_t workspace_bytes;            /* scratch for smaq_encode (64 bytes) */
 } smaq_packed_layout;
 
 /* First bytes of a packed buffer, written by smaq_encode on the device. */
 typedef struct smaq_packed_header {
-  uint32_t magic;            /* 'SQB2' */
+  uint32_t magic;            /* 'SQB3' */
   int32_t bits_main, bits_outlier;
   int32_t stochastic;
   int64_t n;
@@ -180,15 +182,18 @@ typedef struct smaq_packed_header {
   uint64_t n_outlier;        /* smart.py:184-187: compressed bits = 8*n_outlier + 6*(n-n_outlier) */
   uint64_t n_saturated;      /* scaled values the field width cannot hold, or NaN (H1); ~0 when
                                 not counted (smaq_codec_params.count_saturated == 0) */
-  uint64_t extras_words;     /* 32-bit words actually used in the extras section */
+  uint64_t extras_words;     /* 32-bit words actually used in the extras section (sum over the warp tiles) */
   uint64_t status;           /* 0 ok (reserved for failure codes) */
 } smaq_packed_header;
 
 int smaq_packed_layout_for(int64_t n, int32_t bits_main, int32_t bits_outlier, smaq_packed_layout* out);
 
 /* Quantise and pack — the materialised form of the code the reference only ever holds as an
- * fp32 value (smart.py:164-169).  Codes saturate at the field width.  ws must be
- * layout.workspace_bytes; it is cleared on `stream` by this call. */
+ * fp32 value (smart.py:164-169).  Codes saturate at the field width.  ONE kernel, one read of x.
+ * ws: layout.workspace_bytes of scratch (an arrival ticket and three counters), zeroed ONCE after allocation
+ * with smaq_encode_workspace_init; every call leaves it zero again, so no memset node is issued per call.
+ * Calls sharing a workspace must be ordered on one stream. */
+int smaq_encode_workspace_init(void* ws, size_t ws_bytes, smaq_stream_t stream);
 int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* probs,
                 const smaq_codec_params* params, void* packed, size_t packed_bytes, void* ws,
                 size_t ws_bytes, smaq_stream_t stream);

@@ -1,4 +1,4 @@
-"""CPU oracle for the PACKED SmaQ stream "SQB2" (TEST INFRASTRUCTURE ONLY).
+"""CPU oracle for the PACKED SmaQ stream "SQB3" (TEST INFRASTRUCTURE ONLY).
 
 The reference never materialises codes: SmartFP is fake quantisation (smart.py:154-172) and only
 *accounts* for a size of 6 bits per main element and 8 per outlier (smart.py:184-187).  The
@@ -20,7 +20,7 @@ Per element, with L = 2^(bits-2) - 1 the largest code magnitude its width holds
     base = U mod 2^pm    stored for every element at a fixed position (main: S in two's complement)
     ext  = U >> pm       xb bits, stored only for outliers, densely   (outlier: U is S, offset binary)
 so the stream holds exactly  n + pm*n + xb*n_out = bits_main*n_main + bits_outlier*n_out  bits
-(+ the per-tile table and word alignment, reported as overhead).
+(+ word alignment per warp tile, reported as overhead).
 
 Geometry (chosen so one warp reads its 1024 values as one 4 KB bulk copy and every lane packs its own
 32 values in registers with packed fp32 arithmetic):
@@ -34,10 +34,11 @@ Geometry (chosen so one warp reads its 1024 values as one 4 KB bulk copy and eve
     extras    : per warp tile, lanes in order, per lane its chunks in order (LSB-first); inside a
                 chunk the outliers' ext fields are concatenated with the FIRST outlier in the MOST
                 significant position (E = E * 2^xb + ext); the warp-tile segment is padded to a
-                whole uint32; warp-tile segments follow each other in tile order.
-    CTA tile  = 8 warp tiles; table[t] = first word of CTA tile t's first segment in the extras
-                section, table[n_cta_tiles] = total words (a warp finds its own segment by adding
-                the word counts of the warps before it, which follow from the tag words).
+                whole uint32 and starts at a FIXED place, word t * (1024 * xb / 32) of the extras section
+                for warp tile t: only its used words (their number follows from the tile's tag words) are
+                ever written or read, the rest of the stride is unspecified.  (Round 1's "SQB2" packed the
+                segments densely across tiles behind a per-CTA-tile table; that made the encoder two
+                passes — see DESIGN.md §3.)
 Elements past n (padding of the last tile) are main elements with S = 0.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this.
@@ -54,7 +55,7 @@ from .smaq import SmaqConfig, SmaqResult
 WARP_TILE = 1024
 WARPS_PER_CTA = 8
 CTA_TILE = WARP_TILE * WARPS_PER_CTA
-MAGIC = 0x32425153  # 'SQB2' little endian
+MAGIC = 0x33425153  # 'SQB3' little endian
 
 
 @dataclass
@@ -64,8 +65,8 @@ class Packed:
     mean: np.float32
     std_raw: np.float32
     planes: np.ndarray   # uint32 [n_warp_tiles, 1+pm, 32]
-    table: np.ndarray    # uint32 [n_cta_tiles + 1]
-    extras: np.ndarray   # uint32 [table[-1]]
+    extras: np.ndarray   # uint32 [n_warp_tiles, seg_words]; words past seg_used[t] are zero here, unspecified on the device
+    seg_used: np.ndarray  # int64 [n_warp_tiles] words of each segment that are part of the stream
     n_outlier: int
     n_saturated: int
 
@@ -76,8 +77,12 @@ class Packed:
         return c.num_bits_outlier * self.n_outlier + c.num_bits_main * (self.n - self.n_outlier)
 
     @property
+    def extras_words(self) -> int:
+        return int(self.seg_used.sum())
+
+    @property
     def stored_bits(self) -> int:
-        return 32 * (self.planes.size + self.table.size + self.extras.size)
+        return 32 * (self.planes.size + self.extras_words)
 
 
 def lane_order_index(n_padded: int) -> np.ndarray:
@@ -108,7 +113,7 @@ def stored_values(res: SmaqResult, cfg: SmaqConfig):
     n_sat = int((isn | (c.abs() > lim)).sum())
     cc = torch.where(isn, torch.zeros_like(c), torch.maximum(torch.minimum(c, lim), -lim))
     if cfg.stochastic_rounding:
-        code = round_stochastic(cc, res.extras["probs"].reshape(-1))
+        code = round_stochastic(cc, res.extras["probs"].reshape(-1), res.extras.get("rng_rule", False))
     else:
         code = cc.trunc()
     # where nothing was clipped this IS the reference's code (pinned), elsewhere its clamp
@@ -132,7 +137,6 @@ def pack(res: SmaqResult, cfg: SmaqConfig) -> Packed:
     U = (S + (1 << (po - 1))).astype(np.uint64)
 
     n_wt = -(-n // WARP_TILE)
-    n_ct = -(-n_wt // WARPS_PER_CTA)
     n_pad = n_wt * WARP_TILE
     upad = np.full(n_pad, 1 << (po - 1), dtype=np.uint64)   # padding: main, S = 0
     tag = np.zeros(n_pad, dtype=bool)
@@ -146,39 +150,37 @@ def pack(res: SmaqResult, cfg: SmaqConfig) -> Packed:
     weights = (np.uint64(1) << np.arange(32, dtype=np.uint64))
     planes[:, 0, :] = (tag_l.astype(np.uint64) * weights).sum(axis=2).astype(np.uint32)
     base = u_l & np.uint64((1 << pm) - 1)
-    # scatter the 32 pm-bit fields of each lane into its 32*pm-bit string
-    bits = np.zeros((n_wt, 32, 32 * pm), dtype=np.uint64)
+    # the 32 pm-bit fields of each lane go into its 32*pm-bit string (pm words, LSB-first)
+    words = np.zeros((n_wt, 32, pm + 1), dtype=np.uint64)
     pos = field_bit_positions(pm)
-    for b in range(pm):
-        bits[:, :, pos + b] = (base >> np.uint64(b)) & np.uint64(1)
-    words = (bits.reshape(n_wt, 32, pm, 32) * weights).sum(axis=3).astype(np.uint32)
-    planes[:, 1:, :] = np.transpose(words, (0, 2, 1))
+    for i in range(32):
+        wi, sh = int(pos[i]) >> 5, int(pos[i]) & 31
+        v = base[:, :, i] << np.uint64(sh)
+        words[:, :, wi] |= v & np.uint64(0xFFFFFFFF)
+        words[:, :, wi + 1] |= v >> np.uint64(32)
+    assert not words[:, :, pm].any()
+    planes[:, 1:, :] = np.transpose(words[:, :, :pm].astype(np.uint32), (0, 2, 1))
 
-    # extras: one word-aligned segment per warp tile
-    ext = (u_l >> np.uint64(pm))
-    seg_words = np.zeros(n_ct * WARPS_PER_CTA, dtype=np.int64)
-    chunks = []
-    for w in range(n_wt):
-        bl = []
-        if xb:
-            for l in range(32):
-                for k in range(4):
-                    sl = slice(8 * k, 8 * k + 8)
-                    e = ext[w, l, sl][tag_l[w, l, sl]]
-                    # first outlier most significant: LSB-first bit list = reversed field order
-                    for v in e[::-1]:
-                        bl.extend(((int(v) >> t) & 1) for t in range(xb))
-        nbits = len(bl)
-        nwords = -(-nbits // 32)
-        seg_words[w] = nwords
-        if nwords:
-            b = np.array(bl + [0] * (nwords * 32 - nbits), dtype=np.uint64)
-            chunks.append((b.reshape(nwords, 32) * weights).sum(axis=1).astype(np.uint32))
-    table = np.zeros(n_ct + 1, dtype=np.uint32)
-    table[1:] = np.cumsum(seg_words.reshape(n_ct, WARPS_PER_CTA).sum(axis=1))
-    extras = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.uint32)
+    # extras: one word-aligned segment per warp tile, at a fixed stride
+    seg_w = WARP_TILE * xb // 32
+    extras = np.zeros((n_wt, max(seg_w, 1)), dtype=np.uint32)
+    seg_used = np.zeros(n_wt, dtype=np.int64)
+    if xb:
+        t4 = tag_l.reshape(n_wt, 32, 4, 8)
+        per_chunk = t4.sum(axis=3).reshape(n_wt, 128)                       # outliers per (lane, chunk), stream order
+        before = np.cumsum(per_chunk, axis=1) - per_chunk                    # ... in the chunks before this one
+        after = np.flip(np.cumsum(np.flip(t4, axis=3), axis=3), axis=3) - t4  # ... after this element in its chunk
+        slot = (before.reshape(n_wt, 32, 4, 1) + after).reshape(n_wt, 32, 32)  # first outlier of a chunk: highest slot
+        ext = (u_l >> np.uint64(pm)).astype(np.int64)
+        w_idx, l_idx, i_idx = np.nonzero(tag_l)
+        bitpos = slot[w_idx, l_idx, i_idx] * xb
+        val = ext[w_idx, l_idx, i_idx]
+        for t in range(xb):
+            bp = bitpos + t
+            np.bitwise_or.at(extras, (w_idx, bp >> 5), (((val >> t) & 1) << (bp & 31)).astype(np.uint32))
+        seg_used = -(-(tag_l.reshape(n_wt, -1).sum(axis=1) * xb) // 32)
     return Packed(n=n, cfg=cfg, mean=np.float32(res.mean), std_raw=np.float32(res.std), planes=planes,
-                  table=table, extras=extras, n_outlier=int(outlier.sum()), n_saturated=n_sat)
+                  extras=extras, seg_used=seg_used.astype(np.int64), n_outlier=int(outlier.sum()), n_saturated=n_sat)
 
 
 def unpack_values(p: Packed):
@@ -190,33 +192,30 @@ def unpack_values(p: Packed):
     n_pad = n_wt * WARP_TILE
     shifts = np.arange(32, dtype=np.uint32)
     tag_l = ((p.planes[:, 0, :, None] >> shifts) & 1).astype(bool)          # [w, l, i]
-    words = np.transpose(p.planes[:, 1:, :], (0, 2, 1))                      # [w, l, pm]
-    bits = ((words[..., None] >> shifts) & 1).reshape(n_wt, 32, 32 * pm).astype(np.uint64)
+    words = np.transpose(p.planes[:, 1:, :], (0, 2, 1)).astype(np.uint64)    # [w, l, pm]
+    words = np.concatenate([words, np.zeros((n_wt, 32, 1), dtype=np.uint64)], axis=2)
     pos = field_bit_positions(pm)
     base = np.zeros((n_wt, 32, 32), dtype=np.uint64)
-    for b in range(pm):
-        base |= bits[:, :, pos + b] << np.uint64(b)
+    for i in range(32):
+        wi, sh = int(pos[i]) >> 5, int(pos[i]) & 31
+        two = words[:, :, wi] | (words[:, :, wi + 1] << np.uint64(32))
+        base[:, :, i] = (two >> np.uint64(sh)) & np.uint64((1 << pm) - 1)
     ext = np.zeros((n_wt, 32, 32), dtype=np.uint64)
-    word = 0
-    for w in range(n_wt):
-        k_out = int(tag_l[w].sum())
-        nwords = -(-(k_out * xb) // 32)
-        if w % WARPS_PER_CTA == 0:
-            assert word == int(p.table[w // WARPS_PER_CTA]), "table does not match the tag words"
-        if k_out and xb:
-            seg = p.extras[word: word + nwords]
-            sb = ((seg[:, None] >> shifts) & 1).reshape(-1).astype(np.uint64)
-            at = 0
-            for l in range(32):
-                for k in range(4):
-                    idx = np.nonzero(tag_l[w, l, 8 * k: 8 * k + 8])[0] + 8 * k
-                    for i in idx[::-1]:   # LSB-first in the stream = last outlier of the chunk first
-                        v = 0
-                        for t in range(xb):
-                            v |= int(sb[at + t]) << t
-                        ext[w, l, i] = v
-                        at += xb
-        word += nwords
+    if xb:
+        t4 = tag_l.reshape(n_wt, 32, 4, 8)
+        per_chunk = t4.sum(axis=3).reshape(n_wt, 128)
+        before = np.cumsum(per_chunk, axis=1) - per_chunk
+        after = np.flip(np.cumsum(np.flip(t4, axis=3), axis=3), axis=3) - t4
+        slot = (before.reshape(n_wt, 32, 4, 1) + after).reshape(n_wt, 32, 32)
+        used = -(-(tag_l.reshape(n_wt, -1).sum(axis=1) * xb) // 32)
+        assert np.array_equal(used, p.seg_used), "segment sizes do not match the tag words"
+        w_idx, l_idx, i_idx = np.nonzero(tag_l)
+        bitpos = slot[w_idx, l_idx, i_idx] * xb
+        v = np.zeros(w_idx.shape, dtype=np.uint64)
+        for t in range(xb):
+            bp = bitpos + t
+            v |= ((p.extras[w_idx, bp >> 5].astype(np.uint64) >> (bp & 31).astype(np.uint64)) & np.uint64(1)) << np.uint64(t)
+        ext[w_idx, l_idx, i_idx] = v
     u_l = (base | (ext << np.uint64(pm))).reshape(-1)
     tflat = tag_l.reshape(-1)
     perm = lane_order_index(n_pad).reshape(-1)

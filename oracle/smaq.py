@@ -99,10 +99,17 @@ def full_mean_std(data: torch.Tensor, cfg: SmaqConfig):
     return data.mean(), std_of(data, cfg)
 
 
-def round_stochastic(c: torch.Tensor, probs: torch.Tensor) -> torch.Tensor:
-    """smart.py:93-98 with ``probs`` supplied by the caller instead of rand_like."""
+def round_stochastic(c: torch.Tensor, probs: torch.Tensor, rng_rule: bool = False) -> torch.Tensor:
+    """smart.py:93-98 with ``probs`` supplied by the caller instead of rand_like.
+
+    ``rng_rule`` (NOT in the reference): the rule the CUDA kernels apply to their OWN random numbers
+    (oracle/rng.py): floor(c) + [frac >= p].  It is the reference's expression except where
+    |frac - p| <= 2^-25, i.e. where ``(frac - p) + 0.5`` lands on the tie of round-half-even.  With
+    caller-supplied ``probs`` (parity mode) the kernels evaluate the reference's expression itself."""
     floored = c.floor()
     fractions = c - floored
+    if rng_rule:
+        return floored + (fractions >= probs).to(c.dtype)
     return floored + torch.relu((fractions - probs) + 0.5).round()
 
 
@@ -118,6 +125,7 @@ def smaq_roundtrip(
     all_positive: bool = False,
     saturate: bool = False,
     batch_norm_stats=None,
+    rng_rule: bool = False,
 ) -> SmaqResult:
     """The whole fake-quantisation call, smart.py:121-190.
 
@@ -168,7 +176,7 @@ def smaq_roundtrip(
     c = (z + scalars) * ranges  # smart.py:164
     if cfg.stochastic_rounding:  # smart.py:166-169
         assert probs is not None, "stochastic rounding needs explicit probs"
-        code = round_stochastic(c, probs)
+        code = round_stochastic(c, probs, rng_rule)
     else:
         code = c.trunc()
 
@@ -184,7 +192,7 @@ def smaq_roundtrip(
     if all_positive:  # smart.py:181-182
         y = y.clamp_min(0.0)
 
-    return SmaqResult(y=y, mean=mean, std=std_raw, hi=hi, lo=lo, code=code, extras={"z": z, "c": c, "probs": probs})
+    return SmaqResult(y=y, mean=mean, std=std_raw, hi=hi, lo=lo, code=code, extras={"z": z, "c": c, "probs": probs, "rng_rule": rng_rule})
 
 
 def compressed_bits(res: SmaqResult, cfg: SmaqConfig) -> int:

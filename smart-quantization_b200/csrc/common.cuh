@@ -148,6 +148,36 @@ __host__ __device__ __forceinline__ uint32_t philox_word(const uint4& q, int j) 
   return j == 0 ? q.x : j == 1 ? q.y : j == 2 ? q.z : q.w;
 }
 
+// ---- SmaQ's in-kernel uniforms: 16 random bits per element, ONE Philox4x32-7 call per 16 elements -------------
+// Elements are taken in groups of eight (group g = elements 8g .. 8g+7: one 256-bit access, one "chunk" of the
+// packed encoder).  Groups g and g ^ 32 share a call — in the packed encoder's warp tile these are chunks k and k+1
+// of the SAME lane, so a lane draws twice per 32 elements instead of four times (the Philox calls were 19 % of the
+// encoder's time).  Word q of the call serves elements 2q and 2q+1 of both groups; a 32-bit word
+// b3 b2 b1 b0 holds four 16-bit windows at byte stride, (b1 b0), (b2 b1), (b3 b2), (b0 b3):
+//     group with bit 5 clear: element 2q -> (b1 b0), element 2q+1 -> (b3 b2)      [the two disjoint halves]
+//     group with bit 5 set  : element 2q -> (b2 b1), element 2q+1 -> (b0 b3)      [the two windows in between]
+// Inside a group the eight values are disjoint bit fields of the call (independent); each value is exactly
+// uniform on 0..65535; a value of the second group shares one byte with each of two values of the first group,
+// 256 elements away (its low byte is the high byte of one of them: a dependence of order 2^-8 between two
+// rounding decisions).  The number depends on (seed, stream offset, element index) only, never on the launch
+// geometry, and every kernel (round trip, small / multi-tensor, packed encoder) draws the same one for the same
+// element.  oracle/rng.py restates the scheme in numpy; the parity tests feed its numbers to the CPU oracle.
+__host__ __device__ __forceinline__ uint64_t rnd16_call_index(uint64_t g) { return ((g >> 6) << 5) | (g & 31u); }
+__host__ __device__ __forceinline__ uint32_t rnd16_sub(uint64_t g) { return (uint32_t)(g >> 5) & 1u; }
+__host__ __device__ __forceinline__ uint4 rnd16_call(const PhiloxKeys& K, uint64_t g, uint64_t offset) {
+  return philox_group(K, rnd16_call_index(g), offset);
+}
+// the 16-bit value of element j (0..7) of a group whose call returned r
+__host__ __device__ __forceinline__ uint32_t rnd16_k(const uint4& r, uint32_t sub, int j) {
+  const uint32_t w = philox_word(r, j >> 1);
+  const uint32_t t = 2u * (uint32_t)(j & 1) + sub;              // window: bytes t and (t + 1) & 3
+  return ((w >> (8u * t)) & 0xFFu) | (((w >> (8u * ((t + 1u) & 3u))) & 0xFFu) << 8);
+}
+// PRMT selectors that build the float 2^e + k * 2^(e-23) from a word and a constant 0xEE000000 (exponent byte):
+// result bytes = [low byte of k, high byte of k, 0x00, exponent byte]
+__host__ __device__ __forceinline__ uint32_t rnd16_sel_even(uint32_t sub) { return sub ? 0x7621u : 0x7610u; }
+__host__ __device__ __forceinline__ uint32_t rnd16_sel_odd(uint32_t sub) { return sub ? 0x7603u : 0x7632u; }
+
 // ---- warp helpers --------------------------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }

@@ -3,9 +3,8 @@
 //
 // The reference only ever holds the code as an fp32 value (smart_compress/compress/smart.py:164-169)
 // and accounts for 6 bits per main element and 8 per outlier (smart.py:184-187).  The stream
-// written here has exactly that size plus a 4-byte table entry per 8192 elements and at most 31
-// padding bits per 1024 elements; its layout ("SQB2") is specified in DESIGN.md and restated
-// executable in oracle/pack.py.
+// written here holds exactly those bits plus at most 31 padding bits per 1024 elements; its layout
+// ("SQB3") is specified in DESIGN.md and restated executable in oracle/pack.py.
 //
 // Stored value of an element.  With L = 2^(bits-2)-1 the largest code magnitude the width holds,
 //   S = clamp(code, -L, L) - [z < 0]      (z < 0 implies code <= 0, z >= 0 implies code >= 0, so S is
@@ -32,10 +31,14 @@
 //   * rare elements leave the hot path per chunk: |z| beyond what an outlier code can hold takes a
 //     clamp-and-count detour (the H1 rule), a zero/denormal/NaN quotient re-runs the chunk with
 //     IEEE division (generic_chunk);
-//   * the variable part — XB extra bits per OUTLIER — is placed inside the warp tile by a shuffle
-//     prefix scan of the per-lane bit counts and shared-memory atomicOr, then in the tensor by
-//     reduce-then-scan over two launches (no block ever waits for another).  Placement is
-//     deterministic: the stream is byte-identical run to run;
+//   * the variable part — XB extra bits per OUTLIER — is dense inside the warp tile (shuffle prefix
+//     scan of the per-lane bit counts, shared-memory atomicOr) and the warp tile's segment sits at a
+//     FIXED stride in the extras section (kWarpTile * XB bits): nothing in the tensor depends on
+//     another warp's outlier count, so the encoder is ONE pass with no cross-CTA step — round 1's
+//     stream was dense across tiles, which cost a parked copy of every segment, a scan over group
+//     totals and a second (placement) launch: 15 % of the encoder.  Only the used
+//     words of a segment are written or read; placement is a pure function of the input, the stream
+//     is byte-identical run to run;
 //   * the decoder is a table lookup: every (class, U) pair has ONE decoded value per tensor, so
 //     each CTA evaluates the reference's inverse (smart.py:171-172,181-182, IEEE division) for the
 //     2^PM + 2^(PM+XB) possible fields into shared memory and the element loop is bit-field
@@ -43,6 +46,8 @@
 //
 // HBM roofline (6/8 bits, fraction f of outliers): encode reads 4 B and writes (6 + 2f)/8 B per
 // element; decode the reverse.  f = 0.165 on the benchmark input -> 4.79 B per element each way.
+#include <atomic>
+
 #include "params.cuh"
 
 namespace smaq {
@@ -51,7 +56,7 @@ constexpr int kWarpTile = 1024;
 constexpr int kWarpsPerCta = 8;
 constexpr int kCtaTile = kWarpTile * kWarpsPerCta;
 constexpr int kPackThreads = 32 * kWarpsPerCta;
-constexpr uint32_t kMagic = 0x32425153u;  // 'SQB2'
+constexpr uint32_t kMagic = 0x33425153u;  // 'SQB3'
 
 // 32-bit words of extras a warp tile can need
 __host__ __device__ constexpr int seg_words(int xb) { return xb == 0 ? 1 : kWarpTile * xb / 32; }
@@ -70,7 +75,7 @@ struct ChunkBits {
 
 // ---- generic chunk: any width, IEEE division, padding, NaN — the literal operator sequence ------
 // (also the re-run of a hot chunk that met a zero / denormal / NaN quotient).  Out of line.
-template <int PM, int XB, bool kStochastic>
+template <int PM, int XB, bool kStochastic, bool kRng>
 __device__ __forceinline__ void generic_chunk(const float* __restrict__ xv, const float* __restrict__ pv, int nvalid,
                                            const Scalars& s, ChunkBits& out, uint32_t& n_sat) {
   uint32_t h0 = 0, h1 = 0, tag = 0, ext = 0, sat = 0;
@@ -91,7 +96,9 @@ __device__ __forceinline__ void generic_chunk(const float* __restrict__ xv, cons
       sat += (isn || fabsf(c) > lim) ? 1u : 0u;                      // H1: what the field cannot hold
       c = isn ? 0.0f : fminf(fmaxf(c, -lim), lim);                   // clamping c == clamping the rounded code
       float code;
-      if (kStochastic) {                                             // :93-98
+      if (kStochastic && kRng) {                                     // in-kernel uniforms: floor(c + q), exactly
+        code = floorf(add_rd(c, pv[j]));
+      } else if (kStochastic) {                                      // :93-98
         const float f = floorf(c);
         const float frac = sub_rn(c, f);
         const float u = max_nan(add_rn(sub_rn(frac, pv[j]), 0.5f), 0.0f);
@@ -128,6 +135,7 @@ struct Hot {
   float z_lo, z_hi;      // outside [z_lo, z_hi] a chunk leaves the hot path
   float lim_out;         // L_out
   float off_mid;         // 2^(PO-1) - 0.5: U = code + off_mid +- 0.5
+  float cq_mid;          // off_mid - 128 + 2^-17: the offset folded into the in-kernel uniform (hot_chunk)
 };
 
 __device__ __forceinline__ Hot make_hot(const Scalars& s) {
@@ -144,6 +152,7 @@ __device__ __forceinline__ Hot make_hot(const Scalars& s) {
   h.z_lo = 9.094947017729282e-13f;  // 2^-40
   h.lim_out = s.lim_out;
   h.off_mid = s.lim_out + 0.5f;  // L_out + 1 == 2^(PO-1)
+  h.cq_mid = (s.lim_out + 0.5f) - 127.99999237060546875f;  // exact for PO == 7: -64.5 + 2^-17 has 24 significant bits
   // the largest |z| whose outlier code needs no clamp: fl(z * ro - K) <= L_out
   float zh = true_div(add_rn(s.lim_out, K), s.range_out.b);
   for (int it = 0; it < 4 && __fmaf_rn(zh, s.range_out.b, -K) > s.lim_out; ++it) zh = from_bits(bits_of(zh) - 1u);
@@ -180,11 +189,14 @@ __device__ __forceinline__ f32x2 fma2_rm(f32x2 a, f32x2 b, f32x2 c) {  // round 
 #endif
 }
 
-// Eight elements: v0 | v1 in memory order; uniforms either explicit (p0 | p1) or the four Philox
-// words `rnd` (16 bits per element).  Returns false when the chunk must be re-run by generic_chunk.
-template <bool kStochastic, bool kHasProbs, bool kCountSat>
-__device__ __forceinline__ bool hot_chunk(const float4& v0, const float4& v1, const float4& p0, const float4& p1,
-                                          const uint4& rnd, const Hot& h, ChunkBits& out, f32x2& sat2) {
+// Eight elements: v0 | v1 in memory order; uniforms either explicit (p0 | p1) or the four Philox words `rnd`
+// (16 bits per element, window set kSub: common.cuh rnd16_*).  `amin` returns the smallest |quotient| (NaN if any
+// is): below Hot::z_lo the three-instruction division is not trusted and the caller re-runs the lane's tile through
+// slow_chunk — checked once per TILE, so the four chunks of a lane are one straight-line block.
+template <bool kStochastic, bool kHasProbs, bool kCountSat, int kSub>
+__device__ __forceinline__ void hot_chunk(const float4& v0, const float4& v1, const float4& p0, const float4& p1,
+                                          const uint4& rnd, const Hot& h, ChunkBits& out, f32x2& sat2, float& amin) {
+  constexpr bool kRng = kStochastic && !kHasProbs;
   const f32x2 x[4] = {pair(v0.x, v0.y), pair(v0.z, v0.w), pair(v1.x, v1.y), pair(v1.z, v1.w)};
   const f32x2 nmean2 = splat(-h.mean), nb2 = splat(h.nb), r2 = splat(h.r);
   f32x2 z[4];
@@ -195,10 +207,8 @@ __device__ __forceinline__ bool hot_chunk(const float4& v0, const float4& v1, co
     const f32x2 e = fma2(qq, nb2, d);
     z[q] = fma2(e, r2, qq);
   }
-  // a zero, denormal-range or NaN quotient leaves the straight-line path
   const float m1 = min3_nan_abs(z[0].x, z[0].y, z[1].x), m2 = min3_nan_abs(z[1].y, z[2].x, z[2].y);
-  const float amin = min_nan(min3_nan_abs(z[3].x, z[3].y, m1), m2);  // NaN if any quotient is
-  if (!(amin >= h.z_lo)) return false;
+  amin = min_nan(min3_nan_abs(z[3].x, z[3].y, m1), m2);  // NaN if any quotient is
   // class, scaled value and stored offset of each element                              :155-164
   bool P[8];
   float c[8];
@@ -210,7 +220,8 @@ __device__ __forceinline__ bool hot_chunk(const float4& v0, const float4& v1, co
     // outlier: (z -+ t) * range_outlier == fma(z, ro, -+K), exactly (see make_hot)
     const float k0 = from_bits((~bits_of(z[q].x) & 0x80000000u) | h.kbits);
     const float k1 = from_bits((~bits_of(z[q].y) & 0x80000000u) | h.kbits);
-    off[q] = fma2(pair(k0, k1), splat(h.nhk), splat(h.off_mid));  // 2^(PO-1) - [z < 0]
+    // 2^(PO-1) - [z < 0]; with the in-kernel uniforms the same minus 128 - 2^-17 (see below)
+    off[q] = fma2(pair(k0, k1), splat(h.nhk), splat(kRng ? h.cq_mid : h.off_mid));
     P[2 * q] = fabsf(z[q].x) > h.thr;
     P[2 * q + 1] = fabsf(z[q].y) > h.thr;
     c[2 * q] = P[2 * q] ? __fmaf_rn(z[q].x, h.ro, k0) : cm.x;
@@ -232,31 +243,32 @@ __device__ __forceinline__ bool hot_chunk(const float4& v0, const float4& v1, co
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const f32x2 c2 = pair(c[2 * q], c[2 * q + 1]);
-    f32x2 U;
-    if (kStochastic) {
+    f32x2 U, W;
+    if (kRng) {
+      // U = floor(c + q) + off with q = (k + 1/2) / 2^16 from 16 random bits k, as ONE round-down addition and a
+      // floor: the Philox bytes become 128 + k / 2^16 by PRMT (exponent byte 0x43), off[] already carries
+      // off - 128 + 2^-17, so kf + off[] == off + q exactly (24 significant bits), and
+      // floor(RD(c + (off + q))) == floor(c + q) + off because the floor is representable.
+      const uint32_t w = q == 0 ? rnd.x : q == 1 ? rnd.y : q == 2 ? rnd.z : rnd.w;
+      constexpr uint32_t kSelE = kSub ? 0x7621u : 0x7610u, kSelO = kSub ? 0x7603u : 0x7632u;
+      const f32x2 kf = pair(from_bits(__byte_perm(w, 0x43000000u, kSelE)), from_bits(__byte_perm(w, 0x43000000u, kSelO)));
+      W = add2_rd(c2, add2(kf, off[q]));
+      U = pair(floorf(W.x), floorf(W.y));
+    } else if (kStochastic) {
       const f32x2 f = pair(floorf(c2.x), floorf(c2.y));
       const f32x2 frac = add2(c2, neg2(f));
-      f32x2 r;
-      if (kHasProbs) {
-        const float pa = q == 0 ? p0.x : q == 1 ? p0.z : q == 2 ? p1.x : p1.z;
-        const float pb = q == 0 ? p0.y : q == 1 ? p0.w : q == 2 ? p1.y : p1.w;
-        f32x2 u = add2(add2(frac, pair(-pa, -pb)), splat(0.5f));
-        u = pair(fmaxf(u.x, 0.0f), fmaxf(u.y, 0.0f));                                   // relu
-        r = add2(add2(u, splat(8388608.0f)), splat(-8388608.0f));                       // rint, 0 <= u < 2
-      } else {
-        // p = (k + 1/2) / 2^16 from 16 random bits k, built without a conversion: 2^23 + k by byte
-        // permute, then one FMA.  rint(relu((frac - p) + 0.5)) == 1  <=>  frac - p > 2^-25  (p > 0)
-        const uint32_t w = q == 0 ? rnd.x : q == 1 ? rnd.y : q == 2 ? rnd.z : rnd.w;
-        const f32x2 kf = pair(from_bits(__byte_perm(w, 0x4B000000u, 0x7610)), from_bits(__byte_perm(w, 0x4B000000u, 0x7632)));
-        const f32x2 p = fma2(kf, splat(1.52587890625e-05f), splat(-127.99999237060546875f));
-        const f32x2 t = add2(frac, neg2(p));
-        r = pair(t.x > 2.98023223876953125e-08f ? 1.0f : 0.0f, t.y > 2.98023223876953125e-08f ? 1.0f : 0.0f);
-      }
+      const float pa = q == 0 ? p0.x : q == 1 ? p0.z : q == 2 ? p1.x : p1.z;
+      const float pb = q == 0 ? p0.y : q == 1 ? p0.w : q == 2 ? p1.y : p1.w;
+      f32x2 u = add2(add2(frac, pair(-pa, -pb)), splat(0.5f));
+      u = pair(fmaxf(u.x, 0.0f), fmaxf(u.y, 0.0f));                                     // relu
+      const f32x2 r = add2(add2(u, splat(8388608.0f)), splat(-8388608.0f));             // rint, 0 <= u < 2
       U = add2(add2(f, off[q]), r);
+      W = U;
     } else {
       U = add2(pair(truncf(c2.x), truncf(c2.y)), off[q]);
+      W = U;
     }
-    const f32x2 hm = fma2_rm(U, splat(0.03125f), splat(8388608.0f));  // 2^23 + floor(U / 32)
+    const f32x2 hm = fma2_rm(W, splat(0.03125f), splat(8388608.0f));  // 2^23 + floor(U / 32) (== floor(W / 32))
     const f32x2 ex = add2(hm, splat(-8388608.0f));                    // ext
     const f32x2 lo = fma2(ex, splat(-32.0f), U);                      // base (a main element's ext is dropped)
     const float wq = q == 0 ? 1.0f : q == 1 ? 32.0f : q == 2 ? 1024.0f : 32768.0f;
@@ -274,7 +286,6 @@ __device__ __forceinline__ bool hot_chunk(const float4& v0, const float4& v1, co
   out.half[1] = bits_of(acc.y) & 0x007FFFFFu;
   out.tag = bits_of(T) & 0xFFu;
   out.ext = bits_of(E + 8388608.0f) & 0xFFFFu;
-  return true;
 }
 
 // ---- per-lane assembly of a warp tile's words from its four chunks ---------------------------------
@@ -312,41 +323,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-constexpr int kMaxRounds = 4;  // CTA tiles per CTA ("group")
 constexpr int kStages = 2;
 constexpr int kStageBytes = kWarpTile * 4;                                  // 4 KB per warp tile
 constexpr int kEncodeDynSmem = kWarpsPerCta * kStages * kStageBytes + 1024;  // + alignment slack
 
-// Scratch of one encode call (device).  Placement of the variable-length part is
-// reduce-then-scan: pass 1 (the expensive one, one read of x) quantises, writes the fixed part of
-// the stream, parks every warp tile's extras segment at a fixed stride and adds each group's word
-// count to its super-group's total (integer atomics: order-independent); the LAST CTA of pass 1 to
-// finish (atomic ticket) scans the n / 2 Mi super-group totals and writes the header; pass 2 (the
-// placement kernel) moves the segments to their dense positions.  No block ever waits on another,
-// so nothing here can hang, and the placement is a pure function of the input: the stream is
-// byte-identical run to run.  (Measured first: a single-pass decoupled look-back — with ~450 groups
-// resident each group's look-back walk under full HBM load cost ~10x its own compute time; and a
-// separate scan kernel over the per-group counts — 20 us plus a launch at 2^28 elements.)
-constexpr int kSuperShift = 6;  // groups per super-group = 64
-
-struct EncodeScratch {
-  uint32_t* group_words;  // [n_groups] extras words of each group (a group = one CTA of pass 1: <= 32 warp tiles)
-  uint32_t* seg_words;    // [n_warp_tiles] words of each warp tile's segment
-  uint32_t* staging;      // [n_warp_tiles][seg_words(XB)] parked segments
-  uint32_t* super_off;    // [n_super] exclusive prefix of super_words (written by the last CTA of pass 1)
-  // ---- zero on entry (one memset per call) ----
-  unsigned int* ticket;         // CTAs that have finished pass 1
-  unsigned long long* totals;   // [2] outliers, clipped / NaN codes (integer atomics: order-independent)
-  uint32_t* super_words;        // [n_super] extras words of each run of 64 groups
-};
-
-// What the last CTA of pass 1 needs to finish the header.
-struct HeaderArgs {
-  smaq_packed_header* hdr;
-  uint32_t* table;
-  long long n_super, n_cta_tiles;
-  int64_t n;
-  int stochastic, count_saturated;
+// Scratch of one encode call (device, 64 bytes): an arrival ticket and three totals.  Zero on entry
+// (smaq_encode_workspace_init, once); the last CTA to finish moves the totals into the header and leaves the
+// scratch zero again, so no memset node is issued per call.  Integer atomics: order-independent, deterministic.
+struct EncodeWs {
+  unsigned int ticket;
+  unsigned int pad;
+  unsigned long long n_outlier, n_saturated, extras_words;
 };
 
 __device__ __forceinline__ void red_or_shared(uint32_t addr, uint32_t v) {
@@ -368,19 +355,21 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 
 // A chunk the hot path cannot take (or any chunk of a tile that is not hot): the literal sequence.
 // Out of line, arguments and result by value (registers), so that none of its set-up is scheduled
-// into the hot path.  Returns (half0, half1, tag | n_saturated << 8, ext).
+// into the hot path.  `rnd` / `sub`: the chunk's Philox words and window set when the uniforms are drawn
+// in-kernel.  Returns (half0, half1, tag | n_saturated << 8, ext).
 template <int PM, int XB, bool kStochastic, bool kHasProbs>
-__device__ __noinline__ uint4 slow_chunk(float4 v0, float4 v1, float4 p0, float4 p1, uint4 rnd, int nvalid,
+__device__ __noinline__ uint4 slow_chunk(float4 v0, float4 v1, float4 p0, float4 p1, uint4 rnd, uint32_t sub, int nvalid,
                                          const Scalars* s) {
+  constexpr bool kRng = kStochastic && !kHasProbs;
   float xv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
   float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-  if (kStochastic && !kHasProbs) {
-    pv[0] = uniform16(rnd.x, 0); pv[1] = uniform16(rnd.x, 1); pv[2] = uniform16(rnd.y, 0); pv[3] = uniform16(rnd.y, 1);
-    pv[4] = uniform16(rnd.z, 0); pv[5] = uniform16(rnd.z, 1); pv[6] = uniform16(rnd.w, 0); pv[7] = uniform16(rnd.w, 1);
+  if (kRng) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pv[j] = rnd16_q(rnd16_k(rnd, sub, j));
   }
   ChunkBits out;
   uint32_t n_sat = 0;
-  generic_chunk<PM, XB, kStochastic>(xv, pv, nvalid, *s, out, n_sat);
+  generic_chunk<PM, XB, kStochastic, kRng>(xv, pv, nvalid, *s, out, n_sat);
   return make_uint4(out.half[0], out.half[1], out.tag | (n_sat << 8), out.ext);
 }
 __device__ __forceinline__ void take_slow(const uint4& r, ChunkBits& out, uint32_t& n_sat) {
@@ -391,23 +380,31 @@ __device__ __forceinline__ void take_slow(const uint4& r, ChunkBits& out, uint32
   n_sat += r.z >> 8;
 }
 
-// One warp tile on the hot path: the tile is in shared memory at `stage` (TMA).
+// One warp tile on the hot path: the tile is in shared memory at `stage` (TMA).  A lane draws TWO Philox calls
+// for its 32 elements: chunks (0, 1) and (2, 3) share one each (common.cuh: rnd16_*).
 template <bool kStochastic, bool kHasProbs, bool kCountSat>
 __device__ __forceinline__ void hot_tile(uint32_t stage, const float* __restrict__ probs, int64_t wt, bool probs_vec,
                                          const KernelParams& kp, const Scalars& s, const Hot& hot, ChunkBits (&ch)[4],
                                          uint32_t& n_sat) {
+  constexpr bool kRng = kStochastic && !kHasProbs;
   const int lane = lane_id();
   f32x2 sat2 = splat(0.0f);
-  // Philox counter of a chunk = index of its first element / 8 = 128 wt + 32 k + lane
-  const uint32_t g_lo = ((uint32_t)wt << 7) | (uint32_t)lane, g_hi = (uint32_t)((uint64_t)wt >> 25);
+  // call index of chunks (2h, 2h + 1) = (2 wt + h) * 32 + lane
+  const uint32_t c_lo = ((uint32_t)wt << 6) | (uint32_t)lane, c_hi = (uint32_t)((uint64_t)wt >> 26);
   const uint32_t lane_addr = stage + 32 * lane;
+  uint4 rnd[2];
+  rnd[0] = rnd[1] = make_uint4(0u, 0u, 0u, 0u);
+  if (kRng) {
+    rnd[0] = philox4x32(kp.keys, c_lo, c_hi, (uint32_t)kp.offset, (uint32_t)(kp.offset >> 32));
+    rnd[1] = philox4x32(kp.keys, c_lo + 32u, c_hi, (uint32_t)kp.offset, (uint32_t)(kp.offset >> 32));
+  }
+  float tmin = INFINITY;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     float4 v[2], p4[2];
     v[0] = lds128(lane_addr + 1024 * k);
     v[1] = lds128(lane_addr + 1024 * k + 16);
     p4[0] = p4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
     if (kStochastic && kHasProbs) {
       const int64_t e = wt * kWarpTile + 256 * k + 8 * lane;
       if (probs_vec) {
@@ -418,12 +415,31 @@ __device__ __forceinline__ void hot_tile(uint32_t stage, const float* __restrict
         p4[1] = make_float4(probs[e + 4], probs[e + 5], probs[e + 6], probs[e + 7]);
       }
     }
-    if (kStochastic && !kHasProbs)
-      rnd = philox4x32(kp.keys, g_lo + 32u * k, g_hi, (uint32_t)kp.offset, (uint32_t)(kp.offset >> 32));
-    if (!hot_chunk<kStochastic, kHasProbs, kCountSat>(v[0], v[1], p4[0], p4[1], rnd, hot, ch[k], sat2))
-      take_slow(slow_chunk<5, 2, kStochastic, kHasProbs>(v[0], v[1], p4[0], p4[1], rnd, 8, &s), ch[k], n_sat);
+    float amin;
+    if (k & 1) hot_chunk<kStochastic, kHasProbs, kCountSat, 1>(v[0], v[1], p4[0], p4[1], rnd[k >> 1], hot, ch[k], sat2, amin);
+    else hot_chunk<kStochastic, kHasProbs, kCountSat, 0>(v[0], v[1], p4[0], p4[1], rnd[k >> 1], hot, ch[k], sat2, amin);
+    tmin = min_nan(tmin, amin);
   }
-  if (kCountSat) n_sat += (uint32_t)__float2int_rn(sat2.x + sat2.y);
+  if (!(tmin >= hot.z_lo)) {
+    // rare: a zero, denormal-range or NaN quotient somewhere in this lane's 32 values — all four chunks again,
+    // with IEEE division (the tile is still in shared memory)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float4 v[2], p4[2];
+      v[0] = lds128(lane_addr + 1024 * k);
+      v[1] = lds128(lane_addr + 1024 * k + 16);
+      p4[0] = p4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kStochastic && kHasProbs) {
+        const int64_t e = wt * kWarpTile + 256 * k + 8 * lane;
+        p4[0] = make_float4(probs[e], probs[e + 1], probs[e + 2], probs[e + 3]);
+        p4[1] = make_float4(probs[e + 4], probs[e + 5], probs[e + 6], probs[e + 7]);
+      }
+      take_slow(slow_chunk<5, 2, kStochastic, kHasProbs>(v[0], v[1], p4[0], p4[1], rnd[k >> 1], (uint32_t)(k & 1), 8, &s),
+                ch[k], n_sat);
+    }
+  } else if (kCountSat) {
+    n_sat += (uint32_t)__float2int_rn(sat2.x + sat2.y);
+  }
 }
 
 // Any other warp tile (other widths, degenerate statistics, unaligned tensors, the ragged last
@@ -433,6 +449,7 @@ __device__ __forceinline__ void generic_tile(const float* __restrict__ x, int64_
                                           const KernelParams& kp, const Scalars& s, int64_t base, ChunkBits (&ch)[4],
                                           uint32_t& n_sat) {
   const int lane = lane_id();
+#pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int64_t e = base + 256 * k + 8 * lane;
     float4 v[2], p4[2];
@@ -447,96 +464,42 @@ __device__ __forceinline__ void generic_tile(const float* __restrict__ x, int64_
         p4[h] = make_float4(eh < n ? probs[eh] : 0.f, eh + 1 < n ? probs[eh + 1] : 0.f, eh + 2 < n ? probs[eh + 2] : 0.f,
                             eh + 3 < n ? probs[eh + 3] : 0.f);
     }
-    if (kStochastic && !kHasProbs) rnd = philox_group(kp.keys, (uint64_t)(e >> 3), kp.offset);
+    const uint64_t g = (uint64_t)(e >> 3);
+    if (kStochastic && !kHasProbs) rnd = rnd16_call(kp.keys, g, kp.offset);
     const int64_t left = n - e;
-    take_slow(slow_chunk<PM, XB, kStochastic, kHasProbs>(v[0], v[1], p4[0], p4[1], rnd,
+    take_slow(slow_chunk<PM, XB, kStochastic, kHasProbs>(v[0], v[1], p4[0], p4[1], rnd, rnd16_sub(g),
                                                          left >= 8 ? 8 : (left > 0 ? (int)left : 0), &s), ch[k], n_sat);
   }
 }
 
-// Run by the LAST CTA of pass 1 to finish (atomic ticket): exclusive scan of the
-// super-group word counts (n / 2 Mi entries), header.
-__device__ __forceinline__ void finish_stream(const EncodeScratch& sc, const HeaderArgs& ha,
-                                              const float* __restrict__ mean_std, const KernelParams& kp) {
-  __shared__ uint32_t s_part[kWarpsPerCta];
-  __shared__ uint32_t s_carry;
-  const int lane = lane_id(), warp = warp_id();
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  for (long long base = 0; base < ha.n_super; base += kPackThreads) {
-    const long long i = base + threadIdx.x;
-    const uint32_t w = i < ha.n_super ? __ldcg(sc.super_words + i) : 0u;
-    const uint32_t inc = warp_inclusive_scan(w);
-    if (lane == 31) s_part[warp] = inc;
-    __syncthreads();
-    uint32_t before = s_carry, all = 0;
-#pragma unroll
-    for (int k = 0; k < kWarpsPerCta; ++k) {
-      before += k < warp ? s_part[k] : 0u;
-      all += s_part[k];
-    }
-    if (i < ha.n_super) {
-      sc.super_off[i] = before + inc - w;
-      sc.super_words[i] = 0;  // leave the workspace reusable
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_carry += all;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    smaq_packed_header* hdr = ha.hdr;
-    hdr->magic = kMagic;
-    hdr->bits_main = kp.bits_main;
-    hdr->bits_outlier = kp.bits_outlier;
-    hdr->stochastic = ha.stochastic;
-    hdr->n = ha.n;
-    hdr->mean = mean_std[0];
-    hdr->std_raw = mean_std[1];
-    hdr->threshold = kp.thr;
-    hdr->range_main = kp.range_main;
-    hdr->range_outlier = kp.range_out;
-    hdr->clamp_lo = kp.clamp_lo;
-    hdr->clamp_hi = kp.clamp_hi;
-    hdr->pad0 = 0.0f;
-    hdr->n_outlier = __ldcg(sc.totals);
-    hdr->n_saturated = ha.count_saturated ? __ldcg(sc.totals + 1) : ~0ull;  // all ones: not counted
-    hdr->extras_words = s_carry;
-    hdr->status = 0;
-    ha.table[ha.n_cta_tiles] = s_carry;
-    sc.totals[0] = 0;
-    sc.totals[1] = 0;
-    *sc.ticket = 0;
-  }
-}
+// What the last CTA needs to write the header.
+struct HeaderArgs {
+  smaq_packed_header* hdr;
+  int64_t n;
+  int stochastic, count_saturated;
+};
 
-// Pass 1.  A GROUP is `rounds` consecutive CTA tiles (<= 32 warp tiles; the unit of the placement
-// pass); a CTA owns `gpc` consecutive groups, so the per-CTA set-up is amortised.  Each warp runs through its warp tiles on its own: while it quantises tile r out of
-// shared memory, TMA is already filling the other stage with tile r+1 (across group boundaries
-// too).  The only block barrier is the one that closes a group.
+// The encoder.  A CTA owns `tiles_per_cta` consecutive CTA tiles; each of its warps runs through its warp tiles on
+// its own: while it quantises tile r out of shared memory, TMA is already filling the other stage with tile r+1.
+// There is no block barrier in the loop, no cross-CTA dependency, and one launch per call.
 template <int PM, int XB, bool kStochastic, bool kHasProbs, bool kCountSat>
-// Two CTAs per SM (100 registers per thread) measured 1 % faster than three (79 registers): this kernel is bound
-// by what each warp can issue, not by latency hiding — 16 resident warps lose nothing against 24.
 #ifndef SMAQ_ENC_CTAS
 #define SMAQ_ENC_CTAS 2
 #endif
 __global__ void __launch_bounds__(kPackThreads, SMAQ_ENC_CTAS)
     encode_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ mean_std,
                   const float* __restrict__ probs, const __grid_constant__ KernelParams kp,
-                  uint32_t* __restrict__ planes, EncodeScratch sc, long long n_cta_tiles, int rounds, int gpc,
-                  long long n_groups, int aligned, HeaderArgs ha) {
+                  uint32_t* __restrict__ planes, uint32_t* __restrict__ extras, EncodeWs* __restrict__ ws,
+                  long long n_cta_tiles, int tiles_per_cta, int aligned, HeaderArgs ha) {
   constexpr int kSeg = seg_words(XB);
   constexpr bool kCanHot = (PM == 5 && XB == 2);
   extern __shared__ unsigned char dyn_smem[];
   __shared__ uint32_t s_seg[kWarpsPerCta][kSeg + 2];  // +2: spill words of the last atomicOr
-  __shared__ uint32_t s_tot[2][3][kWarpsPerCta];       // double-buffered by group parity
   __shared__ __align__(8) uint64_t s_bar[kWarpsPerCta][kStages];
   __shared__ Scalars s_scalars;
   __shared__ Hot s_hot;
   __shared__ bool s_last;
 
-  // pass 2 is launched behind this kernel as a programmatic dependent: its CTAs may become resident as this
-  // grid's leave; it waits for this grid's completion before it reads anything
-  asm volatile("griddepcontrol.launch_dependents;");
   const int lane = lane_id(), warp = warp_id();
   const uint32_t seg_addr = smem_u32(&s_seg[warp][0]);
   if (lane == 0) {
@@ -545,10 +508,8 @@ __global__ void __launch_bounds__(kPackThreads, SMAQ_ENC_CTAS)
     mbar_fence_init();
   }
   for (int j = lane; j < kSeg + 2; j += 32) sts32(seg_addr + 4 * j, 0u);  // kept zero between tiles by the copy-out loop
-  const long long g_first = (long long)blockIdx.x * gpc;
-  const int n_my_groups = (int)min((long long)gpc, n_groups - g_first);
-  const long long first_tile = g_first * rounds;
-  const int nrounds = (int)min((long long)n_my_groups * rounds, n_cta_tiles - first_tile);  // CTA tiles of this CTA
+  const long long first_tile = (long long)blockIdx.x * tiles_per_cta;
+  const int nrounds = (int)min((long long)tiles_per_cta, n_cta_tiles - first_tile);  // CTA tiles of this CTA
 
   // this warp's two 4 KB stages (1 KB aligned)
   const uint32_t stage0 = ((smem_u32(dyn_smem) + 1023u) & ~1023u) + (uint32_t)warp * kStages * kStageBytes;
@@ -565,7 +526,7 @@ __global__ void __launch_bounds__(kPackThreads, SMAQ_ENC_CTAS)
   const float* x_next = x + base0;            // source of the next TMA request
   int64_t wt = base0 >> 10;                    // warp tile index of the current round
   uint32_t* rec = planes + wt * (int64_t)((1 + PM) * 32) + lane;
-  uint32_t* park = sc.staging + wt * (int64_t)kSeg + lane;
+  uint32_t* seg_out = extras + wt * (int64_t)kSeg + lane;
   int r_issued = 0;
   auto issue = [&]() {  // request round r_issued (if it is a staged one)
     if (r_issued < r_full && lane == 0) {
@@ -590,162 +551,125 @@ __global__ void __launch_bounds__(kPackThreads, SMAQ_ENC_CTAS)
   __syncthreads();
   const Scalars s = s_scalars;
   const Hot hot = s_hot;
+  // lane masks of the warp scan (loop-invariant)
+  const uint32_t m1 = lane >= 1 ? ~0u : 0u, m2 = lane >= 2 ? ~0u : 0u, m4 = lane >= 4 ? ~0u : 0u,
+                 m8 = lane >= 8 ? ~0u : 0u, m16 = lane >= 16 ? ~0u : 0u;
 
-  int r = 0;
-  for (int gi = 0; gi < n_my_groups; ++gi) {
-    uint32_t n_out_total = 0, n_sat_total = 0, words_total = 0;
-    const int r_end = min(r + rounds, nrounds);
-    for (; r < r_end; ++r, wt += kWarpsPerCta, rec += kWarpsPerCta * (1 + PM) * 32, park += kWarpsPerCta * kSeg) {
-      issue();  // round r + 1: its stage was fully consumed in round r - 1 (__syncwarp below)
-      if (r >= r_any) continue;  // warp tiles past the end of the tensor: nothing stored (uniform per warp)
-      ChunkBits ch[4];
-      if (r < r_full) {
-        mbar_wait(&s_bar[warp][r & 1], (uint32_t)((r >> 1) & 1));
-        if constexpr (kCanHot) {
-          if (hot.ok)
-            hot_tile<kStochastic, kHasProbs, kCountSat>(stage0 + (r & 1) * kStageBytes, probs, wt, probs_vec, kp, s, hot, ch,
-                                                        n_sat_total);
-          else
-            generic_tile<PM, XB, kStochastic, kHasProbs>(x, n, probs, kp, s, wt << 10, ch, n_sat_total);
+  uint32_t n_out_total = 0, n_sat_total = 0, words_total = 0;
+  for (int r = 0; r < nrounds; ++r, wt += kWarpsPerCta, rec += kWarpsPerCta * (1 + PM) * 32, seg_out += kWarpsPerCta * kSeg) {
+    issue();  // round r + 1: its stage was fully consumed in round r - 1 (__syncwarp below)
+    if (r >= r_any) continue;  // warp tiles past the end of the tensor: nothing stored (uniform per warp)
+    ChunkBits ch[4];
+    if (r < r_full) {
+      mbar_wait(&s_bar[warp][r & 1], (uint32_t)((r >> 1) & 1));
+      if constexpr (kCanHot) {
+        if (hot.ok)
+          hot_tile<kStochastic, kHasProbs, kCountSat>(stage0 + (r & 1) * kStageBytes, probs, wt, probs_vec, kp, s, hot, ch,
+                                                      n_sat_total);
+        else
+          generic_tile<PM, XB, kStochastic, kHasProbs>(x, n, probs, kp, s, wt << 10, ch, n_sat_total);
+      }
+    } else {
+      generic_tile<PM, XB, kStochastic, kHasProbs>(x, n, probs, kp, s, wt << 10, ch, n_sat_total);
+    }
+    __syncwarp();  // stage fully read (lane 0 may refill it)
+
+    // fixed-position part of the stream: (1 + PM) rows of 32 words per warp tile, coalesced
+    uint32_t bw[PM];
+    assemble_base<PM>(ch, bw);
+    const uint32_t tagw = ch[0].tag | (ch[1].tag << 8) | (ch[2].tag << 16) | (ch[3].tag << 24);
+    rec[0] = tagw;
+#pragma unroll
+    for (int w = 0; w < PM; ++w) rec[32 * (w + 1)] = bw[w];
+
+    // variable part: the lane's extras (chunks in order, LSB-first) go into this warp tile's segment, which
+    // sits at a fixed place in the extras section
+    const uint32_t n_out = __popc(tagw);
+    n_out_total += n_out;
+    if (XB > 0) {
+      uint32_t inc = n_out * XB;
+      inc += __shfl_up_sync(0xffffffffu, inc, 1) & m1;
+      inc += __shfl_up_sync(0xffffffffu, inc, 2) & m2;
+      inc += __shfl_up_sync(0xffffffffu, inc, 4) & m4;
+      inc += __shfl_up_sync(0xffffffffu, inc, 8) & m8;
+      inc += __shfl_up_sync(0xffffffffu, inc, 16) & m16;
+      uint32_t pos = inc - n_out * XB;
+      if (XB <= 2) {  // at most 64 bits per lane: one 64-bit string, two (rarely three) atomics
+        unsigned long long str = 0;
+        uint32_t len = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          str |= (unsigned long long)ch[k].ext << len;
+          len += __popc(ch[k].tag) * XB;
+        }
+        if (len) {
+          const uint32_t wa = seg_addr + ((pos >> 5) << 2), sh = pos & 31;
+          const uint32_t lo32 = (uint32_t)str, hi32 = (uint32_t)(str >> 32);
+          red_or_shared(wa, lo32 << sh);
+          if (sh + len > 32) red_or_shared(wa + 4, __funnelshift_l(lo32, hi32, sh));  // bits 32..63 of (str << sh)
+          if (sh + len > 64) red_or_shared(wa + 8, hi32 >> (32 - sh));               // sh > 0 here
         }
       } else {
-        generic_tile<PM, XB, kStochastic, kHasProbs>(x, n, probs, kp, s, wt << 10, ch, n_sat_total);
-      }
-      __syncwarp();  // stage fully read (lane 0 may refill it)
-
-      // fixed-position part of the stream: (1 + PM) rows of 32 words per warp tile, coalesced
-      uint32_t bw[PM];
-      assemble_base<PM>(ch, bw);
-      const uint32_t tagw = ch[0].tag | (ch[1].tag << 8) | (ch[2].tag << 16) | (ch[3].tag << 24);
-      rec[0] = tagw;
 #pragma unroll
-      for (int w = 0; w < PM; ++w) rec[32 * (w + 1)] = bw[w];
-
-      // variable part: the lane's extras (chunk groups in order, LSB-first) go into this warp tile's
-      // word-aligned segment
-      const uint32_t n_out = __popc(tagw);
-      n_out_total += n_out;
-      if (XB > 0) {
-        const uint32_t inc = warp_inclusive_scan(n_out * XB);
-        uint32_t pos = inc - n_out * XB;
-        if (XB <= 2) {  // at most 64 bits per lane: one 64-bit string, two (rarely three) atomics
-          unsigned long long str = 0;
-          uint32_t len = 0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            str |= (unsigned long long)ch[k].ext << len;
-            len += __popc(ch[k].tag) * XB;
-          }
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t len = __popc(ch[k].tag) * XB;  // <= 32
           if (len) {
             const uint32_t wa = seg_addr + ((pos >> 5) << 2), sh = pos & 31;
-            const uint32_t lo32 = (uint32_t)str, hi32 = (uint32_t)(str >> 32);
-            red_or_shared(wa, lo32 << sh);
-            if (sh + len > 32) red_or_shared(wa + 4, __funnelshift_l(lo32, hi32, sh));  // bits 32..63 of (str << sh)
-            if (sh + len > 64) red_or_shared(wa + 8, hi32 >> (32 - sh));               // sh > 0 here
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t len = __popc(ch[k].tag) * XB;  // <= 32
-            if (len) {
-              const uint32_t wa = seg_addr + ((pos >> 5) << 2), sh = pos & 31;
-              red_or_shared(wa, ch[k].ext << sh);
-              if (sh + len > 32) red_or_shared(wa + 4, ch[k].ext >> (32 - sh));
-              pos += len;
-            }
+            red_or_shared(wa, ch[k].ext << sh);
+            if (sh + len > 32) red_or_shared(wa + 4, ch[k].ext >> (32 - sh));
+            pos += len;
           }
         }
-        const uint32_t nwords = (__shfl_sync(0xffffffffu, inc, 31) + 31) >> 5;  // <= kSeg <= 128
-        __syncwarp();
+      }
+      const uint32_t nwords = (__shfl_sync(0xffffffffu, inc, 31) + 31) >> 5;  // <= kSeg <= 128
+      __syncwarp();
 #pragma unroll
-        for (int j = 0; j < (kSeg + 31) / 32; ++j) {  // copy out and re-zero for the next tile
-          if ((uint32_t)(32 * j + lane) < nwords) {
-            park[32 * j] = lds32(seg_addr + 4 * (32 * j + lane));
-            sts32(seg_addr + 4 * (32 * j + lane), 0u);
-          }
+      for (int j = 0; j < (kSeg + 31) / 32; ++j) {  // copy out the used words and re-zero them for the next tile
+        if ((uint32_t)(32 * j + lane) < nwords) {
+          seg_out[32 * j] = lds32(seg_addr + 4 * (32 * j + lane));
+          sts32(seg_addr + 4 * (32 * j + lane), 0u);
         }
-        if (lane == 0) sc.seg_words[wt] = nwords;
-        words_total += nwords;
-        __syncwarp();  // the segment is clean before the next round's atomics
       }
-      if (XB == 0 && lane == 0) sc.seg_words[wt] = 0;  // the placement pass still writes the (all-zero) table
+      words_total += nwords;  // uniform over the warp
+      __syncwarp();  // the segment is clean before the next round's atomics
     }
+  }
 
-    // totals of this group: its word count is stored, and added (integer atomics: order-independent,
-    // so the stream stays deterministic) to its super-group's and to the tensor's
-    const uint32_t w_out = warp_sum(n_out_total), w_sat = warp_sum(n_sat_total);
-    if (lane == 0) {
-      s_tot[gi & 1][0][warp] = words_total;
-      s_tot[gi & 1][1][warp] = w_out;
-      s_tot[gi & 1][2][warp] = w_sat;
-    }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-      const long long group = g_first + gi;
-      uint32_t t = 0;
-#pragma unroll
-      for (int w = 0; w < kWarpsPerCta; ++w) t += s_tot[gi & 1][threadIdx.x][w];
-      if (threadIdx.x == 0) {
-        sc.group_words[group] = t;
-        atomicAdd(sc.super_words + (group >> kSuperShift), t);
-      } else {
-        atomicAdd(sc.totals + (threadIdx.x - 1), (unsigned long long)t);
-      }
-    }
-  }
-  if (threadIdx.x < 3) __threadfence();  // the totals are visible before the ticket is
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(sc.ticket, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (s_last) finish_stream(sc, ha, mean_std, kp);
-}
-
-// Pass 2: move every parked segment to its dense position and write the per-CTA-tile table.  One
-// CTA per group (<= 32 warp tiles); eight threads per segment, every load issued before the first
-// store: the pass is latency-bound (three dependent memory round trips), not bandwidth-bound.
-template <int XB>
-__global__ void __launch_bounds__(kPackThreads) encode_place_kernel(EncodeScratch sc, uint32_t* __restrict__ table,
-                                                                    uint32_t* __restrict__ extras,
-                                                                    long long n_cta_tiles, long long n_warp_tiles,
-                                                                    int rounds) {
-  constexpr int kSeg = seg_words(XB);
-  constexpr int kPerThread = (kSeg + 7) / 8;
-  __shared__ uint32_t s_off[kMaxRounds * kWarpsPerCta + 1];
-  // launched as a programmatic dependent of pass 1 (launch latency and CTA set-up overlap its tail): everything
-  // below reads what pass 1 wrote
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  const int lane = lane_id(), warp = warp_id();
-  const long long group = blockIdx.x;
-  const long long first_wt = group * rounds * kWarpsPerCta;
-  const int nseg = rounds * kWarpsPerCta;  // <= 32
-  if (warp == 0) {
-    const long long wt = first_wt + lane;
-    const uint32_t wds = (lane < nseg && wt < n_warp_tiles) ? sc.seg_words[wt] : 0u;
-    // this group's offset: its super-group's + the groups before it inside the super-group (<= 63)
-    const long long sg0 = (group >> kSuperShift) << kSuperShift;
-    uint32_t part = (sg0 + lane < group ? sc.group_words[sg0 + lane] : 0u) +
-                    (sg0 + 32 + lane < group ? sc.group_words[sg0 + 32 + lane] : 0u);
-    const uint32_t goff = sc.super_off[group >> kSuperShift] + warp_sum(part);
-    const uint32_t inc = warp_inclusive_scan(wds);
-    s_off[lane] = goff + inc - wds;
-    if (lane == 31) s_off[32] = goff + inc;
+  // totals (integer atomics: order-independent), then the ticket: the last CTA writes the header
+  const uint32_t w_out = warp_sum(n_out_total), w_sat = warp_sum(n_sat_total);
+  if (lane == 0) {
+    if (w_out) atomicAdd(&ws->n_outlier, (unsigned long long)w_out);
+    if (w_sat) atomicAdd(&ws->n_saturated, (unsigned long long)w_sat);
+    if (words_total) atomicAdd(&ws->extras_words, (unsigned long long)words_total);
+    __threadfence();
   }
   __syncthreads();
-  const int i = threadIdx.x >> 3, sub = threadIdx.x & 7;
-  const long long wt = first_wt + i;
-  if (i < nseg && wt < n_warp_tiles) {
-    const uint32_t off = s_off[i], cnt = s_off[i + 1] - off;
-    const uint32_t* src = sc.staging + wt * (int64_t)kSeg;
-    uint32_t v[kPerThread];
-#pragma unroll
-    for (int j = 0; j < kPerThread; ++j) v[j] = (uint32_t)(sub + 8 * j) < cnt ? __ldcs(src + sub + 8 * j) : 0u;
-#pragma unroll
-    for (int j = 0; j < kPerThread; ++j)
-      if ((uint32_t)(sub + 8 * j) < cnt) extras[(size_t)off + sub + 8 * j] = v[j];
-  }
-  if ((int)threadIdx.x < rounds) {
-    const long long tile = group * rounds + threadIdx.x;
-    if (tile < n_cta_tiles) table[tile] = s_off[threadIdx.x * kWarpsPerCta];
+  if (threadIdx.x == 0) s_last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    smaq_packed_header* hdr = ha.hdr;
+    hdr->magic = kMagic;
+    hdr->bits_main = kp.bits_main;
+    hdr->bits_outlier = kp.bits_outlier;
+    hdr->stochastic = ha.stochastic;
+    hdr->n = ha.n;
+    hdr->mean = mean_std[0];
+    hdr->std_raw = mean_std[1];
+    hdr->threshold = kp.thr;
+    hdr->range_main = kp.range_main;
+    hdr->range_outlier = kp.range_out;
+    hdr->clamp_lo = kp.clamp_lo;
+    hdr->clamp_hi = kp.clamp_hi;
+    hdr->pad0 = 0.0f;
+    hdr->n_outlier = __ldcg(&ws->n_outlier);
+    hdr->n_saturated = ha.count_saturated ? __ldcg(&ws->n_saturated) : ~0ull;  // all ones: not counted
+    hdr->extras_words = __ldcg(&ws->extras_words);
+    hdr->status = 0;
+    ws->n_outlier = 0;  // leave the scratch reusable
+    ws->n_saturated = 0;
+    ws->extras_words = 0;
+    ws->ticket = 0;
   }
 }
 
@@ -759,36 +683,37 @@ __device__ __forceinline__ uint32_t base_field(const uint32_t (&bw)[PM], int k, 
   return v & ((1u << PM) - 1u);
 }
 
+// words of a warp tile's extras segment requested together with its planes, before the tag words say how many
+// are used: two 32-byte sectors — enough for 256 outliers per 1024 elements (the benchmark input has 169);
+// denser tiles fetch the rest once the count is known
+constexpr int kSpecWords = 16;
+
 template <int PM, int XB>
 __global__ void __launch_bounds__(kPackThreads, 4)
-    decode_kernel(const smaq_packed_header* __restrict__ hdr, const uint32_t* __restrict__ table,
-                  const uint32_t* __restrict__ planes, const uint32_t* __restrict__ extras, float* __restrict__ y,
-                  int64_t n, int all_positive, int aligned) {
+    decode_kernel(const smaq_packed_header* __restrict__ hdr, const uint32_t* __restrict__ planes,
+                  const uint32_t* __restrict__ extras, float* __restrict__ y, int64_t n, int all_positive, int aligned) {
   constexpr int kSeg = seg_words(XB);
   constexpr int kMainEntries = 1 << PM, kOutEntries = 1 << (PM + XB);
   __shared__ float s_lut[kMainEntries + kOutEntries];  // [main | outlier], indexed by the stored value U
-  __shared__ uint32_t s_ext[kWarpsPerCta * kSeg + 2];  // the CTA tile's extras: all 8 segments, contiguous
-  __shared__ uint32_t s_warp[kWarpsPerCta];
+  __shared__ uint32_t s_ext[kWarpsPerCta][kSeg + 2];   // each warp's own segment
   const long long tile = blockIdx.x;
   const int lane = lane_id(), warp = warp_id();
   const int64_t wt = (int64_t)tile * kWarpsPerCta + warp;
   const int64_t base = wt * kWarpTile;
 
-  // Everything this CTA reads from HBM is requested up front, so the three dependent round trips of
-  // the naive order (header -> planes -> table -> extras) overlap: the CTA tile's extras range comes
-  // from the table alone, the warps' places inside it from the tag words.
-  const uint32_t ext_first = table[tile], ext_words = min(table[tile + 1] - ext_first, (uint32_t)(kWarpsPerCta * kSeg));
-  uint32_t tagw = 0, bw[PM];
+  // Everything this warp reads from HBM is requested up front: its planes and the head of its extras segment
+  // (whose place is fixed: wt * kSeg words)
+  uint32_t tagw = 0, bw[PM], spec = 0;
 #pragma unroll
   for (int w = 0; w < PM; ++w) bw[w] = 0;
+  const uint32_t* seg_in = extras + wt * (int64_t)kSeg;
   if (base < n) {
     const uint32_t* rec = planes + wt * (int64_t)((1 + PM) * 32) + lane;
     tagw = __ldcs(rec);
 #pragma unroll
     for (int w = 0; w < PM; ++w) bw[w] = __ldcs(rec + 32 * (w + 1));
+    if (XB > 0 && lane < kSpecWords) spec = __ldcs(seg_in + lane);
   }
-  for (uint32_t i = threadIdx.x; i < ext_words + 2; i += kPackThreads)
-    s_ext[i] = i < ext_words ? __ldcs(extras + (size_t)ext_first + i) : 0u;
 
   // The decoded value of every possible field, by the reference's own inverse (IEEE division).
   {
@@ -811,18 +736,20 @@ __global__ void __launch_bounds__(kPackThreads, 4)
     }
   }
 
-  // lane offsets inside the warp tile's segment; the segment's place inside the CTA tile
+  // lane offsets inside the warp tile's segment; the segment into shared memory
   const uint32_t nb = __popc(tagw) * XB;
   const uint32_t inc = warp_inclusive_scan(nb);
-  const uint32_t my_words = (__shfl_sync(0xffffffffu, inc, 31) + 31) >> 5;
-  if (lane == 0) s_warp[warp] = my_words;
-  __syncthreads();  // LUT, segment sizes and extras are in shared memory
-  uint32_t seg_off = 0;
-#pragma unroll
-  for (int w = 0; w < kWarpsPerCta; ++w) seg_off += (w < warp) ? s_warp[w] : 0u;
+  if (XB > 0) {
+    const uint32_t my_words = (__shfl_sync(0xffffffffu, inc, 31) + 31) >> 5;
+    uint32_t* seg_s = &s_ext[warp][0];
+    if (lane < kSpecWords) seg_s[lane] = spec;
+    for (uint32_t i = kSpecWords + lane; i < my_words; i += 32) seg_s[i] = __ldcs(seg_in + i);
+    if (lane < 2) seg_s[max(my_words, (uint32_t)kSpecWords) + lane] = 0u;  // the funnel shift may read one word past the end
+  }
+  __syncthreads();  // LUT and segments are in shared memory
   if (base >= n) return;
-  uint32_t pos = 32 * seg_off + inc - nb;  // bit position inside the CTA tile's extras
-  const uint32_t* seg = s_ext;
+  uint32_t pos = inc - nb;  // bit position inside the warp tile's segment
+  const uint32_t* seg = &s_ext[warp][0];
   const bool full = aligned && (base + kWarpTile <= n);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -872,30 +799,35 @@ static bool width_supported(int bits_main, int bits_outlier) {
   return pm >= 3 && pm <= 7 && xb >= 0 && xb <= 4;
 }
 
-static int rounds_for(int64_t n_cta_tiles) {
-  // CTA tiles per group: kMaxRounds unless the tensor is too small to give every SM a few groups
-  int sms = sm_count();
-  if (sms <= 0) sms = 148;
-#ifndef SMAQ_ENC_ROUNDS_DIV
-#define SMAQ_ENC_ROUNDS_DIV 12
+// CTA tiles per CTA.  A CTA pipelines its tiles (the next tile's TMA is in flight while the current one is packed),
+// so one tile per CTA leaves every tile's load latency exposed.  Rule: fill the resident slots (SMAQ_ENC_CTAS per
+// SM) once, then deepen the CTAs up to kDeep tiles, then add whole waves — full waves at every size, and for huge
+// tensors the >= 8 CTAs per slot the hardware scheduler needs to even out the tail.
+#ifndef SMAQ_ENC_DEEP
+#define SMAQ_ENC_DEEP 32
 #endif
-  int64_t r = n_cta_tiles / ((int64_t)sms * SMAQ_ENC_ROUNDS_DIV);
-  return (int)(r < 1 ? 1 : (r > kMaxRounds ? kMaxRounds : r));
-}
-// Groups per CTA.  A CTA pipelines its groups (the next tile's TMA is in flight while the current one is
-// packed), so one group per CTA leaves every tile's load latency exposed: a 2^24-element tensor ran as 2048
-// one-group CTAs in 7 waves at 21 % of the HBM peak.  Rule: fill the resident slots (SMAQ_ENC_CTAS per SM) once,
-// then deepen the CTAs up to 8 groups, then add whole waves: w = ceil(groups / (8 slots)) waves of CTAs with
-// ceil(groups / (w slots)) groups each — full waves at every size, and for huge tensors the >= 8 CTAs per slot
-// the hardware scheduler needs to even out the tail (one CTA per slot measured 7 % slower at 2^30).
-static int groups_per_cta(int64_t n_groups) {
+static int tiles_per_cta_for(int64_t n_cta_tiles) {
   int sms = sm_count();
   if (sms <= 0) sms = 148;
   const int64_t slots = (int64_t)sms * SMAQ_ENC_CTAS;
-  if (n_groups <= slots) return 1;
-  const int64_t waves = (n_groups + 8 * slots - 1) / (8 * slots);
-  const int64_t g = (n_groups + waves * slots - 1) / (waves * slots);
-  return (int)(g < 1 ? 1 : (g > 8 ? 8 : g));
+  if (n_cta_tiles <= slots) return 1;
+  const int64_t waves = (n_cta_tiles + SMAQ_ENC_DEEP * slots - 1) / (SMAQ_ENC_DEEP * slots);
+  const int64_t g = (n_cta_tiles + waves * slots - 1) / (waves * slots);
+  return (int)(g < 1 ? 1 : (g > SMAQ_ENC_DEEP ? SMAQ_ENC_DEEP : g));
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel instantiation and device, not per call
+template <typename K>
+static cudaError_t ensure_dyn_smem(K kern) {
+  static std::atomic<unsigned long long> done{0};  // one bit per device ordinal (< 64)
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncodeDynSmem);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
 }
 
 }  // namespace smaq
@@ -919,19 +851,20 @@ int smaq_packed_layout_for(int64_t n, int32_t bits_main, int32_t bits_outlier, s
   l.n_cta_tiles = (l.n_warp_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
   l.header_off = 0;
   l.header_bytes = 128;
-  l.table_off = l.header_off + l.header_bytes;
-  l.table_bytes = align_up((l.n_cta_tiles + 1) * 4, 128);
-  l.planes_off = l.table_off + l.table_bytes;
+  l.planes_off = l.header_off + l.header_bytes;
   l.planes_bytes = l.n_warp_tiles * (int64_t)(1 + pm) * 128;
   l.extras_off = l.planes_off + l.planes_bytes;
-  l.extras_capacity_bytes = align_up(l.n_warp_tiles * (int64_t)(kWarpTile * xb / 32) * 4 + 4, 128);
+  l.extras_stride_bytes = xb == 0 ? 0 : (int64_t)seg_words(xb) * 4;
+  l.extras_capacity_bytes = align_up(l.n_warp_tiles * l.extras_stride_bytes + 8, 128);  // + the decoder's look-ahead
   l.total_capacity_bytes = l.extras_off + l.extras_capacity_bytes;
-  // scratch: [group_words: 1 uint32 per group (at most one group per CTA tile) | seg_words: 1 per warp tile |
-  // super_off | parked segments | zeroed tail: ticket, totals, super_words]
-  const int64_t n_super = (l.n_cta_tiles >> kSuperShift) + 1;
-  l.workspace_bytes = align_up(l.n_cta_tiles * 4 + l.n_warp_tiles * 4 + n_super * 4, 256) +
-                      align_up(l.n_warp_tiles * (int64_t)seg_words(xb) * 4, 256) + align_up(32 + n_super * 4, 256);
+  l.workspace_bytes = 64;
   *out = l;
+  return SMAQ_OK;
+}
+
+int smaq_encode_workspace_init(void* ws, size_t ws_bytes, smaq_stream_t stream) {
+  if (!ws || ws_bytes < sizeof(smaq::EncodeWs)) return smaq::fail(SMAQ_ERR_WORKSPACE, "encode_workspace_init: workspace too small");
+  SMAQ_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(smaq::EncodeWs), (cudaStream_t)stream));
   return SMAQ_OK;
 }
 
@@ -939,19 +872,17 @@ int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* p
                 void* packed, size_t packed_bytes, void* ws, size_t ws_bytes, smaq_stream_t stream_) {
   using namespace smaq;
   static_assert(sizeof(smaq_packed_header) <= 128, "header must fit its slot");
+  static_assert(sizeof(EncodeWs) <= 64, "scratch must fit smaq_packed_layout.workspace_bytes");
   if (int rc = check_params(params)) return rc;
   if (!x || !mean_std || !packed || !ws || n <= 0) return fail(SMAQ_ERR_ARG, "encode: null pointer or n <= 0");
   smaq_packed_layout l;
   if (int rc = smaq_packed_layout_for(n, params->bits_main, params->bits_outlier, &l)) return rc;
   if (packed_bytes < (size_t)l.total_capacity_bytes) return fail(SMAQ_ERR_WORKSPACE, "encode: packed buffer too small");
   if (ws_bytes < (size_t)l.workspace_bytes) return fail(SMAQ_ERR_WORKSPACE, "encode: workspace too small");
-  if (!aligned16(packed)) return fail(SMAQ_ERR_ARG, "encode: packed buffer must be 16-byte aligned");
+  if (!aligned16(packed) || !aligned16(ws)) return fail(SMAQ_ERR_ARG, "encode: packed buffer and workspace must be 16-byte aligned");
   cudaStream_t stream = (cudaStream_t)stream_;
-  const int rounds = rounds_for(l.n_cta_tiles);
-  const long long n_groups = (l.n_cta_tiles + rounds - 1) / rounds;
   char* pb = (char*)packed;
   auto* hdr = (smaq_packed_header*)(pb + l.header_off);
-  auto* table = (uint32_t*)(pb + l.table_off);
   auto* planes = (uint32_t*)(pb + l.planes_off);
   auto* extras = (uint32_t*)(pb + l.extras_off);
   const KernelParams kp = to_kernel_params(*params);
@@ -960,48 +891,20 @@ int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* p
   const bool st = params->stochastic != 0;
   const bool hp = st && probs != nullptr;
   const bool cs = params->count_saturated != 0;
-  const int gpc = groups_per_cta(n_groups);
-  const unsigned grid = (unsigned)((n_groups + gpc - 1) / gpc);
-  const int64_t n_super_alloc = (l.n_cta_tiles >> kSuperShift) + 1;
-  const int64_t zero_bytes = align_up(32 + n_super_alloc * 4, 256);
-  EncodeScratch sc;
-  {
-    uint32_t* w = (uint32_t*)ws;
-    sc.group_words = w;
-    sc.seg_words = w + l.n_cta_tiles;
-    sc.super_off = w + l.n_cta_tiles + l.n_warp_tiles;
-    sc.staging = (uint32_t*)((char*)ws + align_up(l.n_cta_tiles * 4 + l.n_warp_tiles * 4 + n_super_alloc * 4, 256));
-    char* tail = (char*)ws + l.workspace_bytes - zero_bytes;
-    sc.ticket = (unsigned int*)tail;
-    sc.totals = (unsigned long long*)(tail + 16);
-    sc.super_words = (uint32_t*)(tail + 32);
-  }
+  const int tpc = tiles_per_cta_for(l.n_cta_tiles);
+  const unsigned grid = (unsigned)((l.n_cta_tiles + tpc - 1) / tpc);
   HeaderArgs ha;
   ha.hdr = hdr;
-  ha.table = table;
-  ha.n_super = ((n_groups - 1) >> kSuperShift) + 1;
-  ha.n_cta_tiles = l.n_cta_tiles;
   ha.n = n;
   ha.stochastic = st ? 1 : 0;
   ha.count_saturated = cs ? 1 : 0;
-  SMAQ_CUDA_OK(cudaMemsetAsync(sc.ticket, 0, (size_t)zero_bytes, stream));
-
-  cudaLaunchConfig_t place_cfg = {};
-  place_cfg.gridDim = dim3((unsigned)n_groups);
-  place_cfg.blockDim = dim3(kPackThreads);
-  place_cfg.stream = stream;
-  cudaLaunchAttribute place_attr[1];
-  set_dependent_launch(place_cfg, place_attr);
 
 #define SMAQ_ENC_LAUNCH(PM_, XB_, ST_, HP_)                                                                        \
   {                                                                                                                \
-    auto kern = cs ? encode_kernel<PM_, XB_, ST_, HP_, true> : encode_kernel<PM_, XB_, ST_, HP_, false>;                                                                 \
-    SMAQ_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncodeDynSmem));         \
-    kern<<<grid, kPackThreads, kEncodeDynSmem, stream>>>(x, n, mean_std, probs, kp, planes, sc, l.n_cta_tiles,     \
-                                                         rounds, gpc, n_groups, aligned, ha);                      \
-    SMAQ_LAUNCH_OK();                                                                                              \
-    SMAQ_CUDA_OK(cudaLaunchKernelEx(&place_cfg, encode_place_kernel<XB_>, sc, table, extras,                       \
-                                    (long long)l.n_cta_tiles, (long long)l.n_warp_tiles, rounds));                 \
+    auto kern = cs ? encode_kernel<PM_, XB_, ST_, HP_, true> : encode_kernel<PM_, XB_, ST_, HP_, false>;           \
+    SMAQ_CUDA_OK(ensure_dyn_smem(kern));                                                                           \
+    kern<<<grid, kPackThreads, kEncodeDynSmem, stream>>>(x, n, mean_std, probs, kp, planes, extras, (EncodeWs*)ws, \
+                                                         (long long)l.n_cta_tiles, tpc, aligned, ha);              \
   }
 #define SMAQ_ENC(PM_, XB_)                                                                                         \
   if (pm == PM_ && xb == XB_) {                                                                                    \
@@ -1028,11 +931,10 @@ int smaq_decode(const void* packed, size_t packed_bytes, int64_t n, int32_t bits
   if (!packed || !y || n <= 0) return fail(SMAQ_ERR_ARG, "decode: null pointer or n <= 0");
   smaq_packed_layout l;
   if (int rc = smaq_packed_layout_for(n, bits_main, bits_outlier, &l)) return rc;
-  if (packed_bytes < (size_t)l.extras_off) return fail(SMAQ_ERR_WORKSPACE, "decode: packed buffer too small");
+  if (packed_bytes < (size_t)l.total_capacity_bytes) return fail(SMAQ_ERR_WORKSPACE, "decode: packed buffer too small");
   cudaStream_t stream = (cudaStream_t)stream_;
   const char* pb = (const char*)packed;
   auto* hdr = (const smaq_packed_header*)(pb + l.header_off);
-  auto* table = (const uint32_t*)(pb + l.table_off);
   auto* planes = (const uint32_t*)(pb + l.planes_off);
   auto* extras = (const uint32_t*)(pb + l.extras_off);
   const int aligned = aligned32(y);
@@ -1040,7 +942,7 @@ int smaq_decode(const void* packed, size_t packed_bytes, int64_t n, int32_t bits
   const unsigned grid = (unsigned)l.n_cta_tiles;
 #define SMAQ_DEC(PM_, XB_)                                                                                         \
   if (pm == PM_ && xb == XB_)                                                                                      \
-    decode_kernel<PM_, XB_><<<grid, kPackThreads, 0, stream>>>(hdr, table, planes, extras, y, n, all_positive, aligned);
+    decode_kernel<PM_, XB_><<<grid, kPackThreads, 0, stream>>>(hdr, planes, extras, y, n, all_positive, aligned);
 #define SMAQ_DEC_ROW(PM_) SMAQ_DEC(PM_, 0) SMAQ_DEC(PM_, 1) SMAQ_DEC(PM_, 2) SMAQ_DEC(PM_, 3) SMAQ_DEC(PM_, 4)
 #ifdef SMAQ_PACK_MINIMAL
   SMAQ_DEC(5, 2)

@@ -19,13 +19,13 @@ namespace smaq {
 
 // Four elements with the IEEE divide everywhere: degenerate statistics, or a group the fast
 // path flagged.  Out of line so the hot loop stays small.
-template <bool kStochastic>
+template <bool kStochastic, bool kRng>
 __device__ __noinline__ float4 roundtrip_group_exact(float4 v, float4 pr, const Scalars& s, bool saturate,
                                                      bool all_positive) {
   PairClass k0, k1;
   bool unused = false;
-  f32x2 c01 = encode_pair<kStochastic, false>(pair(v.x, v.y), pair(pr.x, pr.y), s, k0, unused);
-  f32x2 c23 = encode_pair<kStochastic, false>(pair(v.z, v.w), pair(pr.z, pr.w), s, k1, unused);
+  f32x2 c01 = encode_pair<kStochastic, false, kRng>(pair(v.x, v.y), pair(pr.x, pr.y), s, k0, unused);
+  f32x2 c23 = encode_pair<kStochastic, false, kRng>(pair(v.z, v.w), pair(pr.z, pr.w), s, k1, unused);
   if (saturate) {
     c01 = pair(saturate_code(c01.x, s, is_outlier0(k0)), saturate_code(c01.y, s, is_outlier1(k0)));
     c23 = pair(saturate_code(c23.x, s, is_outlier0(k1)), saturate_code(c23.y, s, is_outlier1(k1)));
@@ -35,28 +35,36 @@ __device__ __noinline__ float4 roundtrip_group_exact(float4 v, float4 pr, const 
   return make_float4(y01.x, y01.y, y23.x, y23.y);
 }
 
+// q = (k + 1/2) / 2^16 for the eight elements of group g (common.cuh: rnd16_*; smaq_math.cuh: encode_pair kRng)
+__device__ __forceinline__ f32x8 group_q(const KernelParams& kp, uint64_t g) {
+  const uint4 r = rnd16_call(kp.keys, g, kp.offset);
+  const uint32_t sub = rnd16_sub(g);
+  f32x8 q;
+  q.a = make_float4(rnd16_q(rnd16_k(r, sub, 0)), rnd16_q(rnd16_k(r, sub, 1)), rnd16_q(rnd16_k(r, sub, 2)),
+                    rnd16_q(rnd16_k(r, sub, 3)));
+  q.b = make_float4(rnd16_q(rnd16_k(r, sub, 4)), rnd16_q(rnd16_k(r, sub, 5)), rnd16_q(rnd16_k(r, sub, 6)),
+                    rnd16_q(rnd16_k(r, sub, 7)));
+  return q;
+}
+
 // Processes the 8-element group g (elements 8g..8g+7): one Philox call, four packed pairs.
 template <bool kStochastic, bool kHasProbs, bool kAllPos, bool kSaturate, bool kFast>
 __device__ __forceinline__ f32x8 roundtrip_group8(const f32x8& v, f32x8 pr, uint64_t g, const Scalars& s,
                                                   const KernelParams& kp) {
-  if (kStochastic && !kHasProbs) {
-    const uint4 r = philox_group(kp.keys, g, kp.offset);
-    const f32x2 p0 = uniform16_pair(r.x), p1 = uniform16_pair(r.y), p2 = uniform16_pair(r.z), p3 = uniform16_pair(r.w);
-    pr.a = make_float4(p0.x, p0.y, p1.x, p1.y);
-    pr.b = make_float4(p2.x, p2.y, p3.x, p3.y);
-  }
+  constexpr bool kRng = kStochastic && !kHasProbs;
+  if (kRng) pr = group_q(kp, g);
   f32x8 o;
   if (!kFast) {
-    o.a = roundtrip_group_exact<kStochastic>(v.a, pr.a, s, kSaturate, kAllPos);
-    o.b = roundtrip_group_exact<kStochastic>(v.b, pr.b, s, kSaturate, kAllPos);
+    o.a = roundtrip_group_exact<kStochastic, kRng>(v.a, pr.a, s, kSaturate, kAllPos);
+    o.b = roundtrip_group_exact<kStochastic, kRng>(v.b, pr.b, s, kSaturate, kAllPos);
     return o;
   }
   PairClass k0, k1, k2, k3;
   bool suspect = false;
-  f32x2 c0 = encode_pair<kStochastic, true>(pair(v.a.x, v.a.y), pair(pr.a.x, pr.a.y), s, k0, suspect);
-  f32x2 c1 = encode_pair<kStochastic, true>(pair(v.a.z, v.a.w), pair(pr.a.z, pr.a.w), s, k1, suspect);
-  f32x2 c2 = encode_pair<kStochastic, true>(pair(v.b.x, v.b.y), pair(pr.b.x, pr.b.y), s, k2, suspect);
-  f32x2 c3 = encode_pair<kStochastic, true>(pair(v.b.z, v.b.w), pair(pr.b.z, pr.b.w), s, k3, suspect);
+  f32x2 c0 = encode_pair<kStochastic, true, kRng>(pair(v.a.x, v.a.y), pair(pr.a.x, pr.a.y), s, k0, suspect);
+  f32x2 c1 = encode_pair<kStochastic, true, kRng>(pair(v.a.z, v.a.w), pair(pr.a.z, pr.a.w), s, k1, suspect);
+  f32x2 c2 = encode_pair<kStochastic, true, kRng>(pair(v.b.x, v.b.y), pair(pr.b.x, pr.b.y), s, k2, suspect);
+  f32x2 c3 = encode_pair<kStochastic, true, kRng>(pair(v.b.z, v.b.w), pair(pr.b.z, pr.b.w), s, k3, suspect);
   if (kSaturate) {
     c0 = pair(saturate_code(c0.x, s, is_outlier0(k0)), saturate_code(c0.y, s, is_outlier1(k0)));
     c1 = pair(saturate_code(c1.x, s, is_outlier0(k1)), saturate_code(c1.y, s, is_outlier1(k1)));
@@ -70,8 +78,8 @@ __device__ __forceinline__ f32x8 roundtrip_group8(const f32x8& v, f32x8 pr, uint
   o.a = make_float4(y0.x, y0.y, y1.x, y1.y);
   o.b = make_float4(y2.x, y2.y, y3.x, y3.y);
   if (suspect) {  // rare
-    o.a = roundtrip_group_exact<kStochastic>(v.a, pr.a, s, kSaturate, kAllPos);
-    o.b = roundtrip_group_exact<kStochastic>(v.b, pr.b, s, kSaturate, kAllPos);
+    o.a = roundtrip_group_exact<kStochastic, kRng>(v.a, pr.a, s, kSaturate, kAllPos);
+    o.b = roundtrip_group_exact<kStochastic, kRng>(v.b, pr.b, s, kSaturate, kAllPos);
   }
   return o;
 }
@@ -81,7 +89,8 @@ __device__ __forceinline__ f32x8 roundtrip_group8(const f32x8& v, f32x8 pr, uint
 // fewer instructions with bit-identical results (see make_rt_hot):
 //   * (z -+ t) * range_outlier == fma(z, range_outlier, -+K), K = t * range_outlier, because z -+ t is exact for a
 //     power-of-two t and |z| < 2^20 t: the outlier value is ONE predicated FMA over the main value z * range_main;
-//   * rint(relu((frac - p) + 0.5)) == [frac - p > 2^-25] for p > 0 (the in-kernel uniforms are (k + 1/2) / 2^16);
+//   * with the in-kernel uniforms the code is floor(c + q), q = (k + 1/2) / 2^16: one round-down addition and one
+//     floor (encode_pair, kRng); q is built from the Philox bytes by PRMT + one packed addition (no conversion);
 //   * clamping c before rounding == clamping the rounded code (saturate);
 //   * the inverse of an outlier is q -+ (-t) == q + copysign(t, z).
 // Groups with a zero / denormal-range / NaN / huge quotient are re-run with the IEEE-division path.
@@ -150,21 +159,22 @@ __device__ __forceinline__ f32x8 roundtrip_group8_hot(const f32x8& v, const f32x
   const float amin = min_nan(rt_min3_nan_abs(z[3].x, z[3].y, m1), m2);
   const float x1 = rt_max3_abs(z[0].x, z[0].y, z[1].x), x2 = rt_max3_abs(z[1].y, z[2].x, z[2].y);
   const float amax = rt_max3_abs(z[3].x, z[3].y, fmaxf(x1, x2));
+  constexpr bool kRng = kStochastic && !kHasProbs;
   if (!(amin >= h.z_lo) || amax > h.z_hi) {  // rare: the literal sequence with IEEE division
     f32x8 p8 = pr;
-    if (kStochastic && !kHasProbs) {
-      const uint4 rr = philox_group(kp.keys, g, kp.offset);
-      const f32x2 p0 = uniform16_pair(rr.x), p1 = uniform16_pair(rr.y), p2 = uniform16_pair(rr.z), p3 = uniform16_pair(rr.w);
-      p8.a = make_float4(p0.x, p0.y, p1.x, p1.y);
-      p8.b = make_float4(p2.x, p2.y, p3.x, p3.y);
-    }
+    if (kRng) p8 = group_q(kp, g);
     f32x8 o;
-    o.a = roundtrip_group_exact<kStochastic>(v.a, p8.a, s, kSaturate, kAllPos);
-    o.b = roundtrip_group_exact<kStochastic>(v.b, p8.b, s, kSaturate, kAllPos);
+    o.a = roundtrip_group_exact<kStochastic, kRng>(v.a, p8.a, s, kSaturate, kAllPos);
+    o.b = roundtrip_group_exact<kStochastic, kRng>(v.b, p8.b, s, kSaturate, kAllPos);
     return o;
   }
   uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
-  if (kStochastic && !kHasProbs) rnd = philox_group(kp.keys, g, kp.offset);
+  uint32_t sel_e = 0u, sel_o = 0u;
+  if (kRng) {
+    rnd = rnd16_call(kp.keys, g, kp.offset);
+    sel_e = rnd16_sel_even(rnd16_sub(g));
+    sel_o = rnd16_sel_odd(rnd16_sub(g));
+  }
   const f32x2 rm2 = splat(h.rm), std2 = splat(h.std_mul);
   float out[8];
 #pragma unroll
@@ -181,23 +191,21 @@ __device__ __forceinline__ f32x8 roundtrip_group8_hot(const f32x8& v, const f32x
     }
     const f32x2 c2 = pair(c0, c1);
     f32x2 code;
-    if (kStochastic) {                                                                   // :93-98
+    if (kRng) {
+      // 128 + k / 2^16 straight from the Philox bytes (exponent byte 0x43), then q = (k + 1/2) / 2^16 exactly
+      const uint32_t w = q == 0 ? rnd.x : q == 1 ? rnd.y : q == 2 ? rnd.z : rnd.w;
+      const f32x2 kf = pair(from_bits(__byte_perm(w, 0x43000000u, sel_e)), from_bits(__byte_perm(w, 0x43000000u, sel_o)));
+      const f32x2 qv = add2(kf, splat(-127.99999237060546875f));
+      const f32x2 wv = add2_rd(c2, qv);                                                  // RD(c + q)
+      code = pair(floorf(wv.x), floorf(wv.y));                                           // == floor(c + q)
+    } else if (kStochastic) {                                                            // :93-98
       const f32x2 f = pair(floorf(c0), floorf(c1));
       const f32x2 frac = add2(c2, neg2(f));
-      f32x2 r;
-      if (kHasProbs) {
-        const float pa = q == 0 ? pr.a.x : q == 1 ? pr.a.z : q == 2 ? pr.b.x : pr.b.z;
-        const float pb = q == 0 ? pr.a.y : q == 1 ? pr.a.w : q == 2 ? pr.b.y : pr.b.w;
-        f32x2 u = add2(add2(frac, pair(-pa, -pb)), splat(0.5f));
-        u = pair(fmaxf(u.x, 0.0f), fmaxf(u.y, 0.0f));
-        r = add2(add2(u, splat(8388608.0f)), splat(-8388608.0f));                        // rint, 0 <= u < 2
-      } else {
-        const uint32_t w = q == 0 ? rnd.x : q == 1 ? rnd.y : q == 2 ? rnd.z : rnd.w;
-        const f32x2 kf = pair(from_bits(__byte_perm(w, 0x4B000000u, 0x7610)), from_bits(__byte_perm(w, 0x4B000000u, 0x7632)));
-        const f32x2 p = fma2(kf, splat(1.52587890625e-05f), splat(-127.99999237060546875f));  // (k + 1/2) / 2^16
-        const f32x2 t = add2(frac, neg2(p));
-        r = pair(t.x > 2.98023223876953125e-08f ? 1.0f : 0.0f, t.y > 2.98023223876953125e-08f ? 1.0f : 0.0f);
-      }
+      const float pa = q == 0 ? pr.a.x : q == 1 ? pr.a.z : q == 2 ? pr.b.x : pr.b.z;
+      const float pb = q == 0 ? pr.a.y : q == 1 ? pr.a.w : q == 2 ? pr.b.y : pr.b.w;
+      f32x2 u = add2(add2(frac, pair(-pa, -pb)), splat(0.5f));
+      u = pair(fmaxf(u.x, 0.0f), fmaxf(u.y, 0.0f));
+      const f32x2 r = add2(add2(u, splat(8388608.0f)), splat(-8388608.0f));              // rint, 0 <= u < 2
       code = add2(f, r);
     } else {
       code = pair(truncf(c0), truncf(c1));                                               // :169
@@ -314,17 +322,20 @@ __device__ __forceinline__ void roundtrip_body(const float* x, float* y, int64_t
   }
 }
 
-// One element at a time: tails, unaligned tensors, small tensors.  Same random stream as the
-// vector path: element i uses half (i & 1) of word (i & 7) >> 1 of Philox group i >> 3.
+// q of ONE element (tails, unaligned tensors): the same number the vector path draws for it
+__device__ __forceinline__ float element_q(const KernelParams& kp, int64_t i) {
+  const uint64_t g = (uint64_t)(i >> 3);
+  return rnd16_q(rnd16_k(rnd16_call(kp.keys, g, kp.offset), rnd16_sub(g), (int)(i & 7)));
+}
+
+// One element at a time: tails, unaligned tensors, small tensors.  Same random stream as the vector path.
 template <bool kStochastic, bool kHasProbs>
 __device__ __forceinline__ float roundtrip_element(const float* x, const float* probs, int64_t i, const Scalars& s,
                                                    const KernelParams& kp) {
   float p = 0.f;
   if (kStochastic)
-    p = kHasProbs ? probs[i]
-                  : uniform16(philox_word(philox_group(kp.keys, (uint64_t)(i >> 3), kp.offset), (int)((i & 7) >> 1)),
-                              (int)(i & 1));
-  return roundtrip_scalar<kStochastic>(x[i], p, s, kp.saturate != 0, kp.all_positive != 0);
+    p = kHasProbs ? probs[i] : element_q(kp, i);
+  return roundtrip_scalar<kStochastic, kStochastic && !kHasProbs>(x[i], p, s, kp.saturate != 0, kp.all_positive != 0);
 }
 
 // Everything after the statistics are known: the tensor-uniform choice of arithmetic, the vector loop, the tail.
@@ -402,12 +413,9 @@ __global__ void __launch_bounds__(kRtThreads) roundtrip_bn_kernel(const float* x
     const int64_t c = channels == 1 ? 0 : (i / inner) % channels;
     const float g = gamma[c], b = beta[c];
     float p = 0.f;
-    if (kStochastic)
-      p = kHasProbs ? probs[i]
-                    : uniform16(philox_word(philox_group(kp.keys, (uint64_t)(i >> 3), kp.offset), (int)((i & 7) >> 1)),
-                                (int)(i & 1));
+    if (kStochastic) p = kHasProbs ? probs[i] : element_q(kp, i);
     const float xu = true_div(sub_rn(x[i], b), g);                                     // smart.py:144-149
-    float v = roundtrip_scalar<kStochastic>(xu, p, s, kp.saturate != 0, /*all_positive=*/false);
+    float v = roundtrip_scalar<kStochastic, kStochastic && !kHasProbs>(xu, p, s, kp.saturate != 0, /*all_positive=*/false);
     v = add_rn(mul_rn(v, g), b);                                                       // smart.py:174-179
     if (kp.all_positive) v = (v < 0.0f) ? 0.0f : v;                                    // smart.py:181-182
     y[i] = v;

@@ -77,11 +77,10 @@ class PackedLayout(C.Structure):  # smaq_packed_layout
         ("n_cta_tiles", C.c_int64),
         ("header_off", C.c_int64),
         ("header_bytes", C.c_int64),
-        ("table_off", C.c_int64),
-        ("table_bytes", C.c_int64),
         ("planes_off", C.c_int64),
         ("planes_bytes", C.c_int64),
         ("extras_off", C.c_int64),
+        ("extras_stride_bytes", C.c_int64),
         ("extras_capacity_bytes", C.c_int64),
         ("total_capacity_bytes", C.c_int64),
         ("workspace_bytes", C.c_int64),
@@ -133,6 +132,7 @@ _SIGNATURES = {
     "smaq_roundtrip_multi": (C.c_int, [_P, C.c_int32, _I64, _I64, C.POINTER(CodecParams), _I64, _P, C.c_size_t, _P, _P]),
     "smaq_roundtrip_bn": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _I64, _I64, C.POINTER(CodecParams), _P]),
     "smaq_packed_layout_for": (C.c_int, [_I64, C.c_int32, C.c_int32, C.POINTER(PackedLayout)]),
+    "smaq_encode_workspace_init": (C.c_int, [_P, C.c_size_t, _P]),
     "smaq_encode": (C.c_int, [_P, _I64, _P, _P, C.POINTER(CodecParams), _P, C.c_size_t, _P, C.c_size_t, _P]),
     "smaq_decode": (C.c_int, [_P, C.c_size_t, _I64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "smaq_float_quantize": (C.c_int, [_P, _P, _I64, _P, C.POINTER(FloatqParams), _P]),

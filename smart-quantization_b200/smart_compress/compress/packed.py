@@ -1,4 +1,4 @@
-"""The materialised SmaQ stream ("SQB2"): what ``SmartFP.encode`` returns and ``SmartFP.decode`` reads.
+"""The materialised SmaQ stream ("SQB3"): what ``SmartFP.encode`` returns and ``SmartFP.decode`` reads.
 
 Not in the reference (which only fake-quantises, smart.py:154-172); named by the build's north
 star.  The buffer lives in device memory; ``header()`` is the only call that synchronises."""
@@ -34,17 +34,18 @@ class PackedSmaq:
         return N.PackedHeader.from_buffer_copy(raw)
 
     def section(self, name: str) -> torch.Tensor:
-        """uint32 view of 'table', 'planes' or 'extras' (device tensor, capacity-sized)."""
+        """uint32 view of 'planes' or 'extras' (device tensor; the extras hold one fixed-stride segment per warp
+        tile, of which only the used words are specified)."""
         lay = self.layout
         off, nbytes = {
-            "table": (lay.table_off, (lay.n_cta_tiles + 1) * 4),
             "planes": (lay.planes_off, lay.planes_bytes),
-            "extras": (lay.extras_off, lay.extras_capacity_bytes),
+            "extras": (lay.extras_off, lay.n_warp_tiles * lay.extras_stride_bytes),
         }[name]
         return self.buffer[off: off + nbytes].view(torch.int32)
 
     def used_bytes(self) -> int:
-        """Bytes a consumer must keep: header + table + planes + the extras words actually written."""
+        """Bytes that are part of the stream: header + planes + the extras words actually written (the buffer
+        itself is capacity-sized: every warp tile's segment has a fixed place)."""
         lay = self.layout
         return int(lay.extras_off + 4 * self.header().extras_words)
 

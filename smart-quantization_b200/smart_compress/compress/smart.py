@@ -62,6 +62,7 @@ class SmartFP(CompressionAlgorithmBase):
         self._ws_bytes = None
         self._desc_cache = {}            # compress_many: device descriptor arrays by (pointers, sizes)
         self._multi_ws = {}
+        self._encode_ws = {}             # (device, stream) -> the packed encoder's 64-byte scratch
 
     def _derive(self, hp):
         # smart.py:75-84, evaluated in Python floats exactly as there
@@ -367,7 +368,12 @@ class SmartFP(CompressionAlgorithmBase):
         if mean_std is None:
             mean_std = self.statistics(flat, extra.get("_sample_idx"))
         buf = torch.empty(lay.total_capacity_bytes, dtype=torch.uint8, device=data.device)
-        ws = torch.empty(lay.workspace_bytes, dtype=torch.uint8, device=data.device)
+        stream = N.stream_ptr(data.device)
+        key = (data.device.index, stream)
+        ws = self._encode_ws.get(key)
+        if ws is None:  # 64 bytes, zeroed once: every encode leaves it zero (calls on one stream are ordered)
+            ws = self._encode_ws[key] = torch.empty(max(int(lay.workspace_bytes), 64), dtype=torch.uint8, device=data.device)
+            N.check(lib.smaq_encode_workspace_init(N.ptr(ws), ws.numel(), stream), "smaq_encode_workspace_init")
         params = self._params(all_positive=False)
         probs = extra.get("_probs")
         probs_ptr = None
@@ -376,7 +382,7 @@ class SmartFP(CompressionAlgorithmBase):
             probs_ptr = N.ptr(probs)
         N.check(
             lib.smaq_encode(N.ptr(flat), n, N.ptr(mean_std), probs_ptr, C.byref(params), N.ptr(buf), buf.numel(),
-                            N.ptr(ws), ws.numel(), N.stream_ptr(data.device)),
+                            N.ptr(ws), ws.numel(), stream),
             "smaq_encode",
         )
         return PackedSmaq(buffer=buf, layout=lay, shape=data.shape)

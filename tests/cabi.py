@@ -81,6 +81,16 @@ def roundtrip(x, mean_std, params, probs=None, out=None):
     return y
 
 
+def roundtrip_bn(x, mean_std, params, gamma, beta, channels, inner, probs=None):
+    """smaq_roundtrip_bn on a flat NCHW tensor (--use_batch_norm)."""
+    lib = N.load()
+    y = torch.empty_like(x)
+    N.check(lib.smaq_roundtrip_bn(x.data_ptr(), y.data_ptr(), x.numel(), mean_std.data_ptr(),
+                                  None if probs is None else probs.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                  channels, inner, C.byref(params), N.stream_ptr(x.device)), "roundtrip_bn")
+    return y
+
+
 def compress(x, params, probs=None, out=None, ws=None):
     """smaq_compress (statistics + round trip behind one entry point) -> (y, the mean/std it used)."""
     lib = N.load()

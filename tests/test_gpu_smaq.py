@@ -13,7 +13,7 @@ import torch
 
 from oracle.smaq import SmaqConfig, full_mean_std, sample_mean_std, smaq_roundtrip, std_of
 from tests import cabi
-from tests.golden_util import assert_bit_equal, load_golden
+from tests.golden_util import assert_bit_equal, load_golden, uses_bn
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -41,7 +41,15 @@ def test_roundtrip_matches_reference_golden(name):
     params = cabi.codec_params(cfg, all_positive=c["kwargs"].get("all_positive", False))
     xd = x.to(DEV).contiguous().view(-1)
     pd = None if c["probs"] is None else c["probs"].to(DEV).contiguous().view(-1)
-    y = cabi.roundtrip(xd, ms, params, probs=pd)
+    if uses_bn(c):  # --use_batch_norm: the affine wrap runs inside the kernel (smart.py:136-149,174-179)
+        gamma, beta = c["kwargs"]["batch_norm_stats"]
+        if cfg.bn_scalar_params:  # smart.py:140-142 (the means as the reference's CPU run formed them)
+            gamma, beta, channels, inner = gamma.mean().reshape(1), beta.mean().reshape(1), 1, x.numel()
+        else:
+            channels, inner = x.shape[1], x.shape[2] * x.shape[3]
+        y = cabi.roundtrip_bn(xd, ms, params, gamma.to(DEV), beta.to(DEV), channels, inner, probs=pd)
+    else:
+        y = cabi.roundtrip(xd, ms, params, probs=pd)
     assert_bit_equal(y.cpu().view(x.shape), c["y"], name)
 
 
@@ -55,6 +63,76 @@ def test_roundtrip_random_sizes_bit_exact(n, stochastic):
     ms = cabi.mean_std_tensor(ref.mean, ref.std, DEV)
     y = cabi.roundtrip(x.to(DEV), ms, cabi.codec_params(cfg), probs=probs.to(DEV))
     assert_bit_equal(y.cpu(), ref.y, f"n={n}")
+
+
+def test_config0_2p26_roundtrip_matches_oracle():
+    """BASELINE configs[0] itself: 64 Mi elements, N(0,1) with 1 % x10, reference defaults — the fused round trip
+    against the CPU oracle bit for bit (explicit probs, the oracle's statistics), the kernel's own statistics
+    within 1e-6 of the oracle's, and the plugin's one-call path given the kernel's statistics."""
+    n = 1 << 26
+    x, g = make_outlier_tensor(n, seed=1234)
+    probs = torch.rand(n, generator=g)
+    cfg = SmaqConfig()
+    ref = smaq_roundtrip(x, cfg, probs=probs)
+    xd, pd = x.to(DEV), probs.to(DEV)
+    ms = cabi.mean_std_tensor(ref.mean, ref.std, DEV)
+    y = cabi.roundtrip(xd, ms, cabi.codec_params(cfg), probs=pd)
+    assert_bit_equal(y.cpu(), ref.y, "2^26 round trip")
+    del y
+    yc, ms_k = cabi.compress(xd, cabi.codec_params(cfg), probs=pd)
+    msc = ms_k.cpu()
+    assert rel(msc[0].item(), ref.mean.item(), ref.std.item()) < 1e-6 and rel(msc[1].item(), ref.std.item()) < 1e-6
+    ref_k = smaq_roundtrip(x, cfg, probs=probs, mean=msc[0], std=msc[1])
+    assert_bit_equal(yc.cpu(), ref_k.y, "2^26 smaq_compress given its statistics")
+
+
+@pytest.mark.parametrize("n", [8, 9, 1000, 32768, 40001, (1 << 20) + 3, 1 << 24])
+def test_roundtrip_with_in_kernel_random_numbers_matches_oracle(n):
+    """Performance path (no probs tensor): the kernel draws 16 random bits per element (Philox4x32-7, one call per
+    16 elements).  oracle/rng.py restates the generator, so the output is checked bit for bit against the CPU oracle
+    under the kernels' rounding rule — the large kernel, its unaligned form, the one-block kernel, with and without
+    saturation, and a stream offset beyond 32 bits."""
+    from oracle import rng as orng
+
+    x, _ = make_outlier_tensor(n, seed=n + 1)
+    cfg = SmaqConfig()
+    seed, offset = 4242 + n, (3 << 33) + 17
+    probs = torch.from_numpy(orng.probs_for(n, seed=seed, offset=offset))
+    ref = smaq_roundtrip(x, cfg, probs=probs, rng_rule=True)
+    ms = cabi.mean_std_tensor(ref.mean, ref.std, DEV)
+    xd = x.to(DEV)
+    y = cabi.roundtrip(xd, ms, cabi.codec_params(cfg, seed=seed, offset=offset))
+    assert_bit_equal(y.cpu(), ref.y, f"n={n}")
+    sat = smaq_roundtrip(x, cfg, probs=probs, rng_rule=True, saturate=True, all_positive=True)
+    y = cabi.roundtrip(xd, ms, cabi.codec_params(cfg, seed=seed, offset=offset, saturate=True, all_positive=True))
+    assert_bit_equal(y.cpu(), sat.y, f"n={n} saturate, all_positive")
+    buf = torch.empty(n + 1, device=DEV)   # views off the 32-byte grid take the element-wise kernel
+    buf[1:].copy_(xd)
+    y = cabi.roundtrip(buf[1:], ms, cabi.codec_params(cfg, seed=seed, offset=offset))
+    assert_bit_equal(y.cpu(), ref.y, f"n={n} unaligned")
+    if n <= 32768:
+        y, ms_k = cabi.roundtrip_small(xd, cabi.codec_params(cfg, seed=seed, offset=offset), want_stats=True)
+        msc = ms_k.cpu()
+        ref_k = smaq_roundtrip(x, cfg, probs=probs, mean=msc[0], std=msc[1], rng_rule=True)
+        assert_bit_equal(y.cpu(), ref_k.y, f"n={n} one-block kernel")
+    # the rule differs from the reference's expression only on ties |frac - p| <= 2^-25
+    lit = smaq_roundtrip(x, cfg, probs=probs)
+    assert float((lit.y != ref.y).float().mean()) < 1e-5
+
+
+def test_bn_kernel_with_in_kernel_random_numbers_matches_oracle():
+    from oracle import rng as orng
+
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(3, 7, 5, 9, generator=g) * 2 + 0.5
+    gamma, beta = torch.rand(7, generator=g) + 0.5, torch.randn(7, generator=g) * 0.2
+    cfg = SmaqConfig(use_batch_norm=True)
+    probs = torch.from_numpy(orng.probs_for(x.numel(), seed=99, offset=2)).view(x.shape)
+    ref = smaq_roundtrip(x, cfg, probs=probs, rng_rule=True, batch_norm_stats=(gamma, beta), all_positive=True)
+    ms = cabi.mean_std_tensor(ref.mean, ref.std, DEV)
+    y = cabi.roundtrip_bn(x.to(DEV).view(-1), ms, cabi.codec_params(cfg, seed=99, offset=2, all_positive=True),
+                          gamma.to(DEV), beta.to(DEV), 7, 45)
+    assert_bit_equal(y.cpu().view(x.shape), ref.y, "BN kernel, in-kernel uniforms")
 
 
 def test_roundtrip_saturate_matches_oracle():
@@ -234,20 +312,31 @@ def test_plugin_golden_cases(name):
     c = CASES[name]
     fp = make_plugin(c["argv"].split(), c["precision"])
     xd = c["x"].to(DEV)
-    y = fp(xd, tag="t", _probs=c["probs"], _sample_idx=c["idx"], **c["kwargs"])
+    kwargs = dict(c["kwargs"])
+    oracle_kwargs = dict(c["kwargs"])
+    if "batch_norm_stats" in kwargs:  # the layer's gamma / beta live on the device, as the hook passes them
+        kwargs["batch_norm_stats"] = tuple(t.to(DEV) for t in kwargs["batch_norm_stats"])
+        if c["cfg"].bn_scalar_params and c["cfg"].use_batch_norm:
+            # the two means are formed on the device (as the reference would on CUDA); the oracle gets those
+            g, b = kwargs["batch_norm_stats"]
+            oracle_kwargs["batch_norm_stats"] = (g.mean().cpu().expand(g.numel()).clone(), b.mean().cpu().expand(b.numel()).clone())
+    y = fp(xd, tag="t", _probs=c["probs"], _sample_idx=c["idx"], **kwargs)
     if c["same_object"]:
         assert y is xd
         return
     assert y is not xd and y.shape == xd.shape and y.dtype == xd.dtype and y.device == xd.device
     cfg = c["cfg"]
     flat = xd.contiguous().view(-1)
-    ms = (fp.statistics(flat, c["idx"]) if (cfg.use_sample_stats or cfg.use_range_std_dev or
+    ms = (fp.statistics(flat, c["idx"]) if (cfg.use_sample_stats or cfg.use_range_std_dev or uses_bn(c) or
                                               flat.numel() > 32768) else None)
     if ms is None:
         _, ms = cabi.roundtrip_small(flat, cabi.codec_params(cfg), probs=None if c["probs"] is None
                                      else c["probs"].to(DEV).view(-1), want_stats=True)
     ms = ms.cpu()
-    ref = smaq_roundtrip(c["x"].clone(), cfg, probs=c["probs"], idx=c["idx"], mean=ms[0], std=ms[1], **c["kwargs"])
+    if oracle_kwargs is not c["kwargs"] and c["cfg"].bn_scalar_params and uses_bn(c):
+        import dataclasses
+        cfg = dataclasses.replace(cfg, bn_scalar_params=False)  # the per-channel arrays already hold the device's means
+    ref = smaq_roundtrip(c["x"].clone(), cfg, probs=c["probs"], idx=c["idx"], mean=ms[0], std=ms[1], **oracle_kwargs)
     assert_bit_equal(y.cpu(), ref.y, name)
     if not torch.isnan(c["y"]).any():
         # and close to the reference's own output (statistics may differ in the last bits)

@@ -2,7 +2,7 @@
 
 pack -> decode must reproduce, bit for bit, the reference's round trip with codes saturated at the
 field width (oracle/smaq.py, saturate=True), and the stream must have exactly the size the
-reference accounts for (smart.py:184-187) plus the documented table/alignment overhead."""
+reference accounts for (smart.py:184-187) plus the documented alignment overhead."""
 import numpy as np
 import pytest
 import torch
@@ -18,6 +18,21 @@ def make(n, seed, outliers=True):
     if outliers:
         x[torch.randperm(n, generator=g)[: max(1, n // 100)]] *= 10
     return x, torch.rand(n, generator=g)
+
+
+def test_pack_with_the_kernels_own_random_numbers():
+    """The rule the kernels apply to their own uniforms (oracle/rng.py, rng_rule) through the packer."""
+    from oracle import rng
+
+    x, _ = make(30000, 5)
+    cfg = SmaqConfig()
+    probs = torch.from_numpy(rng.probs_for(x.numel(), seed=77, offset=3))
+    res = smaq_roundtrip(x, cfg, probs=probs, rng_rule=True)
+    want = smaq_roundtrip(x, cfg, probs=probs, rng_rule=True, saturate=True)
+    assert_bit_equal(opack.decode(opack.pack(res, cfg)), want.y, "decode(pack(x)), rng rule")
+    # the rule is the reference's expression except on ties: on this input they agree everywhere
+    lit = smaq_roundtrip(x, cfg, probs=probs, saturate=True)
+    assert float((lit.y != want.y).float().mean()) < 1e-4
 
 
 @pytest.mark.parametrize("n", [8, 31, 1024, 1025, 8192, 8193, 50000])
@@ -36,7 +51,9 @@ def test_pack_decode_equals_saturated_roundtrip(n, cfgkw):
     n_pad = p.planes.shape[0] * 1024
     xb = cfg.num_bits_outlier - cfg.num_bits_main
     assert p.planes.size * 32 == n_pad * cfg.num_bits_main
-    assert 0 <= int(p.table[-1]) * 32 - xb * p.n_outlier < 32 * p.planes.shape[0] + 1  # < 32 pad bits per warp tile
+    assert 0 <= p.extras_words * 32 - xb * p.n_outlier < 32 * p.planes.shape[0] + 1  # < 32 pad bits per warp tile
+    for t in range(p.planes.shape[0]):   # nothing outside a segment's used words
+        assert not p.extras[t, p.seg_used[t]:].any()
     # n_saturated is a pure function of the data: scaled values the field cannot hold
     c = res.extras["c"]
     assert p.n_saturated == int((c.abs() > torch.where(res.hi | res.lo, float(cfg.max_code_outlier),

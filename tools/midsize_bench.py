@@ -82,7 +82,7 @@ for log2n in range(a.min, a.max + 1):
     t_f = queued(lambda: lib.smaq_compress(x.data_ptr(), y.data_ptr(), n, None, C.byref(params), cws.data_ptr(), cws_b, st), a.reps)
     lay = packed_layout(n, 6, 8)
     packed = torch.empty(lay.total_capacity_bytes, dtype=torch.uint8, device=dev)
-    pws = torch.empty(lay.workspace_bytes, dtype=torch.uint8, device=dev)
+    pws = torch.zeros(lay.workspace_bytes, dtype=torch.uint8, device=dev)  # smaq_encode_workspace_init: zero once
     p8 = make_floatq_params(5, 2, fp.hparams)
 
     def everything():

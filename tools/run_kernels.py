@@ -32,7 +32,7 @@ fp = make_plugin()
 ms = fp.statistics(x)
 lay = packed_layout(n, 6, 8)
 packed = torch.empty(lay.total_capacity_bytes, dtype=torch.uint8, device=dev)
-ws = torch.empty(lay.workspace_bytes, dtype=torch.uint8, device=dev)
+ws = torch.zeros(lay.workspace_bytes, dtype=torch.uint8, device=dev)  # smaq_encode_workspace_init: zero once
 sws_b = lib.smaq_stats_workspace_bytes(n)
 sws = torch.empty(sws_b, dtype=torch.uint8, device=dev)
 st = N.stream_ptr(dev)
