@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--no-sweep", action="store_true", help="skip the size / codec sweep (N=1 only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the ResNet-34 DDP training block")
+    ap.add_argument("--train-steps", type=int, default=50, help="timed training steps (BASELINE.md §4: >= 50)")
+    ap.add_argument("--train-warmup", type=int, default=10, help="untimed training steps before them (>= 10)")
     return ap.parse_args()
 
 
@@ -82,7 +85,7 @@ def whole_job_gbs(world: int, bytes_per_rank_step: float, ms_per_step: float) ->
 
 def traffic_from_profile(kernel: str, log2n: int):
     """DRAM bytes of one launch of `kernel` from the committed ncu capture (tools/make_profiles.py)."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_traffic.json")
     try:
         with open(path) as f:
             rec = json.load(f)[kernel]
@@ -353,7 +356,10 @@ def run_b200(args):
             for name in k_ms
         },
         "encode_decode_gbs": round(enc_dec_gbs, 1),
+        "encode_decode_frac_of_measured_peak": round(enc_dec_gbs / peak, 4),
+        "encode_decode_frac_of_nominal_8000": round(enc_dec_gbs / 8000.0, 4),
         "frac_of_hbm_peak": round(value / world / peak, 4),
+        "frac_of_nominal_8000": round(value / world / 8000.0, 4),
         "roofline": {
             "bound": "hbm",
             "kernel": f"smaq::{dominant}_kernel<5, 2, ...>",
@@ -362,8 +368,9 @@ def run_b200(args):
             "peak_source": peak_src,
             "unit": "GB/s",
             "frac": round(k_gbs[dominant] / peak, 4),
+            "frac_of_nominal_8000": round(k_gbs[dominant] / 8000.0, 4),
             "traffic": traffic_from_profile(dominant, args.log2n),
-            "traffic_source": "profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one "
+            "traffic_source": "profiles/r2_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one "
                               "`ncu --set full` launch at the same size (null when the size differs)",
             "algorithmic_bytes_per_launch": int(bpe[dominant] * n),
         },
@@ -447,10 +454,62 @@ def run_b200(args):
         result["cpu_baseline"] = cpu_baseline(bpe["step"], steps=3, warmup=1)
         result["cpu_baseline"]["same_port_torch_eager_on_this_gpu"] = eager_gpu_baseline(bpe["step"], device)
 
+    # ---- the other half of BASELINE.json's metric: ResNet-34 img/s at this many GPUs -------------------------------
+    if not args.no_train:
+        del pipe
+        x = None
+        torch.cuda.empty_cache()
+        result["train"] = train_block(args, device, world, local)
+        result["gpu_launches_note"] = "gpu_launches counts the kernel bench's timed region only (statistics + encode + decode per step)"
+
     if rank == 0:
         print(json.dumps(result), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_block(args, device, world, local):
+    """BASELINE.json configs[3] (the training half of `metric`): ResNet-34 with the reference's stem on synthetic
+    224x224 images, batch 32 per GPU, SGD, fp32, random init; DDP over NCCL when world > 1 (its bucketed gradient
+    all-reduce is the only collective, issued before the optimizer-side compression: reference optimizer.py:135-141).
+    Three legs through the SAME hooks and the same wiring (smart_compress/util/train.py; reference util/train.py:
+    197-213, models/base.py:137-163):
+      img_per_s                      --compress smart on all five data structures, this library's kernels;
+      plain_img_per_s                --no_compress (no hooks, the bare optimizer);
+      reference_eager_cuda_img_per_s the reference's own SmartFP.__call__ as torch eager CUDA operators (the CPU
+                                     oracle's port run on the GPU: a baseline leg, fewer steps — it is ~10x slower).
+    >= 50 timed steps after 10 warm-ups; device-timed, max over ranks; clocks sampled during the
+    timed region of the first leg."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from train_bench import run_training
+
+    cfg = dict(model_name="resnet34", batch=32, image=224, device=device, world=world, local=local)
+    clocks = ClockSampler(local)
+    smart = run_training(compress="smart", steps=args.train_steps, warmup=args.train_warmup, clocks=clocks,
+                         profile=True, **cfg)
+    plain = run_training(compress="fp32", steps=args.train_steps, warmup=args.train_warmup, **cfg)
+    ref_steps, ref_warm = max(3, args.train_steps // 5), max(2, args.train_warmup // 5)
+    eager = run_training(compress="smart", codec="reference-eager", steps=ref_steps, warmup=ref_warm, **cfg)
+    prof = smart.pop("profile", None)
+    return {
+        "metric": "resnet34_train_img_per_s", "unit": "img/s", "n_gpus": world,
+        "img_per_s": smart["value"], "ms_per_step": smart["ms_per_step"],
+        "plain_img_per_s": plain["value"], "plain_ms_per_step": plain["ms_per_step"],
+        "reference_eager_cuda_img_per_s": eager["value"], "reference_eager_cuda_ms_per_step": eager["ms_per_step"],
+        "speedup_vs_reference_eager_cuda": round(smart["value"] / eager["value"], 3),
+        "fraction_of_plain": round(smart["value"] / plain["value"], 4),
+        "steps": smart["steps"], "warmup": smart["warmup"],
+        "reference_eager_cuda_steps": ref_steps, "reference_eager_cuda_warmup": ref_warm,
+        "scaling": "weak", "dtype": "f32", "data": "synthetic",
+        "config": {"workload": smart["workload"], "global_batch": 32 * world, "optimizer": "SGD lr 0.1 momentum 0.9",
+                   "parallelism": f"dp{world}" + (" (DistributedDataParallel, NCCL all-reduce)" if world > 1 else ""),
+                   "stem": "reference CIFAR stem (3x3 stride 1; SURVEY.md H10): 52.7 M feature-map elements per image"},
+        "codec_calls_per_step": smart["codec_calls_per_step"],
+        "peak_memory_gib": smart["peak_memory_gib"], "plain_peak_memory_gib": plain["peak_memory_gib"],
+        "loss": smart["loss"], "clocks": clocks.summary(),
+        "profile": None if prof is None else {k: prof[k] for k in ("gpu_busy_ms_per_step", "codec_kernels_ms_per_step",
+                                                                    "nccl_kernels_ms_per_step", "gpu_ops_per_step")},
+    }
 
 
 def sweep(args, device, peak):
@@ -506,6 +565,31 @@ def sweep(args, device, peak):
                 r[name] = {"ms": round(t, 4), "gbs": round(gbs, 1), "frac": round(gbs / peak, 3)}
             r["log2n"] = log2n
             out["float_emulation"] = r
+            # also pure N(0,1) (31.7 % outliers) and --use_sample_stats (k = 16)
+            g = torch.Generator(device=device).manual_seed(4321)
+            xn = torch.randn(n, generator=g, device=device, dtype=torch.float32)
+            N.check(lib.smaq_stats_full(xn.data_ptr(), n, 1, ms.data_ptr(), sws.data_ptr(), sws_b, st), "stats")
+            t_rt_n, _ = time_kernel(lambda: lib.smaq_roundtrip(xn.data_ptr(), y.data_ptr(), n, ms.data_ptr(), None, C.byref(params), st))
+            t_enc_n, _ = time_kernel(lambda: lib.smaq_encode(xn.data_ptr(), n, ms.data_ptr(), None, C.byref(params),
+                                                             packed.data_ptr(), packed.numel(), ws.data_ptr(), ws.numel(), st))
+            t_dec_n, _ = time_kernel(lambda: lib.smaq_decode(packed.data_ptr(), packed.numel(), n, 6, 8, 0, y.data_ptr(), st))
+            hdr_n = N.PackedHeader.from_buffer_copy(bytes(packed[: C.sizeof(N.PackedHeader)].cpu().numpy()))
+            bn = bytes_per_element(hdr_n.n_outlier / n)
+            pn = {"log2n": log2n, "outlier_fraction": round(hdr_n.n_outlier / n, 5)}
+            for name, t, key in (("roundtrip", t_rt_n, "roundtrip"), ("encode", t_enc_n, "encode"), ("decode", t_dec_n, "decode")):
+                gbs = bn[key] * n / (t * 1e-3) / 1e9
+                pn[name] = {"ms": round(t, 4), "gbs": round(gbs, 1), "frac": round(gbs / peak, 3), "frac_of_nominal_8000": round(gbs / 8000.0, 3)}
+            gbs = (bn["encode"] + bn["decode"]) * n / ((t_enc_n + t_dec_n) * 1e-3) / 1e9
+            pn["encode_decode"] = {"gbs": round(gbs, 1), "frac": round(gbs / peak, 3), "frac_of_nominal_8000": round(gbs / 8000.0, 3)}
+            out["pure_normal_input"] = pn
+            del xn
+            t_ss, _ = time_kernel(lambda: lib.smaq_stats_sampled_draw(x.data_ptr(), n, 16, 0, 1234, 7, ms.data_ptr(), st), reps=20)
+            N.check(lib.smaq_stats_sampled_draw(x.data_ptr(), n, 16, 0, 1234, 7, ms.data_ptr(), st), "sampled")
+            t_rt_s, _ = time_kernel(lambda: lib.smaq_roundtrip(x.data_ptr(), y.data_ptr(), n, ms.data_ptr(), None, C.byref(params), st))
+            gbs = 8.0 * n / ((t_ss + t_rt_s) * 1e-3) / 1e9
+            out["use_sample_stats"] = {"log2n": log2n, "num_samples": 16, "stats_ms": round(t_ss, 4), "roundtrip_ms": round(t_rt_s, 4),
+                                       "gbs": round(gbs, 1), "frac": round(gbs / peak, 3), "frac_of_nominal_8000": round(gbs / 8000.0, 3),
+                                       "note": "k indices drawn on the device (Philox + Floyd) instead of randperm(N): 8 B/element algorithmic"}
         del x, y, packed, ws
     return out
 

@@ -16,7 +16,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "smart_compress", "_lib")
-LIB = os.path.join(OUT_DIR, "libsmaq_b200.so")
+# SMAQ_LIB_NAME: development builds next to the product library (A/B experiments; see SMAQ_B200_LIB in _native.py)
+LIB = os.path.join(OUT_DIR, os.environ.get("SMAQ_LIB_NAME", "libsmaq_b200.so"))
 STAMP = LIB + ".stamp"
 
 SOURCES = ["capi.cu", "smaq_stats.cu", "smaq_roundtrip.cu", "smaq_pack.cu", "float_quantize.cu"]
@@ -78,7 +79,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     for s in srcs:
-        o = os.path.join(OUT_DIR, os.path.basename(s)[:-3] + ".o")
+        o = os.path.join(OUT_DIR, os.path.basename(LIB) + "." + os.path.basename(s)[:-3] + ".o")
         cmd = [nvcc_path(), *NVCC_FLAGS, *extra_flags(s), "-c", s, "-o", o]
         if verbose:
             cmd[1:1] = ["-Xptxas", "-v"]

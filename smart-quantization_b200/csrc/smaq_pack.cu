@@ -816,10 +816,9 @@ static int tiles_per_cta_for(int64_t n_cta_tiles) {
   return (int)(g < 1 ? 1 : (g > SMAQ_ENC_DEEP ? SMAQ_ENC_DEEP : g));
 }
 
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel instantiation and device, not per call
-template <typename K>
-static cudaError_t ensure_dyn_smem(K kern) {
-  static std::atomic<unsigned long long> done{0};  // one bit per device ordinal (< 64)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel instantiation and device, not per call.
+// `done` belongs to ONE instantiation (the caller keeps one flag word per launch site and kernel): a bit per device.
+static cudaError_t ensure_dyn_smem(const void* kern, std::atomic<unsigned long long>& done) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
@@ -864,7 +863,7 @@ int smaq_packed_layout_for(int64_t n, int32_t bits_main, int32_t bits_outlier, s
 
 int smaq_encode_workspace_init(void* ws, size_t ws_bytes, smaq_stream_t stream) {
   if (!ws || ws_bytes < sizeof(smaq::EncodeWs)) return smaq::fail(SMAQ_ERR_WORKSPACE, "encode_workspace_init: workspace too small");
-  SMAQ_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(smaq::EncodeWs), (cudaStream_t)stream));
+  SMAQ_CUDA_OK(cudaMemsetAsync(ws, 0, ws_bytes < 64 ? ws_bytes : 64, (cudaStream_t)stream));
   return SMAQ_OK;
 }
 
@@ -902,7 +901,8 @@ int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* p
 #define SMAQ_ENC_LAUNCH(PM_, XB_, ST_, HP_)                                                                        \
   {                                                                                                                \
     auto kern = cs ? encode_kernel<PM_, XB_, ST_, HP_, true> : encode_kernel<PM_, XB_, ST_, HP_, false>;           \
-    SMAQ_CUDA_OK(ensure_dyn_smem(kern));                                                                           \
+    static std::atomic<unsigned long long> smem_set[2];                                                            \
+    SMAQ_CUDA_OK(ensure_dyn_smem((const void*)kern, smem_set[cs ? 1 : 0]));                                        \
     kern<<<grid, kPackThreads, kEncodeDynSmem, stream>>>(x, n, mean_std, probs, kp, planes, extras, (EncodeWs*)ws, \
                                                          (long long)l.n_cta_tiles, tpc, aligned, ha);              \
   }

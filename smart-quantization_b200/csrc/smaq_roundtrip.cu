@@ -15,6 +15,10 @@
 #include "params.cuh"
 #include "smaq_math.cuh"
 
+#ifndef SMAQ_RT_ROUND_FORM
+#define SMAQ_RT_ROUND_FORM 1
+#endif
+
 namespace smaq {
 
 // Four elements with the IEEE divide everywhere: degenerate statistics, or a group the fast
@@ -196,8 +200,17 @@ __device__ __forceinline__ f32x8 roundtrip_group8_hot(const f32x8& v, const f32x
       const uint32_t w = q == 0 ? rnd.x : q == 1 ? rnd.y : q == 2 ? rnd.z : rnd.w;
       const f32x2 kf = pair(from_bits(__byte_perm(w, 0x43000000u, sel_e)), from_bits(__byte_perm(w, 0x43000000u, sel_o)));
       const f32x2 qv = add2(kf, splat(-127.99999237060546875f));
+#if SMAQ_RT_ROUND_FORM == 0
       const f32x2 wv = add2_rd(c2, qv);                                                  // RD(c + q)
       code = pair(floorf(wv.x), floorf(wv.y));                                           // == floor(c + q)
+#else
+      // the same number with the floor OFF the path that waits for the Philox words: floor(c + q) == floor(c) +
+      // [frac + q >= 1], and RD(frac + q) >= 1 <=> frac + q >= 1 (1 is representable).  This kernel runs near the
+      // HBM roofline on latency hiding, and FRND (XU pipe) behind the 7-round Philox chain cost it 5 % at 2^30.
+      const f32x2 f = pair(floorf(c0), floorf(c1));
+      const f32x2 sv = add2_rd(add2(c2, neg2(f)), qv);
+      code = add2(f, pair(sv.x >= 1.0f ? 1.0f : 0.0f, sv.y >= 1.0f ? 1.0f : 0.0f));
+#endif
     } else if (kStochastic) {                                                            // :93-98
       const f32x2 f = pair(floorf(c0), floorf(c1));
       const f32x2 frac = add2(c2, neg2(f));

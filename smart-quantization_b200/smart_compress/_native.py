@@ -17,7 +17,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libsmaq_b200.so")
+# SMAQ_B200_LIB: development override (A/B builds of the same ABI, tools/ab_build.sh); unset in normal use
+LIB_PATH = os.environ.get("SMAQ_B200_LIB") or os.path.join(_HERE, "_lib", "libsmaq_b200.so")
 
 OK = 0
 ABI_VERSION = 4

@@ -18,7 +18,7 @@ os.makedirs(out_dir, exist_ok=True)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 h = rows[0]
-names = {"stats_kernel<0": "stats", "roundtrip_kernel": "roundtrip", "encode_kernel": "encode", "encode_place_kernel": "encode_place",
+names = {"stats_kernel<0": "stats", "roundtrip_kernel": "roundtrip", "encode_kernel": "encode",
          "decode_kernel": "decode", "floatq_kernel<0": "fp8", "stats_kernel<2": "s2fp8_stats", "floatq_kernel<1": "s2fp8_apply"}
 traffic = {}
 seen = set()

@@ -2,24 +2,27 @@
 """Training-level measurement (BASELINE.json configs 3-5): synthetic-input, random-init ResNet-18/34 or
 BERT-base training steps with the codec hooked onto every data structure the reference compresses —
 feature maps and gradient maps (util/pytorch/autograd.py), gradients, weights and optimizer state
-(util/pytorch/optimizer.py) — exactly as reference smart_compress/util/train.py:197-213 and
-models/base.py:137-163 wire them (BatchNorm parameters in a ``no_weight_compression`` group; SGD
-lr 0.1 momentum 0.9 for the ResNets, AdamW for BERT).
+(util/pytorch/optimizer.py) — wired exactly as reference smart_compress/util/train.py:197-213 and
+models/base.py:137-163 wire them (``smart_compress.util.train.parse_compression_args`` /
+``build_compression``; BatchNorm parameters in a ``no_weight_compression`` group; SGD lr 0.1 momentum 0.9 for the
+ResNets, AdamW for BERT; ``--compress_loss`` honoured, models/base.py:114-115).
 
-    python tools/train_bench.py --model resnet18 --batch 256 --image 32 --compress smart --steps 20 --warmup 5
+    python tools/train_bench.py --model resnet18 --batch 256 --image 32 --compress smart --steps 50 --warmup 10
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/train_bench.py \
         --model resnet34 --batch 32 --image 224 --compress smart
 
-One process per GPU; DDP (NCCL over NVLink) issues the only collective, the bucketed gradient
-all-reduce, BEFORE the optimizer-side compression — the reference's layout (optimizer.py:135-141).
-Prints one JSON line: img/s (or seq/s) summed over ranks, device-timed, max over ranks.
+One process per GPU; DDP (NCCL over NVLink) issues the only collective, the bucketed gradient all-reduce, BEFORE
+the optimizer-side compression — the reference's layout (optimizer.py:135-141).  ``run_training`` is also what
+``bench.py`` calls for its ``train`` block.  ``--codec reference-eager`` swaps the CUDA kernels for the CPU oracle's
+port of smart.py evaluated by torch's own CUDA operators through the SAME hooks: what running the reference
+unchanged on this GPU costs (a baseline leg; the only place this file touches ``oracle/``).
 """
 import argparse
+import contextlib
 import json
 import os
 import sys
 import time
-from argparse import ArgumentParser
 from collections import Counter
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -29,6 +32,8 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 import torch.nn as nn  # noqa: E402
 
+DATA_STRUCTURES = ("forward", "backward", "weights", "gradients", "momentum_vectors")
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -37,79 +42,86 @@ def parse():
     ap.add_argument("--image", type=int, default=32)
     ap.add_argument("--seq", type=int, default=128)
     ap.add_argument("--compress", default="smart", choices=["smart", "fp8", "s2fp8", "fp16", "bf16", "fp32"])
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--codec", default="b200", choices=["b200", "reference-eager"])
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--no-batched-optimizer", action="store_true",
                     help="per-tensor optimizer-side calls (the reference's loop) instead of compress_many")
     ap.add_argument("--packed-activations", action="store_true",
                     help="keep autograd's saved tensors as packed SmaQ streams (not in the reference; changes numerics)")
+    ap.add_argument("--compress_loss", action="store_true")
     ap.add_argument("--profile", action="store_true",
                     help="after the timed steps, run 3 more under torch.profiler and print GPU-busy time and the top kernels to stderr")
-    ap.add_argument("--only", default="forward,backward,weights,gradients,momentum_vectors",
+    ap.add_argument("--only", default=",".join(DATA_STRUCTURES),
                     help="which data structures are compressed (reference --no_compress_* flags)")
     return ap.parse_args()
 
 
-def codec_and_hparams(name, only):
-    from smart_compress.compress import ALGORITHMS
+class ReferenceEagerSmaQ:
+    """BASELINE LEG ONLY: the reference's SmartFP.__call__ (smart.py:110-190) as restated op for op by
+    oracle/smaq.py, evaluated by torch's own CUDA operators — ~28 launches, rand_like and the blocking
+    ``if std_dev == 0`` read per call — behind the same hook boundary as the product."""
 
-    cls = ALGORITHMS[name]
-    hp = cls.add_argparse_args(ArgumentParser()).parse_args([])
-    hp.precision = 32
-    for k in ("forward", "backward", "weights", "gradients", "momentum_vectors"):
-        setattr(hp, f"compress_{k}", k in only and name != "fp32")
-    hp.compress_loss = False
-    return cls(hp), hp
+    def __init__(self, hparams):
+        from oracle.smaq import SmaqConfig, smaq_roundtrip
+
+        self.hparams = hparams
+        self.cfg = SmaqConfig()
+        self._rt = smaq_roundtrip
+        self.log = self.log_custom = None
+
+    @torch.no_grad()
+    def __call__(self, t, tag=None, all_positive=False, **_):
+        if t.numel() < self.cfg.min_size:
+            return t
+        return self._rt(t, self.cfg, probs=torch.rand_like(t), all_positive=all_positive).y
 
 
-def build_model(a, device):
-    if a.model.startswith("resnet"):
+def build_model(model_name, batch, image, seq, device):
+    if model_name.startswith("resnet"):
         from smart_compress.models.pytorch.resnet import build
 
-        model = build(a.model, num_classes=10).to(device)
-        x = torch.randn(a.batch, 3, a.image, a.image, device=device)
-        y = torch.randint(0, 10, (a.batch,), device=device)
+        model = build(model_name, num_classes=10).to(device)
+        x = torch.randn(batch, 3, image, image, device=device)
+        y = torch.randint(0, 10, (batch,), device=device)
 
         def loss_fn(m):
             return nn.functional.cross_entropy(m(x), y)
 
-        unit, per_step = "img/s", a.batch
-    else:
-        from transformers import BertConfig, BertForSequenceClassification
+        return model, loss_fn, "img/s"
+    from transformers import BertConfig, BertForSequenceClassification
 
-        cfg = BertConfig(num_labels=1)  # bert-base-uncased shape; STS-B is a regression task
-        model = BertForSequenceClassification(cfg).to(device)
-        ids = torch.randint(0, cfg.vocab_size, (a.batch, a.seq), device=device)
-        mask = torch.ones_like(ids)
-        y = torch.rand(a.batch, device=device) * 5
+    cfg = BertConfig(num_labels=1)  # bert-base-uncased shape; STS-B is a regression task
+    model = BertForSequenceClassification(cfg).to(device)
+    ids = torch.randint(0, cfg.vocab_size, (batch, seq), device=device)
+    mask = torch.ones_like(ids)
+    y = torch.rand(batch, device=device) * 5
 
-        def loss_fn(m):
-            return m(input_ids=ids, attention_mask=mask, labels=y).loss
+    def loss_fn(m):
+        return m(input_ids=ids, attention_mask=mask, labels=y).loss
 
-        unit, per_step = "seq/s", a.batch
-    return model, loss_fn, unit, per_step
+    return model, loss_fn, "seq/s"
 
 
-def main():
-    a = parse()
-    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    torch.manual_seed(1234 + rank)  # the reference seeds nothing: per-rank rounding streams
+def run_training(model_name="resnet34", batch=32, image=224, seq=128, compress="smart", steps=50, warmup=10,
+                 device=None, world=1, local=0, codec="b200", only=DATA_STRUCTURES, batched_optimizer=True,
+                 packed_activations=False, compress_loss_flag=False, profile=False, seed=1234, clocks=None):
+    """`steps` timed training steps after `warmup` untimed ones; returns a dict (device-timed, max over ranks)."""
+    from smart_compress.util.pytorch.autograd import packed_saved_tensors
+    from smart_compress.util.train import build_compression, compress_loss, compression_argv, parse_compression_args
 
-    from smart_compress.util.pytorch.autograd import register_autograd_module
-    from smart_compress.util.pytorch.hooks import wrap_optimizer
-
-    codec, hp = codec_and_hparams(a.compress, set(a.only.split(",")))
+    rank = int(os.environ.get("RANK", 0))
+    torch.manual_seed(seed + rank)  # the reference seeds nothing: per-rank rounding streams (SURVEY §5)
+    argv = compression_argv(compress, only=list(only), extra=["--compress_loss"] if compress_loss_flag else [])
+    if compress == "fp32":
+        argv.append("--no_compress")
+    hp = parse_compression_args(argv)
     calls = Counter()
 
     class Counting:  # counts calls per tag; forwards compress_many when allowed
         def __init__(self, inner):
             self.inner = inner
-            if hasattr(inner, "compress_many") and not a.no_batched_optimizer:
+            if hasattr(inner, "compress_many") and batched_optimizer:
                 self.compress_many = self._many
 
         def __call__(self, t, tag=None, **kw):
@@ -120,32 +132,36 @@ def main():
             calls[f"{tag} (batched)"] += len(tensors)
             return self.inner.compress_many(tensors, kwargs_list, tag=tag)
 
-    fn = Counting(codec)
-    model, loss_fn, unit, per_step = build_model(a, device)
-    if hp.compress_forward or hp.compress_backward:
-        model = register_autograd_module(model, fn, hp)
+    model, loss_fn, unit = build_model(model_name, batch, image, seq, device)
     # reference models/base.py:137-150: BatchNorm2d parameters never have their weights compressed
     bn = [p for m in model.modules() if type(m) == nn.BatchNorm2d for p in m.parameters(recurse=False)]
     rest = [p for m in model.modules() if type(m) != nn.BatchNorm2d for p in m.parameters(recurse=False)]
     groups = [dict(params=bn, no_weight_compression=True), dict(params=rest)] if bn else [dict(params=rest)]
-    if a.model.startswith("resnet"):
+    if model_name.startswith("resnet"):
         inner = torch.optim.SGD(groups, lr=0.1, momentum=0.9, weight_decay=0)
     else:
         inner = torch.optim.AdamW(groups, lr=2e-5)
-    opt = wrap_optimizer(inner, fn, hp) if a.compress != "fp32" else inner
+
+    if codec == "reference-eager":
+        assert compress == "smart"
+        hp.compression_cls = ReferenceEagerSmaQ
+    # util/train.py:197-213 + models/base.py:152-157, with the call counter between the hooks and the codec
+    real_cls = hp.compression_cls
+    hp.compression_cls = lambda args: Counting(real_cls(args))
+    fn, model, opt = build_compression(hp, model, inner)
+    pack_codec = None
+    if packed_activations:
+        from smart_compress.compress.smart import SmartFP
+
+        pack_codec = fn.inner if isinstance(getattr(fn, "inner", None), SmartFP) else SmartFP(parse_compression_args(["--compress", "smart"]))
     net = nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
-
-    import contextlib
-
-    from smart_compress.util.pytorch.autograd import packed_saved_tensors
-
-    pack_codec = codec if hasattr(codec, "encode") else codec_and_hparams("smart", set())[0]
 
     def closure():
         opt.zero_grad(set_to_none=True)
-        ctx = packed_saved_tensors(pack_codec) if a.packed_activations else contextlib.nullcontext()
+        ctx = packed_saved_tensors(pack_codec) if packed_activations else contextlib.nullcontext()
         with ctx:
             loss = loss_fn(net)
+        compress_loss(loss, fn, hp)   # models/base.py:114-115
         loss.backward()
         return loss
 
@@ -154,56 +170,88 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(a.warmup):
+    for _ in range(warmup):
         opt.step(closure)
     sync()
     calls.clear()
+    torch.cuda.reset_peak_memory_stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    last = None
-    for _ in range(a.steps):
-        last = opt.step(closure)
-    e1.record()
-    sync()
-    wall = time.perf_counter() - t0
+    with (clocks if clocks is not None else contextlib.nullcontext()):
+        t0 = time.perf_counter()
+        e0.record()
+        last = None
+        for _ in range(steps):
+            last = opt.step(closure)
+        e1.record()
+        sync()
+        wall = time.perf_counter() - t0
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms.item()) / a.steps
-    if rank == 0:
-        print(json.dumps({
-            "metric": f"{a.model}_train_{unit.replace('/', '_per_')}", "value": round(per_step * world / (ms_per_step / 1e3), 1),
-            "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms_per_step, 3),
-            "wall_ms_per_step": round(1e3 * wall / a.steps, 3), "higher_is_better": True, "scaling": "weak",
-            "dtype": "f32", "data": "synthetic", "loss": float(last),
-            "peak_memory_gib": round(torch.cuda.max_memory_allocated() / 2**30, 2),
-            "packed_activations": bool(a.packed_activations),
-            "config": {"workload": f"{a.model} random-init, synthetic batch {a.batch}/GPU" +
-                       (f" {a.image}x{a.image}" if a.model.startswith("resnet") else f" seq {a.seq}") +
-                       f", --compress {a.compress} on {a.only}", "optimizer": type(inner).__name__,
-                       "batched_optimizer_side": not a.no_batched_optimizer},
-            "codec_calls_per_step": {k: v // a.steps for k, v in sorted(calls.items(), key=lambda kv: str(kv[0]))},
-        }))
-    if a.profile and rank == 0:
-        from torch.profiler import ProfilerActivity, profile
+    ms_per_step = float(ms.item()) / steps
+    out = {
+        "value": round(batch * world / (ms_per_step / 1e3), 1), "unit": unit, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": round(ms_per_step, 3), "wall_ms_per_step": round(1e3 * wall / steps, 3),
+        "loss": float(last), "peak_memory_gib": round(torch.cuda.max_memory_allocated() / 2**30, 2),
+        "workload": f"{model_name} random-init, synthetic batch {batch}/GPU" +
+                    (f" {image}x{image}" if model_name.startswith("resnet") else f" seq {seq}") +
+                    f", --compress {compress} on {','.join(only)}" + (" [reference eager torch-CUDA ops]" if codec == "reference-eager" else ""),
+        "optimizer": type(inner).__name__,
+        "codec_calls_per_step": {str(k): v // steps for k, v in sorted(calls.items(), key=lambda kv: str(kv[0]))},
+    }
+    if profile and rank == 0:
+        out["profile"] = profile_steps(opt, closure, ms_per_step)
+    del net, model, opt, inner
+    torch.cuda.empty_cache()
+    return out
 
-        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-            for _ in range(3):
-                opt.step(closure)
-            torch.cuda.synchronize()
-        ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
-        busy = sum(e.device_time for e in ev) / 3e3
-        ours = sum(e.device_time for e in ev if "smaq" in e.name or "floatq" in e.name) / 3e3
-        print(f"[profile] GPU busy {busy:.3f} ms/step of {ms_per_step:.3f}; codec kernels {ours:.3f} ms/step; "
-              f"{len(ev) // 3} GPU ops/step", file=sys.stderr)
-        agg = Counter()
-        cnt = Counter()
-        for e in ev:
-            agg[e.name[:70]] += e.device_time / 3e3
-            cnt[e.name[:70]] += 1
-        for k, v in agg.most_common(14):
-            print(f"[profile] {v:8.3f} ms  x{cnt[k] // 3:<4d} {k}", file=sys.stderr)
+
+def profile_steps(opt, closure, ms_per_step, n=3):
+    """GPU-busy time, codec-kernel time, NCCL time and the top kernels of `n` more steps (torch.profiler / CUPTI)."""
+    from torch.profiler import ProfilerActivity, profile
+
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        for _ in range(n):
+            opt.step(closure)
+        torch.cuda.synchronize()
+    ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    per = 1e3 * n
+    busy = sum(e.device_time for e in ev) / per
+    ours = sum(e.device_time for e in ev if "smaq" in e.name or "floatq" in e.name) / per
+    nccl = sum(e.device_time for e in ev if "nccl" in e.name.lower()) / per
+    agg, cnt = Counter(), Counter()
+    for e in ev:
+        agg[e.name[:70]] += e.device_time / per
+        cnt[e.name[:70]] += 1
+    return {"gpu_busy_ms_per_step": round(busy, 3), "codec_kernels_ms_per_step": round(ours, 3),
+            "nccl_kernels_ms_per_step": round(nccl, 3), "step_ms": round(ms_per_step, 3), "gpu_ops_per_step": len(ev) // n,
+            "top": [{"ms": round(v, 3), "count": cnt[k] // n, "kernel": k} for k, v in agg.most_common(14)]}
+
+
+def main():
+    a = parse()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    r = run_training(a.model, a.batch, a.image, a.seq, a.compress, a.steps, a.warmup, device, world, local,
+                     codec=a.codec, only=tuple(a.only.split(",")), batched_optimizer=not a.no_batched_optimizer,
+                     packed_activations=a.packed_activations, compress_loss_flag=a.compress_loss, profile=a.profile)
+    if rank == 0:
+        prof = r.pop("profile", None)
+        line = {"metric": f"{a.model}_train_{r['unit'].replace('/', '_per_')}", **r, "higher_is_better": True,
+                "scaling": "weak", "dtype": "f32", "data": "synthetic", "packed_activations": bool(a.packed_activations),
+                "config": {"workload": r["workload"], "optimizer": r["optimizer"],
+                           "batched_optimizer_side": not a.no_batched_optimizer}}
+        print(json.dumps(line))
+        if prof:
+            print(f"[profile] GPU busy {prof['gpu_busy_ms_per_step']} ms/step of {prof['step_ms']}; codec kernels "
+                  f"{prof['codec_kernels_ms_per_step']} ms/step; NCCL {prof['nccl_kernels_ms_per_step']} ms/step; "
+                  f"{prof['gpu_ops_per_step']} GPU ops/step", file=sys.stderr)
+            for t in prof["top"]:
+                print(f"[profile] {t['ms']:8.3f} ms  x{t['count']:<4d} {t['kernel']}", file=sys.stderr)
     if world > 1:
         dist.destroy_process_group()
 
