@@ -491,6 +491,18 @@ def train_block(args, device, world, local):
     ref_steps, ref_warm = max(3, args.train_steps // 5), max(2, args.train_warmup // 5)
     eager = run_training(compress="smart", codec="reference-eager", steps=ref_steps, warmup=ref_warm, **cfg)
     prof = smart.pop("profile", None)
+    config3 = None
+    if world == 1:
+        # BASELINE configs[2]: ResNet-18 on CIFAR-shaped input, batch 256 — bound by the HOST when run eagerly
+        # (360 codec calls + ~600 framework launches per 8 ms step), so also as one CUDA graph per step (§8 f-1)
+        c3 = dict(model_name="resnet18", batch=256, image=32, device=device, world=1, local=local)
+        e = run_training(compress="smart", steps=args.train_steps, warmup=args.train_warmup, **c3)
+        gph = run_training(compress="smart", steps=args.train_steps, warmup=args.train_warmup, cuda_graph=True, **c3)
+        pl = run_training(compress="fp32", steps=args.train_steps, warmup=args.train_warmup, **c3)
+        plg = run_training(compress="fp32", steps=args.train_steps, warmup=args.train_warmup, cuda_graph=True, **c3)
+        config3 = {"workload": e["workload"], "img_per_s_eager": e["value"], "img_per_s_cuda_graph": gph["value"],
+                   "plain_img_per_s_eager": pl["value"], "plain_img_per_s_cuda_graph": plg["value"],
+                   "codec_calls_per_step": e["codec_calls_per_step"], "steps": args.train_steps}
     return {
         "metric": "resnet34_train_img_per_s", "unit": "img/s", "n_gpus": world,
         "img_per_s": smart["value"], "ms_per_step": smart["ms_per_step"],
@@ -506,7 +518,7 @@ def train_block(args, device, world, local):
                    "stem": "reference CIFAR stem (3x3 stride 1; SURVEY.md H10): 52.7 M feature-map elements per image"},
         "codec_calls_per_step": smart["codec_calls_per_step"],
         "peak_memory_gib": smart["peak_memory_gib"], "plain_peak_memory_gib": plain["peak_memory_gib"],
-        "loss": smart["loss"], "clocks": clocks.summary(),
+        "loss": smart["loss"], "clocks": clocks.summary(), "config3_resnet18_cifar": config3,
         "profile": None if prof is None else {k: prof[k] for k in ("gpu_busy_ms_per_step", "codec_kernels_ms_per_step",
                                                                     "nccl_kernels_ms_per_step", "gpu_ops_per_step")},
     }

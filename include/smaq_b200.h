@@ -29,7 +29,7 @@ extern "C" {
 
 #define SMAQ_B200_ABI_VERSION 4 /* 2: packed stream SQB2, count_saturated, smaq_compress, tensor_desc.stream; 3: smaq_float_quantize_multi;
                                     4: smaq_roundtrip_bn, smaq_roundtrip_multi(mean_std_out), range_std in the sampled statistics,
-                                       packed stream SQB3 (one-pass encoder, smaq_encode_workspace_init) */
+                                       packed stream SQB3 (one-pass encoder, smaq_encode_workspace_init), offset_base + smaq_counter_add */
 
 typedef void* smaq_stream_t; /* cudaStream_t */
 
@@ -65,9 +65,20 @@ typedef struct smaq_codec_params {
   int32_t count_saturated; /* packed encoder only: fill header.n_saturated (costs ~5 % of the encode
                            kernel; the plugin sets it under --measure_compression_ratio).  0: the
                            header field is all ones */
+  int32_t zero_on_grid; /* packed encoder only (not in the reference): move the mean the codes are relative to by at
+                           most half a quantisation step so that x == 0.0 lies exactly on the grid and decodes to
+                           exactly 0.0 (smaq_packed_header.mean holds the mean used).  For saved ReLU outputs, whose
+                           backward mask is `output > 0`.  Applies when |0 - mean| <= outlier range; else no-op */
   uint64_t seed;        /* Philox4x32-7 key, used when stochastic && probs == NULL */
   uint64_t offset;      /* Philox stream offset (added to the counter's high words) */
+  const uint64_t* offset_base; /* optional DEVICE counter: the stream is offset + *offset_base, read by the kernel.
+                           What lets a training step be captured in a CUDA graph: the per-call offsets are baked into
+                           the graph, the base advances on the device between replays (smaq_counter_add). NULL: 0 */
 } smaq_codec_params;
+
+/* *counter += delta on `stream` (one thread).  Captured at the end of a graphed training step with delta = the
+ * number of random streams the step used, so every replay draws fresh numbers. */
+int smaq_counter_add(uint64_t* counter, uint64_t delta, smaq_stream_t stream);
 
 /* Full-tensor mean and standard deviation in one pass — replaces data.mean() and data.std()
  * (smart.py:130-132; two read passes there).  Welford chunks per thread, warp-shuffle and
@@ -216,6 +227,7 @@ typedef struct smaq_floatq_params {
   int32_t max_exp_bias;     /* max stored exponent = 127 + 2^(exp_bits-1) + max_exp_bias; 0 for qtorch 0.2.0 */
   int32_t reserved;
   uint64_t seed, offset;
+  const uint64_t* offset_base; /* as in smaq_codec_params */
 } smaq_floatq_params;
 int smaq_float_quantize(const float* x, float* y, int64_t n, const int32_t* rand_bits,
                         const smaq_floatq_params* params, smaq_stream_t stream);

@@ -195,6 +195,27 @@ def smaq_roundtrip(
     return SmaqResult(y=y, mean=mean, std=std_raw, hi=hi, lo=lo, code=code, extras={"z": z, "c": c, "probs": probs, "rng_rule": rng_rule})
 
 
+def snap_mean_to_zero(mean: torch.Tensor, std: torch.Tensor, cfg: SmaqConfig) -> torch.Tensor:
+    """NOT in the reference — the packed encoder's ``zero_on_grid`` option (csrc/params.cuh): the mean m' nearest to
+    ``mean`` for which x == 0 decodes to exactly 0: with c0 the integer code nearest to zero's scaled z-score,
+    m' = -(((c0 / range) - shift) * std), each step rounded to fp32 as smart.py:171-172 rounds it."""
+    mean = torch.as_tensor(mean, dtype=torch.float32)
+    std = torch.as_tensor(std, dtype=torch.float32)
+    std_dev = torch.ones_like(std) if std == 0 else std
+    t = cfg.main_std_dev_threshold
+    z0 = (torch.zeros_like(mean) - mean) / std_dev.clamp(*cfg.clamped_range)
+    if not bool(z0.abs() <= 1e30) or not bool(std_dev > 0) or not bool(std_dev.abs() <= 1e30):
+        return mean
+    hi, lo = z0 > t, z0 < -t
+    shift = (hi * -t) + (lo * t)
+    rng = torch.where(hi | lo, torch.tensor(cfg.range_outlier), torch.tensor(cfg.range_normal)).to(torch.float32)
+    lim = cfg.max_code_outlier if bool(hi | lo) else cfg.max_code_main
+    c0 = ((z0 + shift) * rng).round()
+    if not bool(c0.abs() <= lim):
+        return mean
+    return -(((c0 / rng) - shift) * std_dev)
+
+
 def compressed_bits(res: SmaqResult, cfg: SmaqConfig) -> int:
     """smart.py:184-187: the size the reference reports for one call."""
     n_out = int((res.hi | res.lo).sum())

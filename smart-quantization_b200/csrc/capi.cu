@@ -50,9 +50,17 @@ void set_dependent_launch(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr) {
   cfg.numAttrs = dependent_launch_enabled() ? 1 : 0;
 }
 
+__global__ void counter_add_kernel(unsigned long long* counter, unsigned long long delta) { *counter += delta; }
+
 }  // namespace smaq
 
 extern "C" {
+int smaq_counter_add(uint64_t* counter, uint64_t delta, smaq_stream_t stream) {
+  if (!counter) return smaq::fail(SMAQ_ERR_ARG, "counter_add: null pointer");
+  smaq::counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)counter, (unsigned long long)delta);
+  SMAQ_LAUNCH_OK();
+  return SMAQ_OK;
+}
 int smaq_b200_abi_version(void) { return SMAQ_B200_ABI_VERSION; }
 const char* smaq_b200_last_error(void) { return smaq::last_error_buf(); }
 int smaq_b200_sm_count(void) { return smaq::sm_count(); }

@@ -488,7 +488,7 @@ template <int PM, int XB, bool kStochastic, bool kHasProbs, bool kCountSat>
 #endif
 __global__ void __launch_bounds__(kPackThreads, SMAQ_ENC_CTAS)
     encode_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ mean_std,
-                  const float* __restrict__ probs, const __grid_constant__ KernelParams kp,
+                  const float* __restrict__ probs, const __grid_constant__ KernelParams kp_,
                   uint32_t* __restrict__ planes, uint32_t* __restrict__ extras, EncodeWs* __restrict__ ws,
                   long long n_cta_tiles, int tiles_per_cta, int aligned, HeaderArgs ha) {
   constexpr int kSeg = seg_words(XB);
@@ -500,6 +500,7 @@ __global__ void __launch_bounds__(kPackThreads, SMAQ_ENC_CTAS)
   __shared__ Hot s_hot;
   __shared__ bool s_last;
 
+  const KernelParams kp = resolved(kp_);
   const int lane = lane_id(), warp = warp_id();
   const uint32_t seg_addr = smem_u32(&s_seg[warp][0]);
   if (lane == 0) {
@@ -545,7 +546,9 @@ __global__ void __launch_bounds__(kPackThreads, SMAQ_ENC_CTAS)
 
   // per-tensor constants: derived once per CTA (IEEE divisions, a search loop) and broadcast
   if (threadIdx.x == 0) {
-    s_scalars = scalars_from(mean_std[0], mean_std[1], kp);
+    float mean = mean_std[0];
+    if (kp.zero_on_grid) mean = snap_mean_to_zero(mean, mean_std[1], kp);  // the same in every CTA
+    s_scalars = scalars_from(mean, mean_std[1], kp);
     s_hot = make_hot(s_scalars);
   }
   __syncthreads();
@@ -654,7 +657,7 @@ __global__ void __launch_bounds__(kPackThreads, SMAQ_ENC_CTAS)
     hdr->bits_outlier = kp.bits_outlier;
     hdr->stochastic = ha.stochastic;
     hdr->n = ha.n;
-    hdr->mean = mean_std[0];
+    hdr->mean = s.mean;  // the mean the codes are relative to (zero_on_grid may have moved it)
     hdr->std_raw = mean_std[1];
     hdr->threshold = kp.thr;
     hdr->range_main = kp.range_main;

@@ -371,7 +371,8 @@ template <bool kStochastic, bool kHasProbs, bool kAllPos, bool kSaturate>
 __global__ void __launch_bounds__(kRtThreads, 3) roundtrip_kernel(const float* x, float* y, int64_t n,
                                                                const float* __restrict__ mean_std,
                                                                const float* __restrict__ probs,
-                                                               const __grid_constant__ KernelParams kp) {
+                                                               const __grid_constant__ KernelParams kp_) {
+  const KernelParams kp = resolved(kp_);
   const Scalars s = scalars_from(mean_std[0], mean_std[1], kp);
   RtFirst none;  // unused: the body issues its own first loads
   roundtrip_tensor<kStochastic, kHasProbs, kAllPos, kSaturate, false>(x, y, n, probs, kp, s, none);
@@ -387,7 +388,8 @@ template <bool kStochastic, bool kHasProbs, bool kAllPos>
 __global__ void __launch_bounds__(kRtThreads, 3) roundtrip_after_stats_kernel(const float* x, float* y, int64_t n,
                                                                              const float* mean_std,
                                                                              const float* __restrict__ probs,
-                                                                             const __grid_constant__ KernelParams kp) {
+                                                                             const __grid_constant__ KernelParams kp_) {
+  const KernelParams kp = resolved(kp_);
   const RtFirst first = roundtrip_first_loads<kStochastic && kHasProbs>(x, probs, n);
   asm volatile("griddepcontrol.wait;" ::: "memory");
   float mean, std_raw;  // not through the read-only path, not before the wait
@@ -402,7 +404,8 @@ template <bool kStochastic, bool kHasProbs>
 __global__ void __launch_bounds__(kRtThreads) roundtrip_unaligned_kernel(const float* x, float* y, int64_t n,
                                                                          const float* __restrict__ mean_std,
                                                                          const float* __restrict__ probs,
-                                                                         const __grid_constant__ KernelParams kp) {
+                                                                         const __grid_constant__ KernelParams kp_) {
+  const KernelParams kp = resolved(kp_);
   const Scalars s = scalars_from(mean_std[0], mean_std[1], kp);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = roundtrip_element<kStochastic, kHasProbs>(x, probs, i, s, kp);
@@ -420,7 +423,8 @@ __global__ void __launch_bounds__(kRtThreads) roundtrip_bn_kernel(const float* x
                                                                   const float* __restrict__ probs,
                                                                   const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta, int64_t channels,
-                                                                  int64_t inner, const __grid_constant__ KernelParams kp) {
+                                                                  int64_t inner, const __grid_constant__ KernelParams kp_) {
+  const KernelParams kp = resolved(kp_);
   const Scalars s = scalars_from(mean_std[0], mean_std[1], kp);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t c = channels == 1 ? 0 : (i / inner) % channels;
@@ -483,8 +487,9 @@ __device__ __forceinline__ void small_body(const float* x, float* y, int64_t n, 
 template <bool kStochastic, bool kHasProbs>
 __global__ void __launch_bounds__(kStatsThreads) roundtrip_small_kernel(const float* x, float* y, int64_t n,
                                                                         const float* probs,
-                                                                        const __grid_constant__ KernelParams kp,
+                                                                        const __grid_constant__ KernelParams kp_,
                                                                         float* mean_std_out) {
+  const KernelParams kp = resolved(kp_);
   __shared__ Acc smem[kStatsThreads / 32];
   __shared__ float bcast[2];
   small_body<kStochastic, kHasProbs>(x, y, n, probs, kp, mean_std_out, smem, bcast);
@@ -494,8 +499,9 @@ __global__ void __launch_bounds__(kStatsThreads) roundtrip_small_kernel(const fl
 template <bool kStochastic>
 __global__ void __launch_bounds__(kStatsThreads) multi_small_kernel(const smaq_tensor_desc* __restrict__ descs,
                                                                     int count, int64_t min_size,
-                                                                    const __grid_constant__ KernelParams kp,
+                                                                    const __grid_constant__ KernelParams kp_,
                                                                     float* __restrict__ mean_std_out) {
+  const KernelParams kp = resolved(kp_);
   __shared__ Acc smem[kStatsThreads / 32];
   __shared__ float bcast[2];
   for (int t = blockIdx.x; t < count; t += gridDim.x) {
@@ -614,8 +620,9 @@ __device__ __forceinline__ void multi_apply_chunk(const float* x, float* y, int6
 
 template <bool kStochastic>
 __global__ void __launch_bounds__(kStatsThreads) multi_apply_kernel(const smaq_tensor_desc* __restrict__ descs, int count,
-                                                                    MultiWs ws, const __grid_constant__ KernelParams kp,
+                                                                    MultiWs ws, const __grid_constant__ KernelParams kp_,
                                                                     float* __restrict__ mean_std_out) {
+  const KernelParams kp = resolved(kp_);
   __shared__ Acc smem[kStatsThreads / 32];
   const int item = blockIdx.x;
   if (item >= ws.prefix[count]) return;
@@ -671,8 +678,9 @@ __global__ void __launch_bounds__(kStatsThreads) multi_apply_kernel(const smaq_t
 // --measure_compression_ratio only: how many elements classify as outliers.
 __global__ void __launch_bounds__(kRtThreads) count_outliers_kernel(const float* __restrict__ x, int64_t n,
                                                                     const float* __restrict__ mean_std,
-                                                                    const __grid_constant__ KernelParams kp,
+                                                                    const __grid_constant__ KernelParams kp_,
                                                                     unsigned long long* counter) {
+  const KernelParams kp = resolved(kp_);
   const Scalars s = scalars_from(mean_std[0], mean_std[1], kp);
   unsigned int local = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {

@@ -41,8 +41,10 @@ class CodecParams(C.Structure):  # smaq_codec_params
         ("all_positive", C.c_int32),
         ("saturate", C.c_int32),
         ("count_saturated", C.c_int32),
+        ("zero_on_grid", C.c_int32),
         ("seed", C.c_uint64),
         ("offset", C.c_uint64),
+        ("offset_base", C.c_void_p),
     ]
 
 
@@ -56,6 +58,7 @@ class FloatqParams(C.Structure):  # smaq_floatq_params
         ("reserved", C.c_int32),
         ("seed", C.c_uint64),
         ("offset", C.c_uint64),
+        ("offset_base", C.c_void_p),
     ]
 
 
@@ -117,6 +120,7 @@ _SIGNATURES = {
     "smaq_b200_abi_version": (C.c_int, []),
     "smaq_b200_last_error": (C.c_char_p, []),
     "smaq_b200_sm_count": (C.c_int, []),
+    "smaq_counter_add": (C.c_int, [_P, C.c_uint64, _P]),
     "smaq_stats_workspace_bytes": (C.c_size_t, [_I64]),
     "smaq_stats_full": (C.c_int, [_P, _I64, C.c_int, _P, _P, C.c_size_t, _P]),
     "smaq_stats_range": (C.c_int, [_P, _I64, _P, _P, C.c_size_t, _P]),
@@ -230,6 +234,94 @@ def on_device_of(t: torch.Tensor):
 def wrong_device(t: torch.Tensor) -> bool:
     index = t.device.index
     return index is not None and index != _get_device()
+
+
+# ---- random-stream numbering that survives CUDA-graph replay ---------------------------------------------------
+# Every codec call draws its own Philox stream.  Eagerly the stream number is a host counter passed by value; in a
+# captured training step that value is baked into the graph, so every replay would round with the same numbers.
+# Inside ``counted_step(device)`` the calls are numbered 0, 1, 2 ... from the start of the step and the kernels add
+# a DEVICE counter to that number (smaq_codec_params.offset_base); when the step ends the counter is advanced by the
+# number of streams used (smaq_counter_add, one thread, enqueued on the current stream — captured with the step).
+# Eager execution and graph replay therefore draw the same numbers, step for step.
+class StepCounter:
+    def __init__(self, device):
+        self.base = torch.zeros(1, dtype=torch.int64, device=device)   # read by the kernels as uint64
+        self.calls = 0
+
+    def next(self, count: int = 1) -> int:
+        first = self.calls
+        self.calls += count
+        return first
+
+    @property
+    def base_ptr(self) -> int:
+        return self.base.data_ptr()
+
+
+_step_counters = {}   # device index -> StepCounter (created once per device: graphs hold its address)
+_active_counters = {}  # device index -> StepCounter, while inside counted_step
+
+
+def active_counter():
+    """The StepCounter of the current device if a counted step is open, else None (one dict lookup)."""
+    if not _active_counters:
+        return None
+    return _active_counters.get(_get_device())
+
+
+class counted_step:
+    """``with counted_step(device): loss = opt.step(closure)`` — see above.  Re-entrant per device is an error."""
+
+    def __init__(self, device=None):
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.index = device.index if device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", self.index)
+
+    def __enter__(self):
+        if self.index in _active_counters:
+            raise RuntimeError("counted_step is already open on this device")
+        sc = _step_counters.get(self.index)
+        if sc is None:
+            sc = _step_counters[self.index] = StepCounter(self.device)
+        sc.calls = 0
+        _active_counters[self.index] = sc
+        return sc
+
+    def __exit__(self, *exc):
+        sc = _active_counters.pop(self.index)
+        if exc[0] is None and sc.calls:
+            with torch.cuda.device(self.index):
+                check(load().smaq_counter_add(sc.base_ptr, sc.calls, stream_ptr(self.index)), "smaq_counter_add")
+        return False
+
+
+# Pinned staging for descriptor uploads made WHILE A GRAPH IS BEING CAPTURED: the captured host-to-device copy reads
+# its source at every replay, and allocating pinned memory during capture is not allowed — so slices of one arena,
+# allocated at the first (eager) batched call and never freed.
+_ARENA_BYTES = 8 << 20
+_arena = None
+_arena_used = 0
+
+
+def ensure_pinned_arena():
+    global _arena
+    if _arena is None and not torch.cuda.is_current_stream_capturing():
+        _arena = torch.empty(_ARENA_BYTES, dtype=torch.uint8).pin_memory()
+
+
+def pinned_arena_take(payload: bytes) -> torch.Tensor:
+    global _arena_used
+    if _arena is None:
+        raise NativeLibraryError("a batched codec call must run once eagerly before it is captured in a CUDA graph "
+                                 "(the pinned staging arena is allocated then)")
+    n = len(payload)
+    start = (_arena_used + 63) // 64 * 64
+    if start + n > _ARENA_BYTES:
+        raise NativeLibraryError("pinned staging arena exhausted (too many captured descriptor uploads)")
+    _arena_used = start + n
+    view = _arena[start:start + n]
+    view.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
+    return view
 
 
 def ptr(t: torch.Tensor) -> int:

@@ -63,6 +63,7 @@ class SmartFP(CompressionAlgorithmBase):
         self._desc_cache = {}            # compress_many: device descriptor arrays by (pointers, sizes)
         self._multi_ws = {}
         self._encode_ws = {}             # (device, stream) -> the packed encoder's 64-byte scratch
+        self._graph_keep = []            # buffers a captured CUDA graph reads at replay
 
     def _derive(self, hp):
         # smart.py:75-84, evaluated in Python floats exactly as there
@@ -106,10 +107,21 @@ class SmartFP(CompressionAlgorithmBase):
         # the packed encoder counts what it clipped only when the size accounting is on (like the
         # reference, which only pays for its accounting under --measure_compression_ratio, base.py:79)
         p.count_saturated = 1 if getattr(hp, "measure_compression_ratio", False) else 0
+        p.zero_on_grid = 0
         # torch.manual_seed() governs the stream, as it governs the reference's rand_like
         p.seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
-        p.offset = next(self._calls) if offset is None else offset
+        sc = N.active_counter()   # inside N.counted_step(): numbered from the step's start + a device counter
+        if sc is None:
+            p.offset = next(self._calls) if offset is None else offset
+            p.offset_base = None
+        else:
+            p.offset = sc.next() if offset is None else offset
+            p.offset_base = sc.base_ptr
         return p
+
+    def _next_stream(self) -> int:
+        sc = N.active_counter()
+        return next(self._calls) if sc is None else sc.next()
 
     def statistics(self, flat: torch.Tensor, sample_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Device float[2] = (mean, std) per smart.py:130-134 — no host round trip."""
@@ -127,7 +139,7 @@ class SmartFP(CompressionAlgorithmBase):
                         "smaq_stats_sampled")
             elif k <= 1024:
                 N.check(lib.smaq_stats_sampled_draw(N.ptr(flat), n, k, rng, torch.initial_seed() & (2**64 - 1),
-                                                    (1 << 62) + next(self._calls), N.ptr(out), stream),
+                                                    (1 << 62) + self._next_stream(), N.ptr(out), stream),
                         "smaq_stats_sampled_draw")
             else:
                 idx = torch.randperm(n, device=flat.device)[:k]
@@ -290,9 +302,9 @@ class SmartFP(CompressionAlgorithmBase):
                 results[i] = self(t, tag=tag, **kw)  # comes back untouched (smart.py:125-128)
                 continue
             if first is None:
-                first = next(self._calls)
+                first = self._next_stream()
             else:
-                next(self._calls)
+                self._next_stream()
             stream_no = numbered
             numbered += 1
             ok = (not per_tensor and t.is_cuda and t.dtype == torch.float32
@@ -323,11 +335,20 @@ class SmartFP(CompressionAlgorithmBase):
                 host[j].n = t.numel()
                 host[j].all_positive = int(ap)
                 host[j].stream = sn
-            raw = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).pin_memory()
+            N.ensure_pinned_arena()
+            capturing = torch.cuda.is_current_stream_capturing()
+            raw = (N.pinned_arena_take(bytes(host)) if capturing
+                   else torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).pin_memory())
             descs = raw.to(device, non_blocking=True)
-            if len(self._desc_cache) > 64:
-                self._desc_cache.clear()
-            self._desc_cache[key] = descs
+            if capturing:
+                # the captured copy reads `raw` at every replay: both live as long as the codec
+                self._graph_keep.append((raw, descs))
+            else:
+                if len(self._desc_cache) > 64:
+                    self._desc_cache.clear()
+                self._desc_cache[key] = (descs, raw)
+        else:
+            descs = descs[0]
         params = self._params(all_positive=False, offset=first)
         total = sum(t.numel() for _, t, _, _ in batch)
         need = lib.smaq_multi_workspace_bytes(len(batch), total)
@@ -352,7 +373,9 @@ class SmartFP(CompressionAlgorithmBase):
     @torch.no_grad()
     def encode(self, data: torch.Tensor, mean_std: Optional[torch.Tensor] = None, **extra):
         """Quantise and PACK ``data`` (6-bit main / 8-bit outlier codes with the default flags) into a
-        device buffer; statistics as in ``__call__`` unless ``mean_std`` (device float[2]) is given."""
+        device buffer; statistics as in ``__call__`` unless ``mean_std`` (device float[2]) is given.
+        ``zero_on_grid=True`` (not in the reference): the mean is moved by at most half a step so that exact zeros
+        decode to exact zeros — for saved ReLU outputs (``packed_saved_tensors``)."""
         from .packed import PackedSmaq, packed_layout
 
         N.require_cuda_f32(data, "SmartFP.encode")
@@ -375,6 +398,7 @@ class SmartFP(CompressionAlgorithmBase):
             ws = self._encode_ws[key] = torch.empty(max(int(lay.workspace_bytes), 64), dtype=torch.uint8, device=data.device)
             N.check(lib.smaq_encode_workspace_init(N.ptr(ws), ws.numel(), stream), "smaq_encode_workspace_init")
         params = self._params(all_positive=False)
+        params.zero_on_grid = 1 if extra.get("zero_on_grid") else 0
         probs = extra.get("_probs")
         probs_ptr = None
         if probs is not None:

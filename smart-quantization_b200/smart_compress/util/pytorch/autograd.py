@@ -85,19 +85,20 @@ class packed_saved_tensors(torch.autograd.graph.saved_tensors_hooks):
         loss.backward()
 
     Parameters, small tensors (< ``min_numel``) and anything that is not CUDA fp32 are saved as they are.
-    Caveat: SmaQ has no exact zero, so a saved ReLU *output* comes back with its zeros rounded to small
-    values of either sign and the backward mask ``output > 0`` is wrong for about half of the dead units;
-    pass ``keep=`` to leave such tensors alone (e.g. ``keep=lambda t: bool((t == 0).any())`` at the price of
-    a synchronisation), or use it with smooth activations.
+    Exact zeros survive: SmaQ's grid has no point at 0.0 in general, and a saved ReLU *output* whose zeros came back as
+    small values of either sign would give the backward mask ``output > 0`` wrong for half of the dead units (round 1
+    did).  The encoder is therefore asked to put zero ON the grid (``zero_on_grid``: the mean the codes are relative
+    to moves by at most half a quantisation step, on the device, no synchronisation), so 0.0 decodes to exactly 0.0.
+    ``keep=`` still leaves chosen tensors alone.
     Encoding and decoding run on the calling thread's current stream (the backward pass decodes on
-    autograd's worker thread).  Nothing synchronises: buffers are capacity-sized."""
+    autograd's worker thread).  Nothing synchronises: buffers are capacity-sized (8 bits per element)."""
 
-    def __init__(self, codec, min_numel: int = 1 << 16, keep=None):
+    def __init__(self, codec, min_numel: int = 1 << 16, keep=None, zero_on_grid: bool = True):
         def pack(t: torch.Tensor):
             if (isinstance(t, nn.Parameter) or not t.is_cuda or t.dtype != torch.float32 or t.numel() < min_numel
                     or (keep is not None and keep(t))):
                 return t
-            return codec.encode(t.detach())
+            return codec.encode(t.detach(), zero_on_grid=zero_on_grid)
 
         def unpack(obj):
             if isinstance(obj, torch.Tensor):

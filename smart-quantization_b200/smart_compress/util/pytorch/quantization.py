@@ -84,8 +84,16 @@ def make_floatq_params(exp: int, man: int, hparams, rounding: str = "stochastic"
     p.check_inf = int(bool(getattr(hparams, "float_quantize_check_inf", True)))
     p.max_exp_bias = 0  # qtorch 0.2.0 rule (oracle/floatq.py)
     p.seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
-    p.offset = next(_calls)
+    p.offset, p.offset_base = _next_stream()
     return p
+
+
+def _next_stream():
+    """(stream number, device counter or None): see _native.counted_step."""
+    sc = N.active_counter()
+    if sc is None:
+        return next(_calls), None
+    return sc.next(), sc.base_ptr
 
 
 def float_quantize(x: torch.Tensor, exp: int, man: int, hparams, rand_bits: torch.Tensor = None):
@@ -109,6 +117,7 @@ def float_quantize(x: torch.Tensor, exp: int, man: int, hparams, rand_bits: torc
 
 _multi_cache = {}   # (device, tensors' pointers and sizes) -> device array of smaq_tensor_desc
 _multi_ws = {}      # device -> grow-only scratch
+_graph_keep = []    # buffers a captured CUDA graph reads at replay
 
 
 def float_quantize_many(tensors, exp: int, man: int, hparams):
@@ -127,7 +136,7 @@ def float_quantize_many(tensors, exp: int, man: int, hparams):
         if is_16_bit or not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()) or t.numel() == 0:
             results[i] = float_quantize(t, exp, man, hparams)   # draws its own stream number
             continue
-        no = next(_calls)
+        no = _next_stream()[0]
         if first is None:
             first = no
         batch.append((i, t, no - first))
@@ -147,11 +156,19 @@ def float_quantize_many(tensors, exp: int, man: int, hparams):
             host[j].n = t.numel()
             host[j].all_positive = 0
             host[j].stream = sn
-        raw = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).pin_memory()
+        N.ensure_pinned_arena()
+        capturing = torch.cuda.is_current_stream_capturing()
+        raw = (N.pinned_arena_take(bytes(host)) if capturing
+               else torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).pin_memory())
         descs = raw.to(device, non_blocking=True)
-        if len(_multi_cache) > 64:
-            _multi_cache.clear()
-        _multi_cache[key] = descs
+        if capturing:
+            _graph_keep.append((raw, descs))   # the captured copy reads `raw` at every replay
+        else:
+            if len(_multi_cache) > 64:
+                _multi_cache.clear()
+            _multi_cache[key] = (descs, raw)
+    else:
+        descs = descs[0]
     params = make_floatq_params(exp, man, hparams)
     params.offset = first      # make_floatq_params drew one more number: harmless, the streams stay distinct
     need = lib.smaq_floatq_multi_workspace_bytes(len(batch))

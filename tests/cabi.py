@@ -6,7 +6,8 @@ import torch
 from smart_compress import _native as N
 
 
-def codec_params(cfg, *, all_positive=False, saturate=False, seed=1234, offset=0, count_saturated=True) -> N.CodecParams:
+def codec_params(cfg, *, all_positive=False, saturate=False, seed=1234, offset=0, count_saturated=True,
+                 zero_on_grid=False) -> N.CodecParams:
     """oracle SmaqConfig -> smaq_codec_params (the host-side float->fp32 narrowing happens in ctypes)."""
     p = N.CodecParams()
     p.threshold = cfg.main_std_dev_threshold
@@ -18,6 +19,7 @@ def codec_params(cfg, *, all_positive=False, saturate=False, seed=1234, offset=0
     p.all_positive = int(all_positive)
     p.saturate = int(saturate)
     p.count_saturated = int(count_saturated)
+    p.zero_on_grid = int(zero_on_grid)
     p.seed, p.offset = seed, offset
     return p
 

@@ -215,8 +215,9 @@ def test_packed_saved_tensors_cut_activation_memory_and_keep_gradients_close():
 
     torch.manual_seed(3)
     codec = SmartFP(hparams())
-    # smooth activations: a packed ReLU output would lose its exact zeros, i.e. the backward mask (see the docstring)
-    net = nn.Sequential(nn.Conv2d(8, 32, 3, padding=1), nn.Tanh(), nn.Conv2d(32, 32, 3, padding=1), nn.Tanh(),
+    # a ReLU network: the saved ReLU outputs must keep their exact zeros (the backward mask is `output > 0`), which
+    # the encoder's zero_on_grid option guarantees
+    net = nn.Sequential(nn.Conv2d(8, 32, 3, padding=1), nn.ReLU(), nn.Conv2d(32, 32, 3, padding=1), nn.ReLU(),
                         nn.Conv2d(32, 8, 3, padding=1)).to(DEV)
     x = torch.randn(16, 8, 64, 64, device=DEV)
 
@@ -242,3 +243,95 @@ def test_packed_saved_tensors_cut_activation_memory_and_keep_gradients_close():
         assert bool(torch.isfinite(b).all())
         rel = float((a - b).norm() / a.norm())
         assert rel < 0.15, rel   # 6/8-bit activations: a few percent of gradient noise
+    # the same comparison WITHOUT zero_on_grid is what round 1 shipped: half of the dead units leak gradient
+    net.zero_grad()
+    with packed_saved_tensors(codec, min_numel=1 << 12, zero_on_grid=False):
+        loss = net(x).square().mean()
+    loss.backward()
+    leaky = max(float((a - p.grad).norm() / a.norm()) for a, p in zip(g_plain, net.parameters()))
+    tight = max(float((a - b).norm() / a.norm()) for a, b in zip(g_plain, g_packed))
+    assert tight < leaky, (tight, leaky)
+
+
+def _graph_train(codec_name, use_graph, steps=4):
+    """`steps` SGD steps of a small network with the codec on all five data structures, every step a counted step;
+    steps 2.. either eagerly or as replays of ONE captured CUDA graph."""
+    from smart_compress import _native as N
+    from smart_compress.util.train import build_compression, parse_compression_args
+
+    torch.manual_seed(21)
+    for sc in N._step_counters.values():
+        sc.base.zero_()
+    hp = parse_compression_args(["--compress", codec_name])
+    net = nn.Sequential(nn.Linear(96, 256), nn.Tanh(), nn.LayerNorm(256), nn.Linear(256, 300), nn.Tanh(),
+                        nn.Linear(300, 8)).to(DEV)
+    x = torch.randn(64, 96, device=DEV)
+    y = torch.randn(64, 8, device=DEV)
+    inner = torch.optim.SGD(net.parameters(), lr=0.05, momentum=0.9)
+    codec, net, opt = build_compression(hp, net, inner)
+
+    def closure():
+        opt.zero_grad(set_to_none=True)
+        loss = nn.functional.mse_loss(net(x), y)
+        loss.backward()
+        return loss
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with N.counted_step(DEV):
+            opt.step(closure)                      # step 1, eager: lazy optimizer state, workspaces, plans
+        side.synchronize()
+        if use_graph:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                with N.counted_step(DEV):
+                    opt.step(closure)              # capture only: nothing runs
+            for _ in range(steps - 1):
+                graph.replay()
+        else:
+            for _ in range(steps - 1):
+                with N.counted_step(DEV):
+                    opt.step(closure)
+        side.synchronize()
+    torch.cuda.current_stream().wait_stream(side)
+    counter = int(N._step_counters[torch.device(DEV).index].base.item())
+    return torch.cat([p.detach().flatten() for p in net.parameters()]).clone(), counter
+
+
+@pytest.mark.parametrize("codec_name", ["smart", "fp8"])
+def test_cuda_graph_replay_of_a_whole_training_step_matches_eager_bits(codec_name):
+    """§8 f-1: forward, backward, the hooks and the batched optimizer phases captured as ONE graph.  The random
+    streams are numbered from the start of the step plus a DEVICE counter the step advances, so replays draw fresh
+    numbers — the same ones eager execution draws: after four steps the weights are bit-identical, and so is the
+    counter.  Two replays of the same graph must differ from one another (not the baked-offset bug)."""
+    w_eager, c_eager = _graph_train(codec_name, use_graph=False)
+    w_graph, c_graph = _graph_train(codec_name, use_graph=True)
+    assert c_eager == c_graph and c_eager > 0
+    assert torch.equal(w_eager.view(torch.int32), w_graph.view(torch.int32))
+    w3, _ = _graph_train(codec_name, use_graph=True, steps=3)
+    assert not torch.equal(w3, w_graph)
+
+
+def test_counted_step_numbers_streams_from_a_device_counter():
+    """The kernels add *offset_base to the stream offset: a call with (offset 3, counter 5) equals a call with
+    (offset 8, no counter), for the round trip, the one-block kernel, the packed encoder and float_quantize."""
+    from oracle.smaq import SmaqConfig
+    from tests import cabi, cabi_pack
+
+    g = torch.Generator().manual_seed(1)
+    cfg = SmaqConfig()
+    counter = torch.tensor([5], dtype=torch.int64, device=DEV)
+    for n in (1000, 70001):
+        x = torch.randn(n, generator=g).to(DEV)
+        ms = cabi.stats_full(x)
+        a, b = cabi.codec_params(cfg, seed=9, offset=3), cabi.codec_params(cfg, seed=9, offset=8)
+        a.offset_base = counter.data_ptr()
+        assert torch.equal(cabi.roundtrip(x, ms, a), cabi.roundtrip(x, ms, b))
+        if n <= 32768:
+            assert torch.equal(cabi.roundtrip_small(x, a), cabi.roundtrip_small(x, b))
+        assert torch.equal(cabi_pack.encode(x, ms, a, cfg)[0], cabi_pack.encode(x, ms, b, cfg)[0])
+        fa, fb = cabi.floatq_params(5, 2, seed=9, offset=3), cabi.floatq_params(5, 2, seed=9, offset=8)
+        fa.offset_base = counter.data_ptr()
+        assert torch.equal(cabi.float_quantize(x, fa), cabi.float_quantize(x, fb))
+        assert not torch.equal(cabi.roundtrip(x, ms, a), cabi.roundtrip(x, ms, cabi.codec_params(cfg, seed=9, offset=3)))

@@ -152,6 +152,51 @@ def test_philox_encode_decode_equals_fused_roundtrip_and_is_deterministic():
     assert torch.equal(y.view(torch.int32), fused.view(torch.int32))
 
 
+@pytest.mark.parametrize("kind", ["relu", "relu_shifted", "lower_outlier", "far"])
+def test_zero_on_grid_keeps_exact_zeros_and_matches_the_oracle(kind):
+    """zero_on_grid (packed activation storage; not in the reference): the encoder moves the mean by at most half a
+    quantisation step so that 0.0 is a grid point.  The mean it used is the oracle's restatement of the rule bit
+    for bit; the stream is byte-identical to oracle/pack.py given that mean; and every exact zero decodes to
+    exactly 0.0 (up to the ~1e-6 of them whose scaled value rounds across an integer)."""
+    from oracle import rng as orng
+    from oracle.smaq import snap_mean_to_zero
+
+    g = torch.Generator().manual_seed(12)
+    n = 300007
+    x = torch.randn(n, generator=g)
+    if kind == "relu":
+        x = x.relu()                          # zero inside the main range (z0 ~ -0.68)
+    elif kind == "relu_shifted":
+        x = (x * 0.01 + 0.004).relu()
+    elif kind == "lower_outlier":
+        x = torch.where(torch.rand(n, generator=g) < 0.03, torch.zeros(n), x * 0.3 + 0.5)   # zero ~ 1.6 sigma below the mean
+    else:
+        x = torch.where(torch.rand(n, generator=g) < 0.001, torch.zeros(n), x * 0.05 + 3.0)  # zero far outside: no-op
+    cfg = SmaqConfig()
+    xd = x.to(DEV)
+    ms = cabi.stats_full(xd)
+    msc = ms.cpu()
+    buf, lay = cabi_pack.encode(xd, ms, cabi.codec_params(cfg, seed=31, offset=4, zero_on_grid=True), cfg)
+    hdr, _, _ = cabi_pack.sections(buf, lay)
+    want_mean = snap_mean_to_zero(msc[0], msc[1], cfg)
+    assert np.float32(hdr.mean).view(np.uint32) == want_mean.numpy().view(np.uint32), (hdr.mean, float(want_mean))
+    step = float(msc[1]) / 15
+    if kind == "far":
+        assert hdr.mean == float(msc[0])
+    else:
+        assert abs(hdr.mean - float(msc[0])) <= 0.51 * step * (42 / 15 if kind == "lower_outlier" else 1.0) + 1e-12
+    probs = torch.from_numpy(orng.probs_for(n, seed=31, offset=4))
+    res = smaq_roundtrip(x, cfg, probs=probs, mean=want_mean, std=msc[1], rng_rule=True)
+    cabi_pack.assert_stream_equals_oracle(buf, lay, opack.pack(res, cfg))
+    y = cabi_pack.decode(buf, lay).cpu()
+    zeros = x == 0
+    if kind != "far":
+        wrong = int((y[zeros] != 0).sum())
+        assert wrong <= max(2, int(2e-5 * int(zeros.sum()))), (wrong, int(zeros.sum()))
+    want = smaq_roundtrip(x, cfg, probs=probs, mean=want_mean, std=msc[1], rng_rule=True, saturate=True)
+    assert_bit_equal(y, want.y, "decode")
+
+
 def test_plugin_encode_decode_and_size_accounting():
     fp = make_plugin()
     x, _ = make_outlier_tensor(1 << 20, seed=4)

@@ -50,6 +50,10 @@ def parse():
     ap.add_argument("--packed-activations", action="store_true",
                     help="keep autograd's saved tensors as packed SmaQ streams (not in the reference; changes numerics)")
     ap.add_argument("--compress_loss", action="store_true")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="capture the whole training step (forward, backward, hooks, optimizer) in ONE CUDA graph and replay "
+                         "it: the codec's random streams advance through a device counter (smart_compress._native.counted_step). "
+                         "Single GPU only")
     ap.add_argument("--profile", action="store_true",
                     help="after the timed steps, run 3 more under torch.profiler and print GPU-busy time and the top kernels to stderr")
     ap.add_argument("--only", default=",".join(DATA_STRUCTURES),
@@ -105,7 +109,8 @@ def build_model(model_name, batch, image, seq, device):
 
 def run_training(model_name="resnet34", batch=32, image=224, seq=128, compress="smart", steps=50, warmup=10,
                  device=None, world=1, local=0, codec="b200", only=DATA_STRUCTURES, batched_optimizer=True,
-                 packed_activations=False, compress_loss_flag=False, profile=False, seed=1234, clocks=None):
+                 packed_activations=False, compress_loss_flag=False, profile=False, seed=1234, clocks=None,
+                 cuda_graph=False):
     """`steps` timed training steps after `warmup` untimed ones; returns a dict (device-timed, max over ranks)."""
     from smart_compress.util.pytorch.autograd import packed_saved_tensors
     from smart_compress.util.train import build_compression, compress_loss, compression_argv, parse_compression_args
@@ -140,7 +145,7 @@ def run_training(model_name="resnet34", batch=32, image=224, seq=128, compress="
     if model_name.startswith("resnet"):
         inner = torch.optim.SGD(groups, lr=0.1, momentum=0.9, weight_decay=0)
     else:
-        inner = torch.optim.AdamW(groups, lr=2e-5)
+        inner = torch.optim.AdamW(groups, lr=2e-5, capturable=bool(cuda_graph))
 
     if codec == "reference-eager":
         assert compress == "smart"
@@ -170,9 +175,38 @@ def run_training(model_name="resnet34", batch=32, image=224, seq=128, compress="
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(warmup):
-        opt.step(closure)
+    step_fn = lambda: opt.step(closure)  # noqa: E731
+    graph = None
+    if cuda_graph:
+        # The whole step as ONE graph (§8 f-1): ~600-1200 codec launches plus the network's own kernels replayed
+        # without a line of Python.  Warm-up runs eagerly on the capture stream (lazy optimizer state, workspaces,
+        # cuDNN / cuBLAS plans); every step — eager or replayed — is a counted step, so the random streams advance
+        # on the device exactly as they would eagerly.
+        assert world == 1, "--cuda-graph is a single-GPU option (DDP's reducer is not captured here)"
+        from smart_compress import _native as N
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 3)):
+                with N.counted_step(device):
+                    opt.step(closure)
+            side.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                with N.counted_step(device):
+                    static_loss = opt.step(closure)
+        torch.cuda.current_stream().wait_stream(side)
+
+        def step_fn():
+            graph.replay()
+            return static_loss
+    else:
+        for _ in range(warmup):
+            opt.step(closure)
     sync()
+    per_step_calls = {str(k): v // ((max(warmup, 3) + 1) if cuda_graph else max(warmup, 1)) for k, v in
+                      sorted(calls.items(), key=lambda kv: str(kv[0]))}
     calls.clear()
     torch.cuda.reset_peak_memory_stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -181,7 +215,7 @@ def run_training(model_name="resnet34", batch=32, image=224, seq=128, compress="
         e0.record()
         last = None
         for _ in range(steps):
-            last = opt.step(closure)
+            last = step_fn()
         e1.record()
         sync()
         wall = time.perf_counter() - t0
@@ -197,11 +231,13 @@ def run_training(model_name="resnet34", batch=32, image=224, seq=128, compress="
                     (f" {image}x{image}" if model_name.startswith("resnet") else f" seq {seq}") +
                     f", --compress {compress} on {','.join(only)}" + (" [reference eager torch-CUDA ops]" if codec == "reference-eager" else ""),
         "optimizer": type(inner).__name__,
-        "codec_calls_per_step": {str(k): v // steps for k, v in sorted(calls.items(), key=lambda kv: str(kv[0]))},
+        "codec_calls_per_step": per_step_calls if cuda_graph else
+                                {str(k): v // steps for k, v in sorted(calls.items(), key=lambda kv: str(kv[0]))},
+        "cuda_graph": bool(cuda_graph),
     }
-    if profile and rank == 0:
+    if profile and rank == 0 and not cuda_graph:
         out["profile"] = profile_steps(opt, closure, ms_per_step)
-    del net, model, opt, inner
+    del net, model, opt, inner, graph, step_fn
     torch.cuda.empty_cache()
     return out
 
@@ -238,7 +274,8 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     r = run_training(a.model, a.batch, a.image, a.seq, a.compress, a.steps, a.warmup, device, world, local,
                      codec=a.codec, only=tuple(a.only.split(",")), batched_optimizer=not a.no_batched_optimizer,
-                     packed_activations=a.packed_activations, compress_loss_flag=a.compress_loss, profile=a.profile)
+                     packed_activations=a.packed_activations, compress_loss_flag=a.compress_loss, profile=a.profile,
+                     cuda_graph=a.cuda_graph)
     if rank == 0:
         prof = r.pop("profile", None)
         line = {"metric": f"{a.model}_train_{r['unit'].replace('/', '_per_')}", **r, "higher_is_better": True,
