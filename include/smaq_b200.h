@@ -29,7 +29,7 @@ extern "C" {
 
 #define SMAQ_B200_ABI_VERSION 4 /* 2: packed stream SQB2, count_saturated, smaq_compress, tensor_desc.stream; 3: smaq_float_quantize_multi;
                                     4: smaq_roundtrip_bn, smaq_roundtrip_multi(mean_std_out), range_std in the sampled statistics,
-                                       packed stream SQB3 (one-pass encoder, smaq_encode_workspace_init), offset_base + smaq_counter_add */
+                                       packed stream SQB3 (one-pass encoder, smaq_encode_workspace_init), offset_base + smaq_counter_add, zero_on_grid, smaq_decode_sum */
 
 typedef void* smaq_stream_t; /* cudaStream_t */
 
@@ -212,6 +212,17 @@ int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* p
 /* Unpack and de-normalise (smart.py:171-172,181-182).  Parameters come from the header. */
 int smaq_decode(const void* packed, size_t packed_bytes, int64_t n, int32_t bits_main, int32_t bits_outlier,
                 int32_t all_positive, float* y, smaq_stream_t stream);
+
+/* The reduce step of a COMPRESSED all-reduce (not in the reference, which compresses after DDP's
+ * fp32 all-reduce, optimizer.py:135-141 — so this is opt-in and changes numerics).  `packed` is a HOST array of
+ * `count` (<= 8) device pointers to packed tensors of identical geometry (n, widths), typically one per rank and
+ * living in that rank's memory, mapped into this process (symmetric memory / CUDA IPC over NVLink).  For the CTA
+ * tiles [first_cta_tile, first_cta_tile + n_cta_tiles) — 8192 elements each — it writes
+ *     y[i] = scale * (decode(packed[0])[i] + decode(packed[1])[i] + ...)
+ * y is indexed like the whole tensor (pass the tensor's base pointer).  One kernel: its loads are the transfer. */
+int smaq_decode_sum(const void* const* packed, int32_t count, size_t packed_bytes, int64_t n, int32_t bits_main,
+                    int32_t bits_outlier, int64_t first_cta_tile, int64_t n_cta_tiles, float scale, float* y,
+                    smaq_stream_t stream);
 
 /* ---- low-precision float emulation --------------------------------------------------------- */
 

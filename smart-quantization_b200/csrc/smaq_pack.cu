@@ -686,6 +686,31 @@ __device__ __forceinline__ uint32_t base_field(const uint32_t (&bw)[PM], int k, 
   return v & ((1u << PM) - 1u);
 }
 
+// The decoded value of every possible stored field of one packed tensor — kMainEntries main fields, then
+// kOutEntries outlier fields, indexed by the stored value U — by the reference's own inverse (smart.py:171-172,
+// 181-182, IEEE division).  Every (class, U) pair has ONE decoded value per tensor, so decoding is a table lookup.
+template <int PM, int XB>
+__device__ __forceinline__ void build_decode_lut(const smaq_packed_header* __restrict__ hdr, float* s_lut, bool all_positive) {
+  constexpr int kMainEntries = 1 << PM, kOutEntries = 1 << (PM + XB);
+  const Scalars s = make_scalars(hdr->mean, hdr->std_raw, hdr->threshold, hdr->range_main, hdr->range_outlier,
+                                 hdr->clamp_lo, hdr->clamp_hi, hdr->bits_main, hdr->bits_outlier);
+  const bool stochastic = hdr->stochastic != 0;
+  for (int i = threadIdx.x; i < kMainEntries + kOutEntries; i += kPackThreads) {
+    // S from the field: two's complement (main) / offset binary (outlier)
+    const bool is_out = i >= kMainEntries;
+    const int v = is_out ? i - kMainEntries : i;
+    const int S = is_out ? v - (1 << (PM + XB - 1)) : (v >= (1 << (PM - 1)) && XB > 0 ? v - (1 << PM) : (XB > 0 ? v : v - (1 << (PM - 1))));
+    // S < 0: the lower side, code = S + 1; a zero code there is trunc's -0.0 (stochastic: -1 + 1 = +0)
+    float code = (float)(S < 0 ? S + 1 : S);
+    if (S == -1 && !stochastic) code = -0.0f;
+    const float shift = is_out ? (S < 0 ? s.shift_lo : s.shift_hi) : s.shift_mid;
+    const float rb = is_out ? s.range_out.b : s.range_main.b;
+    bool unused = false;
+    s_lut[i] = decode_pair<false, false>(pair(code, code), pair(shift, shift), pair(rb, rb), pair(1.0f, 1.0f), s,
+                                         all_positive, unused).x;
+  }
+}
+
 // words of a warp tile's extras segment requested together with its planes, before the tag words say how many
 // are used: two 32-byte sectors — enough for 256 outliers per 1024 elements (the benchmark input has 169);
 // denser tiles fetch the rest once the count is known
@@ -719,25 +744,7 @@ __global__ void __launch_bounds__(kPackThreads, 4)
   }
 
   // The decoded value of every possible field, by the reference's own inverse (IEEE division).
-  {
-    const Scalars s = make_scalars(hdr->mean, hdr->std_raw, hdr->threshold, hdr->range_main, hdr->range_outlier,
-                                   hdr->clamp_lo, hdr->clamp_hi, hdr->bits_main, hdr->bits_outlier);
-    const bool stochastic = hdr->stochastic != 0;
-    for (int i = threadIdx.x; i < kMainEntries + kOutEntries; i += kPackThreads) {
-      // S from the field: two's complement (main) / offset binary (outlier)
-      const bool is_out = i >= kMainEntries;
-      const int v = is_out ? i - kMainEntries : i;
-      const int S = is_out ? v - (1 << (PM + XB - 1)) : (v >= (1 << (PM - 1)) && XB > 0 ? v - (1 << PM) : (XB > 0 ? v : v - (1 << (PM - 1))));
-      // S < 0: the lower side, code = S + 1; a zero code there is trunc's -0.0 (stochastic: -1 + 1 = +0)
-      float code = (float)(S < 0 ? S + 1 : S);
-      if (S == -1 && !stochastic) code = -0.0f;
-      const float shift = is_out ? (S < 0 ? s.shift_lo : s.shift_hi) : s.shift_mid;
-      const float rb = is_out ? s.range_out.b : s.range_main.b;
-      bool unused = false;
-      s_lut[i] = decode_pair<false, false>(pair(code, code), pair(shift, shift), pair(rb, rb), pair(1.0f, 1.0f), s,
-                                           all_positive != 0, unused).x;
-    }
-  }
+  build_decode_lut<PM, XB>(hdr, s_lut, all_positive != 0);
 
   // lane offsets inside the warp tile's segment; the segment into shared memory
   const uint32_t nb = __popc(tagw) * XB;
@@ -788,6 +795,118 @@ __global__ void __launch_bounds__(kPackThreads, 4)
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (e + j < n) y[e + j] = out[j];
+    }
+  }
+}
+
+// ---- decode-and-sum: the reduce step of a compressed all-reduce, reading its inputs over NVLink -------------------
+// (§8 f-3; not in the reference, which compresses AFTER DDP's all-reduce, optimizer.py:135-141.)  Up to
+// kMaxSources packed tensors of the SAME geometry — one per rank, each in that rank's memory, mapped into this
+// process (symmetric memory / CUDA IPC) — are decoded and summed for a range of CTA tiles (this rank's shard):
+//     y[i] = scale * sum_s decode_s(i)         i in [first_tile * 8192, (first_tile + n_tiles) * 8192) ∩ [0, n)
+// The kernel's own global loads ARE the transfer: there is no receive buffer and no NCCL call; every warp requests
+// the planes and the head of the extras segment of its tile from ALL sources before it decodes the first one, so
+// the NVLink round trips overlap each other and the arithmetic.  The fixed-stride stream (SQB3) is what makes a
+// tile range a contiguous slice of every section.  The order of the sum is the order of `src`: deterministic.
+constexpr int kMaxSources = 8;
+struct PackedSources {
+  const unsigned char* p[kMaxSources];
+};
+
+template <int PM, int XB>
+__global__ void __launch_bounds__(kPackThreads, 2)
+    decode_sum_kernel(PackedSources src, int count, smaq_packed_layout lay, long long first_tile, long long n_tiles,
+                      float scale, float* __restrict__ y, int aligned) {
+  constexpr int kSeg = seg_words(XB);
+  constexpr int kLut = (1 << PM) + (1 << (PM + XB));
+  constexpr int kMainEntries = 1 << PM;
+  __shared__ float s_lut[kMaxSources][kLut];
+  __shared__ uint32_t s_ext[kWarpsPerCta][kSeg + 2];
+  const int lane = lane_id(), warp = warp_id();
+  const int64_t n = lay.n;
+  for (int sidx = 0; sidx < count; ++sidx)
+    build_decode_lut<PM, XB>(reinterpret_cast<const smaq_packed_header*>(src.p[sidx] + lay.header_off), s_lut[sidx], false);
+  __syncthreads();
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t wt = (int64_t)(first_tile + t) * kWarpsPerCta + warp;
+    const int64_t base = wt * kWarpTile;
+    if (base >= n) continue;  // uniform per warp
+    // every source's words for this warp tile, requested up front
+    uint32_t tagw[kMaxSources], bw[kMaxSources][PM], spec[kMaxSources];
+#pragma unroll
+    for (int sidx = 0; sidx < kMaxSources; ++sidx) {
+      tagw[sidx] = 0;
+      spec[sidx] = 0;
+#pragma unroll
+      for (int w = 0; w < PM; ++w) bw[sidx][w] = 0;
+      if (sidx < count) {
+        const uint32_t* rec = reinterpret_cast<const uint32_t*>(src.p[sidx] + lay.planes_off) + wt * (int64_t)((1 + PM) * 32) + lane;
+        tagw[sidx] = __ldcs(rec);
+#pragma unroll
+        for (int w = 0; w < PM; ++w) bw[sidx][w] = __ldcs(rec + 32 * (w + 1));
+        if (XB > 0 && lane < kSpecWords)
+          spec[sidx] = __ldcs(reinterpret_cast<const uint32_t*>(src.p[sidx] + lay.extras_off) + wt * (int64_t)kSeg + lane);
+      }
+    }
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
+#pragma unroll
+    for (int sidx = 0; sidx < kMaxSources; ++sidx) {
+      if (sidx >= count) break;
+      const uint32_t nb = __popc(tagw[sidx]) * XB;
+      const uint32_t inc = warp_inclusive_scan(nb);
+      uint32_t* seg_s = &s_ext[warp][0];
+      if (XB > 0) {
+        const uint32_t my_words = (__shfl_sync(0xffffffffu, inc, 31) + 31) >> 5;
+        const uint32_t* seg_in = reinterpret_cast<const uint32_t*>(src.p[sidx] + lay.extras_off) + wt * (int64_t)kSeg;
+        __syncwarp();  // the previous source's segment has been consumed
+        if (lane < kSpecWords) seg_s[lane] = spec[sidx];
+        for (uint32_t i = kSpecWords + lane; i < my_words; i += 32) seg_s[i] = __ldcs(seg_in + i);
+        if (lane < 2) seg_s[max(my_words, (uint32_t)kSpecWords) + lane] = 0u;
+        __syncwarp();
+      }
+      uint32_t pos = inc - nb;
+      const float* lut = s_lut[sidx];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t tag = (tagw[sidx] >> (8 * k)) & 0xFFu;
+        uint32_t win = 0;
+        if (XB > 0) {
+          const uint32_t len = __popc(tag) * XB;
+          const uint32_t raw = __funnelshift_r(seg_s[pos >> 5], seg_s[(pos >> 5) + 1], pos & 31);
+          win = len ? (raw << (32 - len)) : 0u;
+          pos += len;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t b = base_field<PM>(bw[sidx], k, j);
+          uint32_t idx = b;
+          if ((tag >> j) & 1u) {
+            idx = kMainEntries + b;
+            if (XB > 0) {
+              idx += (win >> (32 - XB)) << PM;
+              win <<= XB;
+            }
+          }
+          acc[8 * k + j] = __fadd_rn(acc[8 * k + j], lut[idx]);
+        }
+      }
+    }
+    const bool full = aligned && (base + kWarpTile <= n);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t e = base + 256 * k + 8 * lane;
+      if (full) {
+        f32x8 o;
+        o.a = make_float4(acc[8 * k] * scale, acc[8 * k + 1] * scale, acc[8 * k + 2] * scale, acc[8 * k + 3] * scale);
+        o.b = make_float4(acc[8 * k + 4] * scale, acc[8 * k + 5] * scale, acc[8 * k + 6] * scale, acc[8 * k + 7] * scale);
+        stg_stream8(y + e, o);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (e + j < n) y[e + j] = acc[8 * k + j] * scale;
+      }
     }
   }
 }
@@ -954,6 +1073,37 @@ int smaq_decode(const void* packed, size_t packed_bytes, int64_t n, int32_t bits
 #endif
 #undef SMAQ_DEC_ROW
 #undef SMAQ_DEC
+  SMAQ_LAUNCH_OK();
+  return SMAQ_OK;
+}
+
+int smaq_decode_sum(const void* const* packed, int32_t count, size_t packed_bytes, int64_t n, int32_t bits_main,
+                    int32_t bits_outlier, int64_t first_cta_tile, int64_t n_cta_tiles, float scale, float* y,
+                    smaq_stream_t stream_) {
+  using namespace smaq;
+  if (!packed || !y || n <= 0 || count < 1 || first_cta_tile < 0 || n_cta_tiles < 0)
+    return fail(SMAQ_ERR_ARG, "decode_sum: bad argument");
+  if (count > kMaxSources) return fail(SMAQ_ERR_UNSUPPORTED, "decode_sum: at most %d sources per call", kMaxSources);
+  smaq_packed_layout l;
+  if (int rc = smaq_packed_layout_for(n, bits_main, bits_outlier, &l)) return rc;
+  if (packed_bytes < (size_t)l.total_capacity_bytes) return fail(SMAQ_ERR_WORKSPACE, "decode_sum: packed buffers too small");
+  if (first_cta_tile + n_cta_tiles > l.n_cta_tiles) n_cta_tiles = l.n_cta_tiles - first_cta_tile;
+  if (n_cta_tiles <= 0) return SMAQ_OK;
+  PackedSources src;
+  for (int i = 0; i < kMaxSources; ++i) src.p[i] = i < count ? (const unsigned char*)packed[i] : nullptr;
+  for (int i = 0; i < count; ++i)
+    if (!src.p[i]) return fail(SMAQ_ERR_ARG, "decode_sum: source %d is NULL", i);
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  const long long cap = (long long)sms * 2;
+  const unsigned grid = (unsigned)(n_cta_tiles < cap ? n_cta_tiles : cap);
+  const int aligned = aligned32(y);
+  const int pm = bits_main - 1, xb = bits_outlier - bits_main;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (pm == 5 && xb == 2)
+    decode_sum_kernel<5, 2><<<grid, kPackThreads, 0, stream>>>(src, count, l, (long long)first_cta_tile, (long long)n_cta_tiles, scale, y, aligned);
+  else
+    return fail(SMAQ_ERR_UNSUPPORTED, "decode_sum: only the default 6/8-bit widths");
   SMAQ_LAUNCH_OK();
   return SMAQ_OK;
 }

@@ -129,6 +129,8 @@ static int stats_grid(int64_t n) {
   return (int)(want < cap ? want : cap);
 }
 
+int stats_grid_for(int64_t n) { return stats_grid(n); }
+
 template <int kKind>
 static int launch_stats(const float* x, int64_t n, int unbiased, float* out, void* ws, size_t ws_bytes,
                         cudaStream_t stream, bool ticket_is_zero = false) {
