@@ -34,6 +34,9 @@ class S2FP8(CompressionAlgorithmBase):
 
     @torch.no_grad()
     def __call__(self, tensor: torch.Tensor, tag: str = None, **extra):
+        if tensor.is_cuda and N.wrong_device(tensor):  # launch on the tensor's own GPU (the reference's eager ops do)
+            with N.on_device_of(tensor):
+                return self.__call__(tensor, tag, **extra)
         self.log_ratio(tag, tensor.numel(), 32, 8, overhead=64)
         is_16_bit = getattr(self.hparams, "precision", 32) == 16
         src = tensor.float() if is_16_bit else tensor

@@ -99,6 +99,9 @@ def _next_stream():
 def float_quantize(x: torch.Tensor, exp: int, man: int, hparams, rand_bits: torch.Tensor = None):
     """quantization.py:187-204.  Returns a new tensor; fp16 tensors round-trip through fp32 when
     ``hparams.precision == 16`` exactly as there."""
+    if x.is_cuda and N.wrong_device(x):  # launch on the tensor's own GPU (the reference's eager ops do)
+        with N.on_device_of(x):
+            return float_quantize(x, exp, man, hparams, rand_bits)
     lib = N.load()
     is_16_bit = getattr(hparams, "precision", 32) == 16
     src = x.float() if is_16_bit else x
@@ -127,6 +130,10 @@ def float_quantize_many(tensors, exp: int, man: int, hparams):
     numbers its calls, so every tensor gets the bits that loop would give it.  Contiguous fp32 CUDA tensors are
     updated IN PLACE and returned as the same objects (the reference re-binds ``.data`` to a fresh tensor; nothing
     else aliases optimizer tensors); anything else goes through ``float_quantize``."""
+    lead = next((t for t in tensors if t.is_cuda), None)
+    if lead is not None and N.wrong_device(lead):  # launch on the tensors' own GPU (before any stream number is drawn)
+        with N.on_device_of(lead):
+            return float_quantize_many(tensors, exp, man, hparams)
     lib = N.load()
     results = list(tensors)
     is_16_bit = getattr(hparams, "precision", 32) == 16

@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--packed-activations", action="store_true",
                     help="keep autograd's saved tensors as packed SmaQ streams (not in the reference; changes numerics)")
     ap.add_argument("--compress_loss", action="store_true")
+    ap.add_argument("--compress-allreduce", default="", choices=["", "p2p", "nccl"],
+                    help="gradient compression fused with the all-reduce (smart_compress/util/pytorch/allreduce.py; not in the "
+                         "reference, changes numerics): DDP's fp32 all-reduce is replaced by packed SmaQ streams read over NVLink")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="capture the whole training step (forward, backward, hooks, optimizer) in ONE CUDA graph and replay "
                          "it: the codec's random streams advance through a device counter (smart_compress._native.counted_step). "
@@ -110,7 +113,7 @@ def build_model(model_name, batch, image, seq, device):
 def run_training(model_name="resnet34", batch=32, image=224, seq=128, compress="smart", steps=50, warmup=10,
                  device=None, world=1, local=0, codec="b200", only=DATA_STRUCTURES, batched_optimizer=True,
                  packed_activations=False, compress_loss_flag=False, profile=False, seed=1234, clocks=None,
-                 cuda_graph=False):
+                 cuda_graph=False, compress_allreduce=""):
     """`steps` timed training steps after `warmup` untimed ones; returns a dict (device-timed, max over ranks)."""
     from smart_compress.util.pytorch.autograd import packed_saved_tensors
     from smart_compress.util.train import build_compression, compress_loss, compression_argv, parse_compression_args
@@ -160,6 +163,13 @@ def run_training(model_name="resnet34", batch=32, image=224, seq=128, compress="
 
         pack_codec = fn.inner if isinstance(getattr(fn, "inner", None), SmartFP) else SmartFP(parse_compression_args(["--compress", "smart"]))
     net = nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    car = None
+    if compress_allreduce and world > 1:
+        from smart_compress.compress.smart import SmartFP
+        from smart_compress.util.pytorch.allreduce import register_compressed_allreduce
+
+        wire_codec = fn.inner if isinstance(getattr(fn, "inner", None), SmartFP) else SmartFP(parse_compression_args(["--compress", "smart"]))
+        car = register_compressed_allreduce(net, wire_codec, transport=compress_allreduce)
 
     def closure():
         opt.zero_grad(set_to_none=True)
@@ -234,6 +244,8 @@ def run_training(model_name="resnet34", batch=32, image=224, seq=128, compress="
         "codec_calls_per_step": per_step_calls if cuda_graph else
                                 {str(k): v // steps for k, v in sorted(calls.items(), key=lambda kv: str(kv[0]))},
         "cuda_graph": bool(cuda_graph),
+        "compress_allreduce": compress_allreduce or None,
+        "allreduce_stats": None if car is None else dict(car.stats),
     }
     if profile and rank == 0 and not cuda_graph:
         out["profile"] = profile_steps(opt, closure, ms_per_step)
@@ -275,7 +287,7 @@ def main():
     r = run_training(a.model, a.batch, a.image, a.seq, a.compress, a.steps, a.warmup, device, world, local,
                      codec=a.codec, only=tuple(a.only.split(",")), batched_optimizer=not a.no_batched_optimizer,
                      packed_activations=a.packed_activations, compress_loss_flag=a.compress_loss, profile=a.profile,
-                     cuda_graph=a.cuda_graph)
+                     cuda_graph=a.cuda_graph, compress_allreduce=a.compress_allreduce)
     if rank == 0:
         prof = r.pop("profile", None)
         line = {"metric": f"{a.model}_train_{r['unit'].replace('/', '_per_')}", **r, "higher_is_better": True,
