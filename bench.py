@@ -168,6 +168,27 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
+def bind_to_gpu_cpus(index: int):
+    """Pin this process to the CPUs NVML reports as local to GPU `index` (its NUMA node), so that the pinned host
+    buffers of the end-to-end leg are allocated next to the GPU's PCIe root.  At N = 8 the ranks otherwise share
+    whichever node the launcher started them on.  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return "unchanged (NVML reported no local CPUs inside this process's affinity)"
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} CPUs local to GPU {index} (first {min(cpus)}, last {max(cpus)})"
+    except Exception as e:  # no NVML / containers that forbid sched_setaffinity: leave the placement to the OS
+        return f"unchanged ({type(e).__name__})"
+
+
 def make_input(n: int, device, seed=1234):
     """BASELINE.md §4 recipe, generated on the device the tensor lives on."""
     g = torch.Generator(device=device).manual_seed(seed)
@@ -382,6 +403,9 @@ def run_b200(args):
     # ---- end to end through the plugin API with host buffers ---------------------------------------------
     if not args.no_e2e:
         e2e_steps = max(1, min(args.steps, 20))
+        # at N > 1 the pinned pages are first-touched on the GPU's own NUMA node (at N = 1 the CPU baseline leg
+        # later in this process wants every core)
+        numa = bind_to_gpu_cpus(local) if world > 1 else "not bound (single GPU)"
         hx = torch.empty(n, dtype=torch.float32, pin_memory=True)
         hy = torch.empty(n, dtype=torch.float32, pin_memory=True)
         hx.copy_(x)
@@ -443,6 +467,7 @@ def run_b200(args):
                    "streams (copy in / compute / copy out), double-buffered: consecutive steps overlap on the full-duplex "
                    "PCIe link",
             "checksum": float(hy[:: max(1, n // 4096)].double().sum()),
+            "host_numa_binding": numa,
         }
         x = dxs[0]
         del hx, hy, dys

@@ -29,7 +29,7 @@ extern "C" {
 
 #define SMAQ_B200_ABI_VERSION 4 /* 2: packed stream SQB2, count_saturated, smaq_compress, tensor_desc.stream; 3: smaq_float_quantize_multi;
                                     4: smaq_roundtrip_bn, smaq_roundtrip_multi(mean_std_out), range_std in the sampled statistics,
-                                       packed stream SQB3 (one-pass encoder, smaq_encode_workspace_init), offset_base + smaq_counter_add, zero_on_grid, smaq_decode_sum */
+                                       packed stream SQB3 (one-pass encoder, smaq_encode_workspace_init), offset_base + smaq_counter_add, zero_on_grid, smaq_decode_sum, smaq_s2fp8_multi */
 
 typedef void* smaq_stream_t; /* cudaStream_t */
 
@@ -259,6 +259,14 @@ int smaq_s2fp8_stats(const float* x, int64_t n, float* mu_max, void* ws, size_t 
                      smaq_stream_t stream);
 int smaq_s2fp8_apply(const float* x, float* y, int64_t n, const float* mu_max, const int32_t* rand_bits,
                      const smaq_floatq_params* params, smaq_stream_t stream);
+
+/* S2FP8 over MANY tensors in three launches (set-up, per-item log-domain moments, apply) — the loops OptimLP runs
+ * with --compress s2fp8 (optimizer.py:69-127).  descs as in smaq_float_quantize_multi (all_positive ignored);
+ * tensor i is rounded with the Philox stream params->offset + descs[i].stream.  mu_max_out: optional device
+ * float[count][2] receiving each tensor's (mu, m).  In-kernel random numbers only. */
+size_t smaq_s2fp8_multi_workspace_bytes(int32_t count, int64_t total_elems);
+int smaq_s2fp8_multi(const smaq_tensor_desc* descs, int32_t count, int64_t total_elems, const smaq_floatq_params* params,
+                     void* ws, size_t ws_bytes, float* mu_max_out, smaq_stream_t stream);
 
 /* Test hook, not part of the reference's surface: out[i] = a[i] ** y[0] evaluated by the S2FP8 apply kernel's
  * packed fast path for every group of four elements it accepts (accepted[i / 4] = 1), by powf otherwise.  The

@@ -64,3 +64,25 @@ def probs_for(n: int, seed: int, offset: int = 0, first: int = 0) -> np.ndarray:
     """p = 1 - q = (65535.5 - k) / 2^16 as fp32 (exact): what ``oracle.smaq.smaq_roundtrip(rng_rule=True)`` takes."""
     k = rnd16(n, seed, offset, first).astype(np.float64)
     return ((65535.5 - k) / 65536.0).astype(np.float32)
+
+
+def floatq_fields(n: int, seed: int, offset: int = 0, man_bits: int = 2, first: int = 0) -> np.ndarray:
+    """What the float-emulation kernels (csrc/float_quantize.cu ``fq_k16`` / ``rand_field``) add to an element's bit
+    pattern before truncating when they draw their own numbers: one Philox4x32-7 call per eight elements (counter =
+    element index / 8), 16 bits per element — half (j & 1) of word j >> 1 — placed at the top of the (23 - man)-bit
+    field plus half a step of the 16-bit grid.  Returned as int32: feeding it to ``oracle.floatq.float_quantize`` as
+    its ``r`` reproduces the kernel (the oracle masks with the same field mask)."""
+    e = np.arange(first, first + n, dtype=np.uint64)
+    g = e >> np.uint64(3)
+    j = (e & np.uint64(7)).astype(np.int64)
+    ones = np.ones_like(g)
+    words = philox4x32(g & MASK32, g >> np.uint64(32), ones * np.uint64(offset & 0xFFFFFFFF),
+                       ones * np.uint64((offset >> 32) & 0xFFFFFFFF), seed)
+    w = np.choose(j >> 1, words).astype(np.uint64)
+    k16 = np.where(j & 1, w >> np.uint64(16), w & np.uint64(0xFFFF))
+    rshift = (23 - man_bits) - 16
+    if rshift >= 0:
+        field = (k16 << np.uint64(rshift)) | np.uint64((1 << (rshift - 1)) if rshift > 0 else 0)
+    else:
+        field = k16 >> np.uint64(-rshift)
+    return field.astype(np.int64).astype(np.int32)

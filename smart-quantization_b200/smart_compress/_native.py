@@ -144,6 +144,8 @@ _SIGNATURES = {
     "smaq_float_quantize": (C.c_int, [_P, _P, _I64, _P, C.POINTER(FloatqParams), _P]),
     "smaq_floatq_multi_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "smaq_float_quantize_multi": (C.c_int, [_P, C.c_int32, _I64, C.POINTER(FloatqParams), _P, C.c_size_t, _P]),
+    "smaq_s2fp8_multi_workspace_bytes": (C.c_size_t, [C.c_int32, _I64]),
+    "smaq_s2fp8_multi": (C.c_int, [_P, C.c_int32, _I64, C.POINTER(FloatqParams), _P, C.c_size_t, _P, _P]),
     "smaq_s2fp8_stats": (C.c_int, [_P, _I64, _P, _P, C.c_size_t, _P]),
     "smaq_s2fp8_apply": (C.c_int, [_P, _P, _I64, _P, _P, C.POINTER(FloatqParams), _P]),
     "smaq_selftest_pow": (C.c_int, [_P, _P, _P, _P, _I64, _P]),

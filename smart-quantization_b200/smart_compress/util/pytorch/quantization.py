@@ -123,6 +123,82 @@ _multi_ws = {}      # device -> grow-only scratch
 _graph_keep = []    # buffers a captured CUDA graph reads at replay
 
 
+def _descriptors(batch, device):
+    """Device array of smaq_tensor_desc for [(index, tensor, stream number)], cached by pointers and sizes."""
+    key = (device, tuple((t.data_ptr(), t.numel(), sn) for _, t, sn in batch))
+    descs = _multi_cache.get(key)
+    if descs is None:
+        host = (N.TensorDesc * len(batch))()
+        for j, (_, t, sn) in enumerate(batch):
+            host[j].x = host[j].y = t.data_ptr()
+            host[j].n = t.numel()
+            host[j].all_positive = 0
+            host[j].stream = sn
+        N.ensure_pinned_arena()
+        capturing = torch.cuda.is_current_stream_capturing()
+        raw = (N.pinned_arena_take(bytes(host)) if capturing
+               else torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).pin_memory())
+        descs = raw.to(device, non_blocking=True)
+        if capturing:
+            _graph_keep.append((raw, descs))   # the captured copy reads `raw` at every replay
+        else:
+            if len(_multi_cache) > 64:
+                _multi_cache.clear()
+            _multi_cache[key] = (descs, raw)
+    else:
+        descs = descs[0]
+    return descs
+
+
+def s2fp8_many(tensors, hparams, stats_out=None):
+    """``[S2FP8(hparams)(t) for t in tensors]`` in three launches (``smaq_s2fp8_multi``) — the loops OptimLP runs over
+    every parameter, gradient and state tensor with --compress s2fp8 (reference optimizer.py:69-127, s2fp8.py:31-48).
+    Contiguous fp32 CUDA tensors are updated IN PLACE and returned as the same objects; ``stats_out`` (a dict,
+    parity tests) receives {index: device float[2]} with each tensor's (mu, m).  Returns None for tensors it did not
+    take (the caller falls back to the per-tensor call)."""
+    lead = next((t for t in tensors if t.is_cuda), None)
+    if lead is not None and N.wrong_device(lead):
+        with N.on_device_of(lead):
+            return s2fp8_many(tensors, hparams, stats_out)
+    lib = N.load()
+    results = [None] * len(tensors)
+    if getattr(hparams, "precision", 32) == 16:
+        return results
+    batch = []
+    first = None
+    for i, t in enumerate(tensors):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()) or t.numel() == 0:
+            continue
+        if batch and t.device != batch[0][1].device:
+            continue
+        no = _next_stream()[0]
+        if first is None:
+            first = no
+        batch.append((i, t, no - first))
+    if not batch:
+        return results
+    device = batch[0][1].device
+    descs = _descriptors(batch, device)
+    params = make_floatq_params(5, 2, hparams)
+    params.offset = first
+    total = sum(t.numel() for _, t, _ in batch)
+    need = lib.smaq_s2fp8_multi_workspace_bytes(len(batch), total)
+    key = (device, "s2")
+    ws = _multi_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _multi_ws[key] = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
+    mm = None
+    if stats_out is not None:
+        mm = torch.zeros(len(batch), 2, dtype=torch.float32, device=device)
+        for j, (i, _, _) in enumerate(batch):
+            stats_out[i] = mm[j]
+    N.check(lib.smaq_s2fp8_multi(N.ptr(descs), len(batch), total, C.byref(params), N.ptr(ws), ws.numel(),
+                                 None if mm is None else N.ptr(mm), N.stream_ptr(device)), "smaq_s2fp8_multi")
+    for i, t, _ in batch:
+        results[i] = t
+    return results
+
+
 def float_quantize_many(tensors, exp: int, man: int, hparams):
     """``[float_quantize(t, exp, man, hparams) for t in tensors]`` in two launches (``smaq_float_quantize_multi``):
     what OptimLP's loops over every parameter, gradient and state tensor (reference optimizer.py:69-127) cost with
@@ -154,28 +230,7 @@ def float_quantize_many(tensors, exp: int, man: int, hparams):
         for i, t, _ in batch:
             results[i] = float_quantize(t, exp, man, hparams)
         return results
-    key = (device, tuple((t.data_ptr(), t.numel(), sn) for _, t, sn in batch))
-    descs = _multi_cache.get(key)
-    if descs is None:
-        host = (N.TensorDesc * len(batch))()
-        for j, (_, t, sn) in enumerate(batch):
-            host[j].x = host[j].y = t.data_ptr()
-            host[j].n = t.numel()
-            host[j].all_positive = 0
-            host[j].stream = sn
-        N.ensure_pinned_arena()
-        capturing = torch.cuda.is_current_stream_capturing()
-        raw = (N.pinned_arena_take(bytes(host)) if capturing
-               else torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).pin_memory())
-        descs = raw.to(device, non_blocking=True)
-        if capturing:
-            _graph_keep.append((raw, descs))   # the captured copy reads `raw` at every replay
-        else:
-            if len(_multi_cache) > 64:
-                _multi_cache.clear()
-            _multi_cache[key] = (descs, raw)
-    else:
-        descs = descs[0]
+    descs = _descriptors(batch, device)
     params = make_floatq_params(exp, man, hparams)
     params.offset = first      # make_floatq_params drew one more number: harmless, the streams stay distinct
     need = lib.smaq_floatq_multi_workspace_bytes(len(batch))

@@ -325,3 +325,51 @@ def test_fp8_plugin_compress_many_equals_the_loop():
     for j, (g, w, m) in enumerate(zip(got, want, mine)):
         assert g is m                                   # in place, same objects
         assert_bit_equal(g, w, f"tensor {j}")
+
+
+def test_s2fp8_compress_many_matches_the_reference_chain_per_tensor():
+    """S2FP8.compress_many (what OptimLP calls per phase: smaq_s2fp8_multi, three launches) against the reference's
+    op chain evaluated by torch's CUDA operators on this GPU, per tensor: with the (mu, m) the kernel reports — which
+    must be within 1e-6 of the reference's — and the random fields the kernel drew (oracle/rng.py), bit for bit."""
+    from argparse import ArgumentParser
+
+    from oracle import rng as orng
+    from smart_compress.compress.s2fp8 import S2FP8
+
+    hp = S2FP8.add_argparse_args(ArgumentParser()).parse_args([])
+    hp.precision = 32
+    g = torch.Generator().manual_seed(3)
+    sizes = [10, 512, 4096, 5000, 16384, 16385, 70000, (1 << 18) + 3]
+    xs = [torch.randn(n, generator=g) * (0.01 * (i + 1)) for i, n in enumerate(sizes)]
+    xs[2][::7] = 0.0
+    torch.manual_seed(77)
+    codec = S2FP8(hp)
+    from smart_compress.util.pytorch import quantization as Q
+    import itertools
+    Q._calls = itertools.count()            # stream numbers from 0 for this test
+    mine = [x.to(DEV) for x in xs]
+    stats = {}
+    got = codec.compress_many(mine, None, tag="optimizer_grad", stats_out=stats)
+    for i, (x, n) in enumerate(zip(xs, sizes)):
+        assert got[i] is mine[i]
+        mm = stats[i]
+        mu_ref, m_ref = os2.s2fp8_statistics(x.double())
+        assert abs(mm[0].item() - mu_ref.item()) <= 1e-6 * abs(mu_ref.item()), (i, n)
+        assert abs(mm[1].item() - m_ref.item()) <= 2e-7 * abs(m_ref.item()), (i, n)
+        r = torch.from_numpy(orng.floatq_fields(n, seed=77, offset=i, man_bits=2))
+        want, _, _, _ = os2.s2fp8(x.to(DEV), r, mu=mm[0].clone(), m=mm[1].clone())
+        diff = (got[i].view(torch.int32) != want.view(torch.int32)) & ~(torch.isnan(got[i]) & torch.isnan(want))
+        assert int(diff.sum()) == 0, f"tensor {i} ({n} elements): {int(diff.sum())} differ"
+
+
+def test_float_quantize_in_kernel_fields_match_the_oracle_generator():
+    """FP8's performance path (no rand_bits): the fields the kernel adds are oracle/rng.py's, so the output is the
+    oracle's bit for bit."""
+    from oracle import rng as orng
+
+    x, _ = interesting_values(100003, seed=8)
+    for man, exp in ((2, 5), (3, 4), (10, 5), (7, 8)):
+        got = cabi.float_quantize(x.to(DEV), cabi.floatq_params(exp, man, seed=5, offset=(1 << 35) + 3))
+        r = torch.from_numpy(orng.floatq_fields(x.numel(), seed=5, offset=(1 << 35) + 3, man_bits=man))
+        want = ofq.float_quantize(x, exp, man, r)
+        assert torch.equal(got.cpu().view(torch.int32), want.view(torch.int32)), (exp, man)

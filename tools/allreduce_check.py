@@ -43,7 +43,7 @@ def main():
             seed = 1000 + 17 * rank
             torch.manual_seed(seed)
             codec = SmartFP(hp)
-            car = CompressedAllReduce(codec, transport=transport, min_numel=1 << 10)
+            car = CompressedAllReduce(codec, n, transport=transport, min_numel=1 << 10)
             g = torch.Generator().manual_seed(n + rank)
             # gradient-like: Gaussian with a mild heavy tail (values beyond 2.5 sigma saturate in the packed format —
             # the H1 rule — which is one reason this path is opt-in)
@@ -65,8 +65,8 @@ def main():
             # (c) the oracle pipeline on rank 0 (inputs, seeds and stream headers gathered)
             xs = [torch.empty_like(xd) for _ in range(world)]
             dist.all_gather(xs, xd)
-            hdr_a = plan.buf[:128].clone()
-            hdr_b = plan.buf[plan.cap_a: plan.cap_a + 128].clone()
+            hdr_a = car.arena.buf[:128].clone()
+            hdr_b = car.arena.buf[car.arena.cap_a: car.arena.cap_a + 128].clone()
             hdrs_a = [torch.empty_like(hdr_a) for _ in range(world)]
             hdrs_b = [torch.empty_like(hdr_b) for _ in range(world)]
             dist.all_gather(hdrs_a, hdr_a)
@@ -106,7 +106,7 @@ def main():
     xd = torch.randn(n, device=dev)
     torch.manual_seed(5 + rank)
     for transport in ("p2p", "nccl"):
-        car = CompressedAllReduce(SmartFP(hp), transport=transport)
+        car = CompressedAllReduce(SmartFP(hp), n, transport=transport)
         for _ in range(3):
             car.allreduce_mean_(xd.clone())
         buf = xd.clone()

@@ -247,8 +247,10 @@ def run_training(model_name="resnet34", batch=32, image=224, seq=128, compress="
         "compress_allreduce": compress_allreduce or None,
         "allreduce_stats": None if car is None else dict(car.stats),
     }
-    if profile and rank == 0 and not cuda_graph:
-        out["profile"] = profile_steps(opt, closure, ms_per_step)
+    if profile and not cuda_graph:  # on EVERY rank: the extra steps contain DDP's collectives
+        prof = profile_steps(opt, closure, ms_per_step)
+        if rank == 0:
+            out["profile"] = prof
     del net, model, opt, inner, graph, step_fn
     torch.cuda.empty_cache()
     return out
@@ -262,7 +264,11 @@ def profile_steps(opt, closure, ms_per_step, n=3):
         for _ in range(n):
             opt.step(closure)
         torch.cuda.synchronize()
-    ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    def is_kernel(e):  # device-side records of host annotations ("Optimizer.step#...", "DistributedDataParallel.forward") are not kernels
+        return (e.device_type == torch.autograd.DeviceType.CUDA and not getattr(e, "is_user_annotation", False)
+                and not e.name.startswith(("Optimizer.", "DistributedDataParallel", "ProfilerStep", "autograd::")))
+
+    ev = [e for e in prof.events() if is_kernel(e)]
     per = 1e3 * n
     busy = sum(e.device_time for e in ev) / per
     ours = sum(e.device_time for e in ev if "smaq" in e.name or "floatq" in e.name) / per
