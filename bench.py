@@ -528,6 +528,14 @@ def train_block(args, device, world, local):
         config3 = {"workload": e["workload"], "img_per_s_eager": e["value"], "img_per_s_cuda_graph": gph["value"],
                    "plain_img_per_s_eager": pl["value"], "plain_img_per_s_cuda_graph": plg["value"],
                    "codec_calls_per_step": e["codec_calls_per_step"], "steps": args.train_steps}
+    # BASELINE configs[4]: BERT-base, STS-B shape (seq 128, batch 32 per GPU), AdamW incl. its moments
+    c5 = dict(model_name="bert-base", batch=32, seq=128, device=device, world=world, local=local)
+    b_steps, b_warm = max(10, args.train_steps // 2), max(5, args.train_warmup // 2)
+    bert = run_training(compress="smart", steps=b_steps, warmup=b_warm, **c5)
+    bert_plain = run_training(compress="fp32", steps=b_steps, warmup=b_warm, **c5)
+    config5 = {"workload": bert["workload"], "seq_per_s": bert["value"], "plain_seq_per_s": bert_plain["value"],
+               "ms_per_step": bert["ms_per_step"], "steps": b_steps, "warmup": b_warm,
+               "codec_calls_per_step": bert["codec_calls_per_step"], "n_gpus": world}
     return {
         "metric": "resnet34_train_img_per_s", "unit": "img/s", "n_gpus": world,
         "img_per_s": smart["value"], "ms_per_step": smart["ms_per_step"],
@@ -543,7 +551,7 @@ def train_block(args, device, world, local):
                    "stem": "reference CIFAR stem (3x3 stride 1; SURVEY.md H10): 52.7 M feature-map elements per image"},
         "codec_calls_per_step": smart["codec_calls_per_step"],
         "peak_memory_gib": smart["peak_memory_gib"], "plain_peak_memory_gib": plain["peak_memory_gib"],
-        "loss": smart["loss"], "clocks": clocks.summary(), "config3_resnet18_cifar": config3,
+        "loss": smart["loss"], "clocks": clocks.summary(), "config3_resnet18_cifar": config3, "config5_bert_base": config5,
         "profile": None if prof is None else {k: prof[k] for k in ("gpu_busy_ms_per_step", "codec_kernels_ms_per_step",
                                                                     "nccl_kernels_ms_per_step", "gpu_ops_per_step")},
     }

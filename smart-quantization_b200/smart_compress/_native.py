@@ -331,6 +331,22 @@ def ptr(t: torch.Tensor) -> int:
     return t.data_ptr()
 
 
+def is_dense(t: torch.Tensor) -> bool:
+    """The tensor's elements fill one contiguous block of storage in SOME order (contiguous, channels_last, a permuted
+    view of a contiguous tensor ...).  Statistics and the elementwise round trip do not depend on the order, so such
+    tensors are processed in storage order and the result keeps their strides (``torch.empty_like`` preserves them) —
+    like the reference's elementwise chain, and unlike ``.contiguous()``, which would add a transpose copy and hand
+    NCHW tensors to a channels_last network."""
+    return t.is_contiguous() or bool(torch.ops.aten.is_non_overlapping_and_dense(t))
+
+
+def storage_order(t: torch.Tensor) -> torch.Tensor:
+    """1-D view of a dense tensor's elements in storage order."""
+    if t.is_contiguous():
+        return t.view(-1)
+    return t.as_strided((t.numel(),), (1,), t.storage_offset())
+
+
 def require_cuda_f32(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise NativeLibraryError(

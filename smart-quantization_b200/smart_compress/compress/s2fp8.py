@@ -42,8 +42,9 @@ class S2FP8(CompressionAlgorithmBase):
         src = tensor.float() if is_16_bit else tensor
         N.require_cuda_f32(src, "S2FP8")
         lib = N.load()
-        src = src.contiguous()
-        flat = src.view(-1)
+        if not (extra.get("_rand_bits") is None and N.is_dense(src)):   # dense layouts keep their strides
+            src = src.contiguous()
+        flat = N.storage_order(src)
         out = torch.empty_like(src)
         if flat.numel() == 0:
             return out

@@ -220,8 +220,13 @@ class SmartFP(CompressionAlgorithmBase):
         probs = extra.get("_probs")
         sample_idx = extra.get("_sample_idx")
 
-        src = data if data.is_contiguous() else data.contiguous()
-        flat = src.view(-1)
+        # dense layouts (channels_last, permuted views) are processed in storage order and keep their strides; the
+        # batch-norm mode indexes channels from the NCHW position and explicit sample indices are logical positions
+        if data.is_contiguous() or (not use_bn and sample_idx is None and probs is None and N.is_dense(data)):
+            src = data
+        else:
+            src = data.contiguous()
+        flat = N.storage_order(src)
         out = torch.empty_like(src)
         stream = N.stream_ptr(data.device)
         params = self._params(all_positive, offset=extra.get("_offset"))
@@ -308,7 +313,7 @@ class SmartFP(CompressionAlgorithmBase):
             stream_no = numbered
             numbered += 1
             ok = (not per_tensor and t.is_cuda and t.dtype == torch.float32
-                  and t.is_contiguous() and "batch_norm_stats" not in kw and "_probs" not in kw)
+                  and N.is_dense(t) and "batch_norm_stats" not in kw and "_probs" not in kw)
             if ok:
                 batch.append((i, t, bool(kw.get("all_positive", False)), stream_no))
             else:

@@ -106,7 +106,8 @@ def float_quantize(x: torch.Tensor, exp: int, man: int, hparams, rand_bits: torc
     is_16_bit = getattr(hparams, "precision", 32) == 16
     src = x.float() if is_16_bit else x
     N.require_cuda_f32(src, "float_quantize")
-    src = src.contiguous()
+    if not (rand_bits is None and N.is_dense(src)):   # dense layouts keep their strides (elementwise, order-free)
+        src = src.contiguous()
     out = torch.empty_like(src)
     params = make_floatq_params(exp, man, hparams)
     rb = None
@@ -167,7 +168,7 @@ def s2fp8_many(tensors, hparams, stats_out=None):
     batch = []
     first = None
     for i, t in enumerate(tensors):
-        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()) or t.numel() == 0:
+        if not (t.is_cuda and t.dtype == torch.float32 and N.is_dense(t)) or t.numel() == 0:
             continue
         if batch and t.device != batch[0][1].device:
             continue
@@ -216,7 +217,7 @@ def float_quantize_many(tensors, exp: int, man: int, hparams):
     batch = []
     first = None
     for i, t in enumerate(tensors):
-        if is_16_bit or not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()) or t.numel() == 0:
+        if is_16_bit or not (t.is_cuda and t.dtype == torch.float32 and N.is_dense(t)) or t.numel() == 0:
             results[i] = float_quantize(t, exp, man, hparams)   # draws its own stream number
             continue
         no = _next_stream()[0]

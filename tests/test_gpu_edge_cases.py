@@ -281,3 +281,108 @@ def test_dependent_launches_inside_a_cuda_graph():
         assert torch.equal(y.view(torch.int32), want_y.view(torch.int32))
         assert torch.equal(dec.view(torch.int32), want_dec.view(torch.int32))
         assert_bit_equal(s2, want_s2, "S2FP8 in a graph")
+
+
+def test_dense_layouts_keep_their_strides():
+    """a channels_last activation / weight must come back channels_last (the reference's elementwise chain
+    preserves the memory format; `.contiguous()` would add a transpose copy and hand NCHW tensors to a channels_last
+    network).  Processed in storage order: the result is the contiguous call's on the permuted tensor, bit for bit."""
+    from argparse import ArgumentParser
+
+    from smart_compress.compress.fp8 import FP8
+    from smart_compress.compress.s2fp8 import S2FP8
+
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(8, 32, 24, 24, generator=g).to(DEV).to(memory_format=torch.channels_last)
+    assert not x.is_contiguous()
+    torch.manual_seed(4)
+    y = make_plugin()(x, tag="forward_autograd")
+    assert y.stride() == x.stride() and y.is_contiguous(memory_format=torch.channels_last)
+    torch.manual_seed(4)
+    flat = x.permute(0, 2, 3, 1).contiguous()          # the same elements in storage order
+    want = make_plugin()(flat, tag="forward_autograd")
+    assert torch.equal(y.permute(0, 2, 3, 1), want)
+    # the batched optimizer path takes such tensors in place
+    w = torch.randn(64, 16, 3, 3, generator=g).to(DEV).to(memory_format=torch.channels_last)
+    before = w.clone()
+    out = make_plugin().compress_many([w], None, tag="optimizer_weight")
+    assert out[0] is w and w.stride() == before.stride() and not torch.equal(w, before)
+    assert float((w - before).abs().max()) < float(before.std()) / 10
+    for cls in (FP8, S2FP8):
+        hp = cls.add_argparse_args(ArgumentParser()).parse_args([])
+        hp.precision = 32
+        z = cls(hp)(x, tag="t")
+        assert z.stride() == x.stride() and bool(torch.isfinite(z).all())
+    # a strided view that is NOT dense still works (copied)
+    v = torch.randn(64, 200, generator=g).to(DEV)[:, ::2]
+    assert make_plugin()(v, tag="t").shape == v.shape
+
+
+def test_hparams_edits_act_as_in_the_reference():
+    """the reference derives its ranges once, in __init__ (smart.py:75-84), and reads the threshold and the
+    widths from hparams on every call.  An in-place edit of the threshold must therefore take effect on the next call
+    (it silently did not in round 1), with the ranges unchanged — bit for bit the oracle's result for that mix."""
+    import dataclasses
+
+    fp = make_plugin(["--no_stochastic_rounding"])
+    x, _ = make_outlier_tensor(50000, seed=2)
+    xd = x.to(DEV)
+    fp(xd, tag="t")
+    fp.hparams.main_std_dev_threshold = 1.25
+    y = fp(xd, tag="t")
+    ms = fp.statistics(xd).cpu()
+    base = SmaqConfig(stochastic_rounding=False)
+
+    @dataclasses.dataclass
+    class Mixed(SmaqConfig):   # threshold re-read, ranges as derived at construction
+        @property
+        def range_normal(self):
+            return base.range_normal
+
+        @property
+        def range_outlier(self):
+            return base.range_outlier
+
+    ref = smaq_roundtrip(x, Mixed(stochastic_rounding=False, main_std_dev_threshold=1.25), mean=ms[0], std=ms[1])
+    assert_bit_equal(y.cpu(), ref.y, "threshold edited in place")
+
+
+def test_beyond_two_to_the_31_elements():
+    """The header promises 64-bit element counts: 2^31 + 2^20 + 5 elements (8.6 GB) through the statistics, the fused
+    round trip and the packed encode -> decode; the CPU oracle on slices from the start, the 2^31 boundary and the
+    ragged end (the kernels' own random numbers via oracle/rng.py with 64-bit element indices)."""
+    from oracle import pack as opack
+    from oracle import rng as orng
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 << 30:
+        pytest.skip("needs ~35 GB of device memory")
+    n = (1 << 31) + (1 << 20) + 5
+    g = torch.Generator(device=DEV).manual_seed(7)
+    xd = torch.empty(n, device=DEV)
+    for lo in range(0, n, 1 << 28):                      # generated in pieces: randn's own 2^31 limits are not the subject
+        hi = min(n, lo + (1 << 28))
+        xd[lo:hi] = torch.randn(hi - lo, generator=g, device=DEV) * 1.5 + 0.25
+    cfg = SmaqConfig()
+    ms = cabi.stats_full(xd)
+    msc = ms.cpu()
+    mean = sum(float(xd[lo:lo + (1 << 28)].double().sum()) for lo in range(0, n, 1 << 28)) / n
+    sq = sum(float(((xd[lo:lo + (1 << 28)].double() - mean) ** 2).sum()) for lo in range(0, n, 1 << 28))
+    std = (sq / (n - 1)) ** 0.5
+    assert abs(msc[0].item() - mean) <= 1e-6 * std and abs(msc[1].item() - std) <= 1e-6 * std
+    params = cabi.codec_params(cfg, seed=3, offset=11, saturate=True)
+    y = cabi.roundtrip(xd, ms, params)
+    buf, lay = cabi_pack.encode(xd, ms, params, cfg)
+    dec = cabi_pack.decode(buf, lay)
+    assert torch.equal(dec[-(1 << 22):].view(torch.int32), y[-(1 << 22):].view(torch.int32))
+    assert torch.equal(dec[: 1 << 22].view(torch.int32), y[: 1 << 22].view(torch.int32))
+    for first, count in ((0, 4096), ((1 << 31) - 2048, 4096), (n - 3000, 3000)):
+        xs = xd[first:first + count].cpu()
+        probs = torch.from_numpy(orng.probs_for(count, seed=3, offset=11, first=first))
+        ref = smaq_roundtrip(xs, cfg, probs=probs, mean=msc[0], std=msc[1], rng_rule=True, saturate=True)
+        assert_bit_equal(y[first:first + count].cpu(), ref.y, f"round trip at {first}")
+        assert_bit_equal(dec[first:first + count].cpu(), ref.y, f"decode at {first}")
+    h = N.PackedHeader.from_buffer_copy(bytes(buf[:128].cpu().numpy())[: C.sizeof(N.PackedHeader)])
+    assert h.n == n and h.status == 0 and 0.25 * n < h.n_outlier < 0.40 * n
+    del y, dec, buf, xd
+    torch.cuda.empty_cache()
