@@ -16,7 +16,14 @@ struct KernelParams {
   PhiloxKeys keys;
 };
 
-// The parameters a kernel works with: a copy of the launch parameters whose stream offset includes the device
+// The stream offset a kernel works with: the launch parameter plus the device counter.  The two hot kernels (packed
+// encoder, fused round trip) take it as a separate value and keep reading everything else — the Philox keys above
+// all — straight from the launch parameters (constant-bank operands); copying the struct cost them 1-2 %.
+__device__ __forceinline__ uint64_t resolved_offset(const KernelParams& kp) {
+  return kp.offset + (kp.offset_base ? __ldg(kp.offset_base) : 0ull);
+}
+
+// The parameters a kernel works with (everything that is not bandwidth-critical): a copy of the launch parameters whose stream offset includes the device
 // counter (the copy's other fields stay what they are — loads from the constant bank)
 __device__ __forceinline__ KernelParams resolved(const KernelParams& kp) {
   KernelParams k = kp;

@@ -384,8 +384,8 @@ __device__ __forceinline__ void take_slow(const uint4& r, ChunkBits& out, uint32
 // for its 32 elements: chunks (0, 1) and (2, 3) share one each (common.cuh: rnd16_*).
 template <bool kStochastic, bool kHasProbs, bool kCountSat>
 __device__ __forceinline__ void hot_tile(uint32_t stage, const float* __restrict__ probs, int64_t wt, bool probs_vec,
-                                         const KernelParams& kp, const Scalars& s, const Hot& hot, ChunkBits (&ch)[4],
-                                         uint32_t& n_sat) {
+                                         const KernelParams& kp, uint64_t rng_offset, const Scalars& s, const Hot& hot,
+                                         ChunkBits (&ch)[4], uint32_t& n_sat) {
   constexpr bool kRng = kStochastic && !kHasProbs;
   const int lane = lane_id();
   f32x2 sat2 = splat(0.0f);
@@ -395,8 +395,8 @@ __device__ __forceinline__ void hot_tile(uint32_t stage, const float* __restrict
   uint4 rnd[2];
   rnd[0] = rnd[1] = make_uint4(0u, 0u, 0u, 0u);
   if (kRng) {
-    rnd[0] = philox4x32(kp.keys, c_lo, c_hi, (uint32_t)kp.offset, (uint32_t)(kp.offset >> 32));
-    rnd[1] = philox4x32(kp.keys, c_lo + 32u, c_hi, (uint32_t)kp.offset, (uint32_t)(kp.offset >> 32));
+    rnd[0] = philox4x32(kp.keys, c_lo, c_hi, (uint32_t)rng_offset, (uint32_t)(rng_offset >> 32));
+    rnd[1] = philox4x32(kp.keys, c_lo + 32u, c_hi, (uint32_t)rng_offset, (uint32_t)(rng_offset >> 32));
   }
   float tmin = INFINITY;
 #pragma unroll
@@ -446,8 +446,8 @@ __device__ __forceinline__ void hot_tile(uint32_t stage, const float* __restrict
 // tile): direct global loads with bounds checks.
 template <int PM, int XB, bool kStochastic, bool kHasProbs>
 __device__ __forceinline__ void generic_tile(const float* __restrict__ x, int64_t n, const float* __restrict__ probs,
-                                          const KernelParams& kp, const Scalars& s, int64_t base, ChunkBits (&ch)[4],
-                                          uint32_t& n_sat) {
+                                          const KernelParams& kp, uint64_t rng_offset, const Scalars& s, int64_t base,
+                                          ChunkBits (&ch)[4], uint32_t& n_sat) {
   const int lane = lane_id();
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -465,7 +465,7 @@ __device__ __forceinline__ void generic_tile(const float* __restrict__ x, int64_
                             eh + 3 < n ? probs[eh + 3] : 0.f);
     }
     const uint64_t g = (uint64_t)(e >> 3);
-    if (kStochastic && !kHasProbs) rnd = rnd16_call(kp.keys, g, kp.offset);
+    if (kStochastic && !kHasProbs) rnd = rnd16_call(kp.keys, g, rng_offset);
     const int64_t left = n - e;
     take_slow(slow_chunk<PM, XB, kStochastic, kHasProbs>(v[0], v[1], p4[0], p4[1], rnd, rnd16_sub(g),
                                                          left >= 8 ? 8 : (left > 0 ? (int)left : 0), &s), ch[k], n_sat);
@@ -500,7 +500,8 @@ __global__ void __launch_bounds__(kPackThreads, SMAQ_ENC_CTAS)
   __shared__ Hot s_hot;
   __shared__ bool s_last;
 
-  const KernelParams kp = resolved(kp_);
+  const KernelParams& kp = kp_;
+  const uint64_t rng_offset = resolved_offset(kp_);
   const int lane = lane_id(), warp = warp_id();
   const uint32_t seg_addr = smem_u32(&s_seg[warp][0]);
   if (lane == 0) {
@@ -567,13 +568,13 @@ __global__ void __launch_bounds__(kPackThreads, SMAQ_ENC_CTAS)
       mbar_wait(&s_bar[warp][r & 1], (uint32_t)((r >> 1) & 1));
       if constexpr (kCanHot) {
         if (hot.ok)
-          hot_tile<kStochastic, kHasProbs, kCountSat>(stage0 + (r & 1) * kStageBytes, probs, wt, probs_vec, kp, s, hot, ch,
-                                                      n_sat_total);
+          hot_tile<kStochastic, kHasProbs, kCountSat>(stage0 + (r & 1) * kStageBytes, probs, wt, probs_vec, kp, rng_offset, s,
+                                                      hot, ch, n_sat_total);
         else
-          generic_tile<PM, XB, kStochastic, kHasProbs>(x, n, probs, kp, s, wt << 10, ch, n_sat_total);
+          generic_tile<PM, XB, kStochastic, kHasProbs>(x, n, probs, kp, rng_offset, s, wt << 10, ch, n_sat_total);
       }
     } else {
-      generic_tile<PM, XB, kStochastic, kHasProbs>(x, n, probs, kp, s, wt << 10, ch, n_sat_total);
+      generic_tile<PM, XB, kStochastic, kHasProbs>(x, n, probs, kp, rng_offset, s, wt << 10, ch, n_sat_total);
     }
     __syncwarp();  // stage fully read (lane 0 may refill it)
 
@@ -719,7 +720,8 @@ constexpr int kSpecWords = 16;
 template <int PM, int XB>
 __global__ void __launch_bounds__(kPackThreads, 4)
     decode_kernel(const smaq_packed_header* __restrict__ hdr, const uint32_t* __restrict__ planes,
-                  const uint32_t* __restrict__ extras, float* __restrict__ y, int64_t n, int all_positive, int aligned) {
+                  const uint32_t* __restrict__ extras, const uint32_t* __restrict__ seg_table, float* __restrict__ y,
+                  int64_t n, int all_positive, int aligned) {
   constexpr int kSeg = seg_words(XB);
   constexpr int kMainEntries = 1 << PM, kOutEntries = 1 << (PM + XB);
   __shared__ float s_lut[kMainEntries + kOutEntries];  // [main | outlier], indexed by the stored value U
@@ -734,7 +736,9 @@ __global__ void __launch_bounds__(kPackThreads, 4)
   uint32_t tagw = 0, bw[PM], spec = 0;
 #pragma unroll
   for (int w = 0; w < PM; ++w) bw[w] = 0;
-  const uint32_t* seg_in = extras + wt * (int64_t)kSeg;
+  // the segment's place: fixed (wt * kSeg words), or — compacted extras (smaq_extras_compact) — from a per-warp-tile
+  // table of word offsets
+  const uint32_t* seg_in = extras + (seg_table && base < n ? (int64_t)__ldg(seg_table + wt) : wt * (int64_t)kSeg);
   if (base < n) {
     const uint32_t* rec = planes + wt * (int64_t)((1 + PM) * 32) + lane;
     tagw = __ldcs(rec);
@@ -911,6 +915,68 @@ __global__ void __launch_bounds__(kPackThreads, 2)
   }
 }
 
+// ---- compaction of the extras (exact-size storage of a packed tensor) ----------------------------------------
+// The encoder writes every warp tile's segment at a fixed stride (capacity: XB bits per element); a consumer that
+// KEEPS the stream — saved activations — wants the used words only.  Two small kernels over data the stream already
+// holds: (1) one CTA turns the tag words' popcounts into the exclusive prefix of the segments' word counts (a table
+// of one uint32 per warp tile, + the total); (2) every warp copies its tile's used words to table[tile].  Traffic:
+// the tag rows (1/8 byte per element) and the used extras twice — a few per cent of the encoder's.
+template <int PM, int XB>
+__global__ void __launch_bounds__(1024) extras_scan_kernel(const uint32_t* __restrict__ planes, long long n_warp_tiles,
+                                                           uint32_t* __restrict__ table) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const int lane = lane_id(), warp = warp_id();
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (long long base = 0; base < n_warp_tiles; base += 1024) {
+    const long long t = base + threadIdx.x;
+    uint32_t words = 0;
+    if (t < n_warp_tiles) {
+      // the tile's 32 tag words (row 0 of its record): each thread sums its own tile's — 128 contiguous bytes
+      const uint4* row = reinterpret_cast<const uint4*>(planes + t * (long long)((1 + PM) * 32));
+      uint32_t pc = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 v = __ldg(row + i);
+        pc += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+      }
+      words = (pc * XB + 31) >> 5;
+    }
+    const uint32_t inc = warp_inclusive_scan(words);
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t before = s_carry, all = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) {
+      before += w < warp ? s_warp[w] : 0u;
+      all += s_warp[w];
+    }
+    if (t < n_warp_tiles) table[t] = before + inc - words;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += all;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) table[n_warp_tiles] = s_carry;
+}
+
+template <int XB>
+__global__ void __launch_bounds__(kPackThreads) extras_gather_kernel(const uint32_t* __restrict__ src,
+                                                                     const uint32_t* __restrict__ table,
+                                                                     uint32_t* __restrict__ dst, long long n_warp_tiles,
+                                                                     unsigned long long dst_words, unsigned long long* overflow) {
+  constexpr int kSeg = seg_words(XB);
+  const int lane = lane_id();
+  for (long long t = (long long)blockIdx.x * kWarpsPerCta + warp_id(); t < n_warp_tiles; t += (long long)gridDim.x * kWarpsPerCta) {
+    const uint32_t off = __ldg(table + t), cnt = __ldg(table + t + 1) - off;
+    if ((unsigned long long)off + cnt > dst_words) {  // the caller's buffer is smaller than the stream: flag it, write nothing
+      if (lane == 0 && overflow) atomicMax(overflow, (unsigned long long)off + cnt);
+      continue;
+    }
+    for (uint32_t i = lane; i < cnt; i += 32) dst[(size_t)off + i] = __ldcs(src + t * (long long)kSeg + i);
+  }
+}
+
 static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 static bool width_supported(int bits_main, int bits_outlier) {
@@ -926,7 +992,7 @@ static bool width_supported(int bits_main, int bits_outlier) {
 // SM) once, then deepen the CTAs up to kDeep tiles, then add whole waves — full waves at every size, and for huge
 // tensors the >= 8 CTAs per slot the hardware scheduler needs to even out the tail.
 #ifndef SMAQ_ENC_DEEP
-#define SMAQ_ENC_DEEP 32
+#define SMAQ_ENC_DEEP 64  // 8: 1.109 ms, 32: 1.036 ms, 64: 1.026 ms at 2^30 elements (gpurun_out/ab_deep*.json)
 #endif
 static int tiles_per_cta_for(int64_t n_cta_tiles) {
   int sms = sm_count();
@@ -989,23 +1055,26 @@ int smaq_encode_workspace_init(void* ws, size_t ws_bytes, smaq_stream_t stream) 
   return SMAQ_OK;
 }
 
-int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* probs, const smaq_codec_params* params,
-                void* packed, size_t packed_bytes, void* ws, size_t ws_bytes, smaq_stream_t stream_) {
+int smaq_encode_split(const float* x, int64_t n, const float* mean_std, const float* probs, const smaq_codec_params* params,
+                      void* head, size_t head_bytes, void* extras_buf, size_t extras_bytes, void* ws, size_t ws_bytes,
+                      smaq_stream_t stream_) {
   using namespace smaq;
   static_assert(sizeof(smaq_packed_header) <= 128, "header must fit its slot");
   static_assert(sizeof(EncodeWs) <= 64, "scratch must fit smaq_packed_layout.workspace_bytes");
   if (int rc = check_params(params)) return rc;
-  if (!x || !mean_std || !packed || !ws || n <= 0) return fail(SMAQ_ERR_ARG, "encode: null pointer or n <= 0");
+  if (!x || !mean_std || !head || !extras_buf || !ws || n <= 0) return fail(SMAQ_ERR_ARG, "encode: null pointer or n <= 0");
   smaq_packed_layout l;
   if (int rc = smaq_packed_layout_for(n, params->bits_main, params->bits_outlier, &l)) return rc;
-  if (packed_bytes < (size_t)l.total_capacity_bytes) return fail(SMAQ_ERR_WORKSPACE, "encode: packed buffer too small");
+  if (head_bytes < (size_t)l.extras_off) return fail(SMAQ_ERR_WORKSPACE, "encode: header + planes buffer too small");
+  if (extras_bytes < (size_t)l.extras_capacity_bytes) return fail(SMAQ_ERR_WORKSPACE, "encode: extras buffer too small");
   if (ws_bytes < (size_t)l.workspace_bytes) return fail(SMAQ_ERR_WORKSPACE, "encode: workspace too small");
-  if (!aligned16(packed) || !aligned16(ws)) return fail(SMAQ_ERR_ARG, "encode: packed buffer and workspace must be 16-byte aligned");
+  if (!aligned16(head) || !aligned16(extras_buf) || !aligned16(ws))
+    return fail(SMAQ_ERR_ARG, "encode: packed buffers and workspace must be 16-byte aligned");
   cudaStream_t stream = (cudaStream_t)stream_;
-  char* pb = (char*)packed;
+  char* pb = (char*)head;
   auto* hdr = (smaq_packed_header*)(pb + l.header_off);
   auto* planes = (uint32_t*)(pb + l.planes_off);
-  auto* extras = (uint32_t*)(pb + l.extras_off);
+  auto* extras = (uint32_t*)extras_buf;
   const KernelParams kp = to_kernel_params(*params);
   const int aligned = aligned16(x);
   const int pm = params->bits_main - 1, xb = params->bits_outlier - params->bits_main;
@@ -1047,24 +1116,39 @@ int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* p
   return SMAQ_OK;
 }
 
-int smaq_decode(const void* packed, size_t packed_bytes, int64_t n, int32_t bits_main, int32_t bits_outlier,
-                int32_t all_positive, float* y, smaq_stream_t stream_) {
+int smaq_encode(const float* x, int64_t n, const float* mean_std, const float* probs, const smaq_codec_params* params,
+                void* packed, size_t packed_bytes, void* ws, size_t ws_bytes, smaq_stream_t stream) {
   using namespace smaq;
-  if (!packed || !y || n <= 0) return fail(SMAQ_ERR_ARG, "decode: null pointer or n <= 0");
+  if (!params) return fail(SMAQ_ERR_ARG, "params is NULL");
+  if (!packed) return fail(SMAQ_ERR_ARG, "encode: null pointer or n <= 0");
+  smaq_packed_layout l;
+  if (int rc = smaq_packed_layout_for(n, params->bits_main, params->bits_outlier, &l)) return rc;
+  if (packed_bytes < (size_t)l.total_capacity_bytes) return fail(SMAQ_ERR_WORKSPACE, "encode: packed buffer too small");
+  return smaq_encode_split(x, n, mean_std, probs, params, packed, (size_t)l.extras_off, (char*)packed + l.extras_off,
+                           packed_bytes - (size_t)l.extras_off, ws, ws_bytes, stream);
+}
+
+int smaq_decode_split(const void* head, size_t head_bytes, const void* extras_buf, size_t extras_bytes,
+                      const uint32_t* seg_table, int64_t n, int32_t bits_main, int32_t bits_outlier, int32_t all_positive,
+                      float* y, smaq_stream_t stream_) {
+  using namespace smaq;
+  if (!head || !extras_buf || !y || n <= 0) return fail(SMAQ_ERR_ARG, "decode: null pointer or n <= 0");
   smaq_packed_layout l;
   if (int rc = smaq_packed_layout_for(n, bits_main, bits_outlier, &l)) return rc;
-  if (packed_bytes < (size_t)l.total_capacity_bytes) return fail(SMAQ_ERR_WORKSPACE, "decode: packed buffer too small");
+  if (head_bytes < (size_t)l.extras_off) return fail(SMAQ_ERR_WORKSPACE, "decode: header + planes buffer too small");
+  if (!seg_table && extras_bytes < (size_t)(l.n_warp_tiles * l.extras_stride_bytes))
+    return fail(SMAQ_ERR_WORKSPACE, "decode: extras buffer too small");
   cudaStream_t stream = (cudaStream_t)stream_;
-  const char* pb = (const char*)packed;
+  const char* pb = (const char*)head;
   auto* hdr = (const smaq_packed_header*)(pb + l.header_off);
   auto* planes = (const uint32_t*)(pb + l.planes_off);
-  auto* extras = (const uint32_t*)(pb + l.extras_off);
+  auto* extras = (const uint32_t*)extras_buf;
   const int aligned = aligned32(y);
   const int pm = bits_main - 1, xb = bits_outlier - bits_main;
   const unsigned grid = (unsigned)l.n_cta_tiles;
 #define SMAQ_DEC(PM_, XB_)                                                                                         \
   if (pm == PM_ && xb == XB_)                                                                                      \
-    decode_kernel<PM_, XB_><<<grid, kPackThreads, 0, stream>>>(hdr, planes, extras, y, n, all_positive, aligned);
+    decode_kernel<PM_, XB_><<<grid, kPackThreads, 0, stream>>>(hdr, planes, extras, seg_table, y, n, all_positive, aligned);
 #define SMAQ_DEC_ROW(PM_) SMAQ_DEC(PM_, 0) SMAQ_DEC(PM_, 1) SMAQ_DEC(PM_, 2) SMAQ_DEC(PM_, 3) SMAQ_DEC(PM_, 4)
 #ifdef SMAQ_PACK_MINIMAL
   SMAQ_DEC(5, 2)
@@ -1073,6 +1157,64 @@ int smaq_decode(const void* packed, size_t packed_bytes, int64_t n, int32_t bits
 #endif
 #undef SMAQ_DEC_ROW
 #undef SMAQ_DEC
+  SMAQ_LAUNCH_OK();
+  return SMAQ_OK;
+}
+
+int smaq_decode(const void* packed, size_t packed_bytes, int64_t n, int32_t bits_main, int32_t bits_outlier,
+                int32_t all_positive, float* y, smaq_stream_t stream) {
+  using namespace smaq;
+  if (!packed) return fail(SMAQ_ERR_ARG, "decode: null pointer or n <= 0");
+  smaq_packed_layout l;
+  if (int rc = smaq_packed_layout_for(n, bits_main, bits_outlier, &l)) return rc;
+  if (packed_bytes < (size_t)l.total_capacity_bytes) return fail(SMAQ_ERR_WORKSPACE, "decode: packed buffer too small");
+  return smaq_decode_split(packed, (size_t)l.extras_off, (const char*)packed + l.extras_off, packed_bytes - (size_t)l.extras_off,
+                           nullptr, n, bits_main, bits_outlier, all_positive, y, stream);
+}
+
+int smaq_extras_scan(const void* head, size_t head_bytes, int64_t n, int32_t bits_main, int32_t bits_outlier,
+                     uint32_t* seg_table, smaq_stream_t stream_) {
+  using namespace smaq;
+  if (!head || !seg_table || n <= 0) return fail(SMAQ_ERR_ARG, "extras_scan: null pointer or n <= 0");
+  smaq_packed_layout l;
+  if (int rc = smaq_packed_layout_for(n, bits_main, bits_outlier, &l)) return rc;
+  if (head_bytes < (size_t)l.extras_off) return fail(SMAQ_ERR_WORKSPACE, "extras_scan: header + planes buffer too small");
+  auto* planes = (const uint32_t*)((const char*)head + l.planes_off);
+  const int pm = bits_main - 1, xb = bits_outlier - bits_main;
+  cudaStream_t stream = (cudaStream_t)stream_;
+#define SMAQ_SCAN(PM_, XB_) \
+  if (pm == PM_ && xb == XB_) extras_scan_kernel<PM_, XB_><<<1, 1024, 0, stream>>>(planes, (long long)l.n_warp_tiles, seg_table);
+#define SMAQ_SCAN_ROW(PM_) SMAQ_SCAN(PM_, 0) SMAQ_SCAN(PM_, 1) SMAQ_SCAN(PM_, 2) SMAQ_SCAN(PM_, 3) SMAQ_SCAN(PM_, 4)
+#ifdef SMAQ_PACK_MINIMAL
+  SMAQ_SCAN(5, 2)
+#else
+  SMAQ_SCAN_ROW(3) SMAQ_SCAN_ROW(4) SMAQ_SCAN_ROW(5) SMAQ_SCAN_ROW(6) SMAQ_SCAN_ROW(7)
+#endif
+#undef SMAQ_SCAN_ROW
+#undef SMAQ_SCAN
+  SMAQ_LAUNCH_OK();
+  return SMAQ_OK;
+}
+
+int smaq_extras_gather(const void* extras_src, const uint32_t* seg_table, int64_t n, int32_t bits_main,
+                       int32_t bits_outlier, void* extras_dst, size_t dst_bytes, unsigned long long* overflow,
+                       smaq_stream_t stream_) {
+  using namespace smaq;
+  if (!extras_src || !seg_table || !extras_dst || n <= 0) return fail(SMAQ_ERR_ARG, "extras_gather: null pointer or n <= 0");
+  smaq_packed_layout l;
+  if (int rc = smaq_packed_layout_for(n, bits_main, bits_outlier, &l)) return rc;
+  const int xb = bits_outlier - bits_main;
+  if (xb == 0) return SMAQ_OK;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  long long want = (l.n_warp_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
+  const unsigned grid = (unsigned)(want < (long long)sms * 8 ? want : (long long)sms * 8);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const unsigned long long dw = dst_bytes / 4;
+#define SMAQ_GATHER(XB_) \
+  if (xb == XB_) extras_gather_kernel<XB_><<<grid, kPackThreads, 0, stream>>>((const uint32_t*)extras_src, seg_table, (uint32_t*)extras_dst, (long long)l.n_warp_tiles, dw, overflow);
+  SMAQ_GATHER(1) SMAQ_GATHER(2) SMAQ_GATHER(3) SMAQ_GATHER(4)
+#undef SMAQ_GATHER
   SMAQ_LAUNCH_OK();
   return SMAQ_OK;
 }

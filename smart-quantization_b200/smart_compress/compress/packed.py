@@ -20,9 +20,15 @@ def packed_layout(n: int, bits_main: int, bits_outlier: int) -> N.PackedLayout:
 
 @dataclass
 class PackedSmaq:
-    buffer: torch.Tensor          # uint8, device; capacity-sized (see used_bytes)
+    """``buffer`` alone: the whole stream in one capacity-sized allocation (header | planes | fixed-stride extras).
+    With ``extras`` set the stream is SPLIT: ``buffer`` = header + planes (exact), ``extras`` a separate allocation —
+    capacity-sized and fixed-stride right after ``SmartFP.encode(split=True)``, exact and dense (with ``table``: the
+    word offset of every warp tile's segment) after ``SmartFP.compact``."""
+    buffer: torch.Tensor          # uint8, device
     layout: N.PackedLayout
     shape: torch.Size
+    extras: torch.Tensor = None   # uint8, device (split form)
+    table: torch.Tensor = None    # int32[n_warp_tiles + 1], device (compacted form)
 
     @property
     def numel(self) -> int:
@@ -42,6 +48,10 @@ class PackedSmaq:
             "extras": (lay.extras_off, lay.n_warp_tiles * lay.extras_stride_bytes),
         }[name]
         return self.buffer[off: off + nbytes].view(torch.int32)
+
+    def allocated_bytes(self) -> int:
+        """What the stream occupies in device memory right now."""
+        return sum(int(t.numel() * t.element_size()) for t in (self.buffer, self.extras, self.table) if t is not None)
 
     def used_bytes(self) -> int:
         """Bytes that are part of the stream: header + planes + the extras words actually written (the buffer

@@ -395,7 +395,13 @@ class SmartFP(CompressionAlgorithmBase):
         lay = packed_layout(n, hp.num_bits_main, hp.num_bits_outlier)
         if mean_std is None:
             mean_std = self.statistics(flat, extra.get("_sample_idx"))
-        buf = torch.empty(lay.total_capacity_bytes, dtype=torch.uint8, device=data.device)
+        split = bool(extra.get("split"))
+        if split:  # header + planes (exact) and the extras (capacity) as two allocations: the second can be compacted
+            buf = torch.empty(lay.extras_off, dtype=torch.uint8, device=data.device)
+            ext = torch.empty(lay.extras_capacity_bytes, dtype=torch.uint8, device=data.device)
+        else:
+            buf = torch.empty(lay.total_capacity_bytes, dtype=torch.uint8, device=data.device)
+            ext = None
         stream = N.stream_ptr(data.device)
         key = (data.device.index, stream)
         ws = self._encode_ws.get(key)
@@ -409,12 +415,45 @@ class SmartFP(CompressionAlgorithmBase):
         if probs is not None:
             probs = probs.to(device=data.device, dtype=torch.float32).contiguous()
             probs_ptr = N.ptr(probs)
-        N.check(
-            lib.smaq_encode(N.ptr(flat), n, N.ptr(mean_std), probs_ptr, C.byref(params), N.ptr(buf), buf.numel(),
-                            N.ptr(ws), ws.numel(), stream),
-            "smaq_encode",
-        )
-        return PackedSmaq(buffer=buf, layout=lay, shape=data.shape)
+        if split:
+            N.check(
+                lib.smaq_encode_split(N.ptr(flat), n, N.ptr(mean_std), probs_ptr, C.byref(params), N.ptr(buf), buf.numel(),
+                                      N.ptr(ext), ext.numel(), N.ptr(ws), ws.numel(), stream),
+                "smaq_encode_split",
+            )
+        else:
+            N.check(
+                lib.smaq_encode(N.ptr(flat), n, N.ptr(mean_std), probs_ptr, C.byref(params), N.ptr(buf), buf.numel(),
+                                N.ptr(ws), ws.numel(), stream),
+                "smaq_encode",
+            )
+        return PackedSmaq(buffer=buf, layout=lay, shape=data.shape, extras=ext)
+
+    @torch.no_grad()
+    def compact(self, packed, extras_words: int):
+        """Replace a split stream's capacity-sized extras by the used words only (``extras_words`` = the header's
+        count, which the caller has read — ``packed.header()`` or an asynchronous copy): afterwards the stream occupies
+        bits_main * n_main + bits_outlier * n_outlier bits (+ table and padding), the reference's own accounting
+        (smart.py:184-187), in memory.  Two small kernels on the current stream; the old buffer is released."""
+        if packed.extras is None or packed.table is not None:
+            return packed
+        lay = packed.layout
+        if lay.extras_stride_bytes == 0:
+            return packed
+        if N.wrong_device(packed.buffer):
+            with N.on_device_of(packed.buffer):
+                return self.compact(packed, extras_words)
+        lib = N.load()
+        dev = packed.buffer.device
+        stream = N.stream_ptr(dev)
+        table = torch.empty(lay.n_warp_tiles + 1, dtype=torch.int32, device=dev)
+        dense = torch.empty((int(extras_words) + 16) * 4, dtype=torch.uint8, device=dev)  # + the decoder's look-ahead
+        N.check(lib.smaq_extras_scan(N.ptr(packed.buffer), packed.buffer.numel(), lay.n, lay.bits_main, lay.bits_outlier,
+                                     N.ptr(table), stream), "smaq_extras_scan")
+        N.check(lib.smaq_extras_gather(N.ptr(packed.extras), N.ptr(table), lay.n, lay.bits_main, lay.bits_outlier,
+                                       N.ptr(dense), int(extras_words) * 4, None, stream), "smaq_extras_gather")
+        packed.extras, packed.table = dense, table
+        return packed
 
     @torch.no_grad()
     def decode(self, packed, all_positive: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -424,6 +463,15 @@ class SmartFP(CompressionAlgorithmBase):
         lib = N.load()
         lay = packed.layout
         y = out if out is not None else torch.empty(packed.shape, dtype=torch.float32, device=packed.buffer.device)
+        ext, table = packed.extras, packed.table   # read once: a compaction may swap them
+        if ext is not None:
+            N.check(
+                lib.smaq_decode_split(N.ptr(packed.buffer), packed.buffer.numel(), N.ptr(ext), ext.numel(),
+                                      None if table is None else N.ptr(table), lay.n, lay.bits_main, lay.bits_outlier,
+                                      int(bool(all_positive)), N.ptr(y), N.stream_ptr(y.device)),
+                "smaq_decode_split",
+            )
+            return y
         N.check(
             lib.smaq_decode(N.ptr(packed.buffer), packed.buffer.numel(), lay.n, lay.bits_main, lay.bits_outlier,
                             int(bool(all_positive)), N.ptr(y), N.stream_ptr(y.device)),

@@ -90,19 +90,63 @@ class packed_saved_tensors(torch.autograd.graph.saved_tensors_hooks):
     did).  The encoder is therefore asked to put zero ON the grid (``zero_on_grid``: the mean the codes are relative
     to moves by at most half a quantisation step, on the device, no synchronisation), so 0.0 decodes to exactly 0.0.
     ``keep=`` still leaves chosen tensors alone.
+    Exact-size storage without a synchronisation (``exact_size=True``, the default): the stream is encoded into two
+    allocations — header + planes (6 bits per element, exact) and the extras at capacity (2 bits per element) — and
+    its header is copied to pinned host memory asynchronously; at a LATER pack / unpack call, once that copy has
+    landed (``event.query()``), the extras are compacted to the used words (two small kernels) and the capacity
+    buffer is released.  All but the last few saved tensors therefore occupy what the reference only accounts for
+    (smart.py:184-187): ~6.4 bits per element instead of 32, 5.0x instead of round 1's capacity-sized 4.0x.
     Encoding and decoding run on the calling thread's current stream (the backward pass decodes on
-    autograd's worker thread).  Nothing synchronises: buffers are capacity-sized (8 bits per element)."""
+    autograd's worker thread)."""
 
-    def __init__(self, codec, min_numel: int = 1 << 16, keep=None, zero_on_grid: bool = True):
+    def __init__(self, codec, min_numel: int = 1 << 16, keep=None, zero_on_grid: bool = True, exact_size: bool = True):
+        import ctypes as C
+        import threading
+        from collections import deque
+
+        from ... import _native as N
+
+        lock = threading.Lock()
+        pending = deque()          # (packed, pinned header slot, event), oldest first
+        slots = torch.empty(1024, 128, dtype=torch.uint8).pin_memory() if exact_size else None
+        # smaq_packed_header.extras_words is the uint64 at byte 72 of the slot
+        words_view = slots.numpy().view("<u8")[:, 9] if exact_size else None
+        counter = [0]
+        self.compacted = 0
+
+        def drain():
+            # compact every stream whose header has arrived (oldest first; stop at the first that has not)
+            while pending and pending[0][2].query():
+                packed, index, _ = pending.popleft()
+                codec.compact(packed, int(words_view[index]))
+                self.compacted += 1
+
         def pack(t: torch.Tensor):
             if (isinstance(t, nn.Parameter) or not t.is_cuda or t.dtype != torch.float32 or t.numel() < min_numel
                     or (keep is not None and keep(t))):
                 return t
-            return codec.encode(t.detach(), zero_on_grid=zero_on_grid)
+            exact = exact_size and not torch.cuda.is_current_stream_capturing()  # (a graph cannot poll an event)
+            packed = codec.encode(t.detach(), zero_on_grid=zero_on_grid, split=exact)
+            if exact:
+                with lock:
+                    if len(pending) >= slots.shape[0]:   # every slot in flight: wait for the oldest (never in practice)
+                        pending[0][2].synchronize()
+                    drain()
+                    index = counter[0] % slots.shape[0]
+                    counter[0] += 1
+                    slots[index].copy_(packed.buffer[:128], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    pending.append((packed, index, ev))
+            return packed
 
         def unpack(obj):
             if isinstance(obj, torch.Tensor):
                 return obj
+            if exact_size:
+                with lock:
+                    drain()
+                    return codec.decode(obj)
             return codec.decode(obj)
 
         super().__init__(pack, unpack)

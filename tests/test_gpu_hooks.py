@@ -236,8 +236,8 @@ def test_packed_saved_tensors_cut_activation_memory_and_keep_gradients_close():
 
     held_plain, g_plain = run(False)
     held_packed, g_packed = run(True)
-    # saved activations shrink 4x (1 byte of capacity per element); the network output and the packed copy of
-    # the (externally owned) input stay, so the whole graph here shrinks about 2x
+    # saved activations shrink ~5x (exact-size streams: 6.4 bits per element); the network output and the packed
+    # copy of the (externally owned) input stay, so the whole graph here shrinks about 2x
     assert held_packed < 0.6 * held_plain, (held_packed, held_plain)
     for a, b in zip(g_plain, g_packed):
         assert bool(torch.isfinite(b).all())
@@ -335,3 +335,41 @@ def test_counted_step_numbers_streams_from_a_device_counter():
         fa.offset_base = counter.data_ptr()
         assert torch.equal(cabi.float_quantize(x, fa), cabi.float_quantize(x, fb))
         assert not torch.equal(cabi.roundtrip(x, ms, a), cabi.roundtrip(x, ms, cabi.codec_params(cfg, seed=9, offset=3)))
+
+
+def test_packed_saved_tensors_exact_size_delivers_the_accounted_ratio():
+    """§8 f-2: the streams autograd holds are compacted to their used words without a synchronisation (the header is
+    copied to pinned memory asynchronously, the compaction runs at a later pack / unpack call): what stays allocated
+    per saved tensor is >= 4.8x smaller than fp32 (capacity-sized buffers: 4.0x), and compaction changes no value —
+    the gradients are bit-identical to the capacity-sized run under the same seed."""
+    from smart_compress.compress.smart import SmartFP
+    from smart_compress.util.pytorch.autograd import packed_saved_tensors
+
+    net = nn.Sequential(*[m for _ in range(6) for m in (nn.Conv2d(16, 16, 3, padding=1), nn.ReLU())]).to(DEV)
+    x = torch.randn(8, 16, 96, 96, device=DEV)
+
+    def run(exact):
+        torch.manual_seed(5)
+        codec = SmartFP(hparams())
+        kept = []
+        orig = codec.encode
+        codec.encode = lambda t, **kw: (kept.append(orig(t, **kw)), kept[-1])[1]
+        net.zero_grad()
+        ctx = packed_saved_tensors(codec, min_numel=1 << 12, exact_size=exact)
+        with ctx:
+            loss = net(x).square().mean()
+        torch.cuda.synchronize()
+        with ctx:            # one more pack call after the copies have landed drains the queue
+            torch.zeros(1 << 13, device=DEV, requires_grad=True).relu().sum()
+        sizes = [(p.allocated_bytes(), 4 * p.numel) for p in kept[:-1]]
+        loss.backward()
+        return sizes, [p.grad.clone() for p in net.parameters()], ctx
+
+    sizes_cap, g_cap, _ = run(False)
+    sizes_exact, g_exact, ctx = run(True)
+    assert ctx.compacted >= len(sizes_exact) - 1
+    ratio_cap = sum(b for _, b in sizes_cap) / sum(a for a, _ in sizes_cap)
+    ratio_exact = sum(b for _, b in sizes_exact) / sum(a for a, _ in sizes_exact)
+    assert 3.9 < ratio_cap < 4.05 and ratio_exact >= 4.8, (ratio_cap, ratio_exact)
+    for a, b in zip(g_cap, g_exact):
+        assert torch.equal(a, b)

@@ -10,6 +10,7 @@ import torch
 
 from oracle import pack as opack
 from oracle.smaq import SmaqConfig, compressed_bits, smaq_roundtrip
+from smart_compress import _native as N
 from tests import cabi, cabi_pack
 from tests.golden_util import assert_bit_equal, load_golden, uses_bn
 from tests.test_gpu_smaq import make_outlier_tensor, make_plugin
@@ -195,6 +196,45 @@ def test_zero_on_grid_keeps_exact_zeros_and_matches_the_oracle(kind):
         assert wrong <= max(2, int(2e-5 * int(zeros.sum()))), (wrong, int(zeros.sum()))
     want = smaq_roundtrip(x, cfg, probs=probs, mean=want_mean, std=msc[1], rng_rule=True, saturate=True)
     assert_bit_equal(y, want.y, "decode")
+
+
+@pytest.mark.parametrize("n", [1000, 8193, 300007, (1 << 22) + 11])
+def test_split_buffers_and_compacted_extras_match_the_oracle(n):
+    """Exact-size storage: header + planes in one buffer, the extras compacted to their used words behind a
+    per-warp-tile table (smaq_extras_scan / smaq_extras_gather).  Table = exclusive prefix of the oracle's segment
+    sizes, dense extras = the oracle's used words in tile order, decode_split of either form = the plain decode, and
+    the allocation is the reference's accounting (smart.py:184-187) plus table and padding."""
+    fp = make_plugin()
+    x, _ = make_outlier_tensor(n, seed=n + 2)
+    xd = x.to(DEV)
+    torch.manual_seed(9)
+    whole = make_plugin().encode(xd)
+    torch.manual_seed(9)
+    packed = fp.encode(xd, split=True)
+    lay = packed.layout
+    assert packed.buffer.numel() == lay.extras_off and packed.extras.numel() == lay.extras_capacity_bytes
+    hb = C.sizeof(N.PackedHeader)   # (the rest of the 128-byte header slot is never written)
+    assert torch.equal(packed.buffer[:hb], whole.buffer[:hb])
+    assert torch.equal(packed.buffer[lay.planes_off:], whole.buffer[lay.planes_off: lay.extras_off])
+    y_fixed = fp.decode(packed)
+    assert torch.equal(y_fixed, make_plugin().decode(whole))
+    h = packed.header()
+    # the oracle's view of the same stream
+    msc = torch.tensor([h.mean, h.std_raw])
+    probs = torch.from_numpy(__import__("oracle.rng", fromlist=["x"]).probs_for(n, seed=9, offset=0))
+    res = smaq_roundtrip(x, SmaqConfig(), probs=probs, mean=msc[0], std=msc[1], rng_rule=True)
+    p = opack.pack(res, SmaqConfig())
+    fp.compact(packed, h.extras_words)
+    assert packed.table is not None and h.extras_words == p.extras_words
+    table = packed.table.cpu().numpy().astype(np.int64)
+    want_table = np.concatenate([[0], np.cumsum(p.seg_used)])
+    assert np.array_equal(table, want_table)
+    dense = packed.extras[: 4 * h.extras_words].view(torch.int32).cpu().numpy().view(np.uint32)
+    want_dense = np.concatenate([p.extras[t, : p.seg_used[t]] for t in range(p.planes.shape[0])]) if h.extras_words else np.zeros(0, np.uint32)
+    assert np.array_equal(dense, want_dense)
+    assert torch.equal(fp.decode(packed), y_fixed)
+    bits = packed.allocated_bytes() * 8
+    assert bits - packed.payload_bits() <= 8 * (128 + 64 + 4) + 64 * lay.n_warp_tiles + 6 * 1024   # header, look-ahead pad, table + padding per tile, ragged last tile
 
 
 def test_plugin_encode_decode_and_size_accounting():

@@ -378,9 +378,11 @@ def test_plugin_noncontiguous_and_shapes():
     x = torch.randn(6, 5, 7, 3, device=DEV)
     xt = x.permute(0, 3, 1, 2)  # non-contiguous view, as cuDNN channels-last outputs can be
     y = fp(xt)
-    assert y.shape == xt.shape
-    ref = fp(xt.contiguous())
-    assert torch.equal(y, ref)
+    assert y.shape == xt.shape and y.stride() == xt.stride()   # a dense view keeps its layout (as the reference's chain does)
+    assert torch.equal(y, fp(x).permute(0, 3, 1, 2))            # processed in storage order: the contiguous call's bits
+    ref = fp(xt.contiguous())                                   # logical order: the statistics may differ in the last bit
+    step = float(x.std()) / 15
+    assert float((y - ref).abs().max()) <= 1.01 * step and float(((y - ref).abs() > 1e-6).float().mean()) < 1e-3
 
 
 def test_plugin_refuses_cpu_tensors():

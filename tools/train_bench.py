@@ -47,8 +47,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--no-batched-optimizer", action="store_true",
                     help="per-tensor optimizer-side calls (the reference's loop) instead of compress_many")
-    ap.add_argument("--packed-activations", action="store_true",
-                    help="keep autograd's saved tensors as packed SmaQ streams (not in the reference; changes numerics)")
+    ap.add_argument("--packed-activations", nargs="?", const="exact", default="", choices=["exact", "capacity"],
+                    help="keep autograd's saved tensors as packed SmaQ streams (not in the reference; changes numerics); "
+                         "exact: compacted to their used words (5.0x), capacity: 8 bits per element (4.0x)")
     ap.add_argument("--compress_loss", action="store_true")
     ap.add_argument("--compress-allreduce", default="", choices=["", "p2p", "nccl"],
                     help="gradient compression fused with the all-reduce (smart_compress/util/pytorch/allreduce.py; not in the "
@@ -163,6 +164,7 @@ def run_training(model_name="resnet34", batch=32, image=224, seq=128, compress="
 
         pack_codec = fn.inner if isinstance(getattr(fn, "inner", None), SmartFP) else SmartFP(parse_compression_args(["--compress", "smart"]))
     net = nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    packed_ctx = packed_saved_tensors(pack_codec, exact_size=packed_activations != "capacity") if packed_activations else None
     car = None
     if compress_allreduce and world > 1:
         from smart_compress.compress.smart import SmartFP
@@ -173,8 +175,7 @@ def run_training(model_name="resnet34", batch=32, image=224, seq=128, compress="
 
     def closure():
         opt.zero_grad(set_to_none=True)
-        ctx = packed_saved_tensors(pack_codec) if packed_activations else contextlib.nullcontext()
-        with ctx:
+        with (packed_ctx if packed_activations else contextlib.nullcontext()):
             loss = loss_fn(net)
         compress_loss(loss, fn, hp)   # models/base.py:114-115
         loss.backward()
