@@ -30,7 +30,7 @@ extern "C" {
 #define SMAQ_B200_ABI_VERSION 4 /* 2: packed stream SQB2, count_saturated, smaq_compress, tensor_desc.stream; 3: smaq_float_quantize_multi;
                                     4: smaq_roundtrip_bn, smaq_roundtrip_multi(mean_std_out), range_std in the sampled statistics,
                                        packed stream SQB3 (one-pass encoder, smaq_encode_workspace_init), offset_base + smaq_counter_add, zero_on_grid, smaq_decode_sum, smaq_s2fp8_multi,
-                                       split buffers + smaq_extras_scan / _gather */
+                                       split buffers + smaq_extras_compact */
 
 typedef void* smaq_stream_t; /* cudaStream_t */
 
@@ -217,11 +217,12 @@ int smaq_decode(const void* packed, size_t packed_bytes, int64_t n, int32_t bits
 /* The same with the stream in TWO buffers: `head` = header + planes (layout.extras_off bytes, exact for n) and
  * `extras` (layout.extras_capacity_bytes for smaq_encode_split).  A consumer that KEEPS the stream (saved
  * activations) compacts the extras afterwards and frees the capacity-sized buffer:
- *   smaq_extras_scan   : seg_table[t] = first word of warp tile t's segment in the compacted extras, t = 0 ..
- *                        n_warp_tiles (the last entry is the total = header.extras_words); one CTA, reads the tag words;
- *   smaq_extras_gather : copies every tile's used words from the fixed-stride buffer to extras_dst[seg_table[t] ...];
- *                        a destination too small for the stream is reported in *overflow (device, optional: the
- *                        largest word index needed) and nothing is written past it;
+ *   smaq_extras_compact: seg_table[t] = first word of warp tile t's segment in the compacted extras, t = 0 ..
+ *                        n_warp_tiles (the last entry is the total = header.extras_words), computed from the tag
+ *                        words, and every tile's used words copied from the fixed-stride buffer to
+ *                        extras_dst[seg_table[t] ...].  seg_table holds smaq_extras_table_entries(n) uint32 (table +
+ *                        scratch).  A destination too small for the stream is reported in *overflow (device,
+ *                        optional: the largest word index needed) and nothing is written past it.  Two launches;
  *   smaq_decode_split  : seg_table == NULL -> fixed-stride extras; else the compacted form.
  * Stored bits then: bits_main * n_main + bits_outlier * n_outlier (+ < 32 pad bits and 32 table bits per 1024
  * elements) — the reference's own accounting (smart.py:184-187) delivered in memory, not only logged. */
@@ -231,11 +232,10 @@ int smaq_encode_split(const float* x, int64_t n, const float* mean_std, const fl
 int smaq_decode_split(const void* head, size_t head_bytes, const void* extras, size_t extras_bytes,
                       const uint32_t* seg_table, int64_t n, int32_t bits_main, int32_t bits_outlier, int32_t all_positive,
                       float* y, smaq_stream_t stream);
-int smaq_extras_scan(const void* head, size_t head_bytes, int64_t n, int32_t bits_main, int32_t bits_outlier,
-                     uint32_t* seg_table, smaq_stream_t stream);
-int smaq_extras_gather(const void* extras_src, const uint32_t* seg_table, int64_t n, int32_t bits_main,
-                       int32_t bits_outlier, void* extras_dst, size_t dst_bytes, unsigned long long* overflow,
-                       smaq_stream_t stream);
+int64_t smaq_extras_table_entries(int64_t n);
+int smaq_extras_compact(const void* head, size_t head_bytes, const void* extras_src, int64_t n, int32_t bits_main,
+                        int32_t bits_outlier, uint32_t* seg_table, void* extras_dst, size_t dst_bytes,
+                        unsigned long long* overflow, smaq_stream_t stream);
 
 /* The reduce step of a COMPRESSED all-reduce (not in the reference, which compresses after DDP's
  * fp32 all-reduce, optimizer.py:135-141 — so this is opt-in and changes numerics).  `packed` is a HOST array of

@@ -142,8 +142,8 @@ _SIGNATURES = {
     "smaq_decode": (C.c_int, [_P, C.c_size_t, _I64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "smaq_encode_split": (C.c_int, [_P, _I64, _P, _P, C.POINTER(CodecParams), _P, C.c_size_t, _P, C.c_size_t, _P, C.c_size_t, _P]),
     "smaq_decode_split": (C.c_int, [_P, C.c_size_t, _P, C.c_size_t, _P, _I64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
-    "smaq_extras_scan": (C.c_int, [_P, C.c_size_t, _I64, C.c_int32, C.c_int32, _P, _P]),
-    "smaq_extras_gather": (C.c_int, [_P, _P, _I64, C.c_int32, C.c_int32, _P, C.c_size_t, _P, _P]),
+    "smaq_extras_table_entries": (_I64, [_I64]),
+    "smaq_extras_compact": (C.c_int, [_P, C.c_size_t, _P, _I64, C.c_int32, C.c_int32, _P, _P, C.c_size_t, _P, _P]),
     "smaq_decode_sum": (C.c_int, [_P, C.c_int32, C.c_size_t, _I64, C.c_int32, C.c_int32, _I64, _I64, C.c_float, _P, _P]),
     "smaq_float_quantize": (C.c_int, [_P, _P, _I64, _P, C.POINTER(FloatqParams), _P]),
     "smaq_floatq_multi_workspace_bytes": (C.c_size_t, [C.c_int32]),

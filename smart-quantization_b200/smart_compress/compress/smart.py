@@ -446,12 +446,11 @@ class SmartFP(CompressionAlgorithmBase):
         lib = N.load()
         dev = packed.buffer.device
         stream = N.stream_ptr(dev)
-        table = torch.empty(lay.n_warp_tiles + 1, dtype=torch.int32, device=dev)
+        table = torch.empty(int(lib.smaq_extras_table_entries(lay.n)), dtype=torch.int32, device=dev)
         dense = torch.empty((int(extras_words) + 16) * 4, dtype=torch.uint8, device=dev)  # + the decoder's look-ahead
-        N.check(lib.smaq_extras_scan(N.ptr(packed.buffer), packed.buffer.numel(), lay.n, lay.bits_main, lay.bits_outlier,
-                                     N.ptr(table), stream), "smaq_extras_scan")
-        N.check(lib.smaq_extras_gather(N.ptr(packed.extras), N.ptr(table), lay.n, lay.bits_main, lay.bits_outlier,
-                                       N.ptr(dense), int(extras_words) * 4, None, stream), "smaq_extras_gather")
+        N.check(lib.smaq_extras_compact(N.ptr(packed.buffer), packed.buffer.numel(), N.ptr(packed.extras), lay.n,
+                                        lay.bits_main, lay.bits_outlier, N.ptr(table), N.ptr(dense), int(extras_words) * 4,
+                                        None, stream), "smaq_extras_compact")
         packed.extras, packed.table = dense, table
         return packed
 

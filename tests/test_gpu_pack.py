@@ -4,6 +4,8 @@ Contract: given the reference's mean/std and the same uniform numbers, the packe
 words, base fields, extras stream, tile table, counters) is BYTE-IDENTICAL to oracle/pack.py
 applied to the reference's integer codes, and decode() is bit-identical to the reference's
 round trip with codes saturated at the field width."""
+import ctypes as C
+
 import numpy as np
 import pytest
 import torch
@@ -201,7 +203,7 @@ def test_zero_on_grid_keeps_exact_zeros_and_matches_the_oracle(kind):
 @pytest.mark.parametrize("n", [1000, 8193, 300007, (1 << 22) + 11])
 def test_split_buffers_and_compacted_extras_match_the_oracle(n):
     """Exact-size storage: header + planes in one buffer, the extras compacted to their used words behind a
-    per-warp-tile table (smaq_extras_scan / smaq_extras_gather).  Table = exclusive prefix of the oracle's segment
+    per-warp-tile table (smaq_extras_compact).  Table = exclusive prefix of the oracle's segment
     sizes, dense extras = the oracle's used words in tile order, decode_split of either form = the plain decode, and
     the allocation is the reference's accounting (smart.py:184-187) plus table and padding."""
     fp = make_plugin()
@@ -226,7 +228,7 @@ def test_split_buffers_and_compacted_extras_match_the_oracle(n):
     p = opack.pack(res, SmaqConfig())
     fp.compact(packed, h.extras_words)
     assert packed.table is not None and h.extras_words == p.extras_words
-    table = packed.table.cpu().numpy().astype(np.int64)
+    table = packed.table[: lay.n_warp_tiles + 1].cpu().numpy().astype(np.int64)
     want_table = np.concatenate([[0], np.cumsum(p.seg_used)])
     assert np.array_equal(table, want_table)
     dense = packed.extras[: 4 * h.extras_words].view(torch.int32).cpu().numpy().view(np.uint32)
