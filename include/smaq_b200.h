@@ -298,6 +298,15 @@ int smaq_s2fp8_multi(const smaq_tensor_desc* descs, int32_t count, int64_t total
  * of smaq_s2fp8_apply alone would hide a one-ulp difference with probability 1 - 2^-21 per element. */
 int smaq_selftest_pow(const float* a, const float* y, float* out, int32_t* accepted, int64_t n, smaq_stream_t stream);
 
+/* Test hook for the S2FP8 apply kernel's screened path (an approximate |x|^alpha decides every element whose
+ * rounding it cannot change; the rest are recomputed exactly).  Measures on the device, into six floats:
+ *   out[0] max |lg2.approx(a) - log2 a| over EVERY normal a in [0.5, 2];  out[1] max relative error of lg2.approx
+ *   over every other normal a;  out[2] max relative error of ex2.approx over EVERY t in [-126, 128);
+ *   out[3] max |bits(v~) - bits(v)| / margin over `samples` random (alpha, beta, a) — must stay below 1;
+ *   out[4] the largest margin met;  out[5] the number of samples that qualified.
+ * The kernel's error constants are asserted against out[0..2] by the tests. */
+int smaq_selftest_s2_screen(float* out6, int64_t samples, smaq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

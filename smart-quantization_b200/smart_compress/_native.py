@@ -153,6 +153,7 @@ _SIGNATURES = {
     "smaq_s2fp8_stats": (C.c_int, [_P, _I64, _P, _P, C.c_size_t, _P]),
     "smaq_s2fp8_apply": (C.c_int, [_P, _P, _I64, _P, _P, C.POINTER(FloatqParams), _P]),
     "smaq_selftest_pow": (C.c_int, [_P, _P, _P, _P, _I64, _P]),
+    "smaq_selftest_s2_screen": (C.c_int, [_P, _I64, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -155,5 +155,13 @@ def selftest_pow(a, y):
     return out, acc
 
 
+def selftest_s2_screen(samples, dev="cuda:0"):
+    """[lg2 abs err, lg2 rel err, ex2 rel err, bound ratio, largest margin, samples used] (test hook)."""
+    out = torch.zeros(6, dtype=torch.float32, device=dev)
+    N.check(N.load().smaq_selftest_s2_screen(out.data_ptr(), samples, N.stream_ptr(out.device)), "selftest_s2_screen")
+    torch.cuda.synchronize()
+    return out.cpu().tolist()
+
+
 def mean_std_tensor(mean, std, dev):
     return torch.tensor([float(mean), float(std)], dtype=torch.float32, device=dev)

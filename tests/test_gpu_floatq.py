@@ -121,6 +121,84 @@ def test_s2fp8_apply_bit_exact_vs_torch_cuda_oracle(n):
     assert int(diff.sum()) == 0, f"{int(diff.sum())} of {n} differ"
 
 
+# ---- the screened path of the apply kernel (approximate pow decides, near-carry elements are recomputed) ---------
+# the constants of float_quantize.cu (kLg2AbsErr, kLg2RelErr, kEx2RelErr): keep in step
+S2_SCREEN_CONSTANTS = (4.8e-7, 3.0e-7, 4.8e-7)
+
+
+def test_s2fp8_screen_error_constants_hold_for_every_input_of_the_special_function_unit():
+    """The margin the screened path trusts is built from three error constants of lg2.approx / ex2.approx.  They
+    are measured here over EVERY normal input of lg2 and every input of ex2 in [-126, 128) against fp64, and must
+    leave 20 % of headroom; the end-to-end bound |bits(v~) - bits(v)| <= margin is measured over 2^26 random
+    (alpha, beta, magnitude) triples and must leave headroom too."""
+    lg2_abs, lg2_rel, ex2_rel, ratio, margin_max, used = cabi.selftest_s2_screen(1 << 26)
+    print(f"lg2 abs {lg2_abs:.3e} rel {lg2_rel:.3e}  ex2 rel {ex2_rel:.3e}  bound ratio {ratio:.3f}  "
+          f"margin max {margin_max:.0f}  samples {used:.0f}")
+    assert 0 < lg2_abs <= S2_SCREEN_CONSTANTS[0] / 1.2
+    assert 0 < lg2_rel <= S2_SCREEN_CONSTANTS[1] / 1.2
+    assert 0 < ex2_rel <= S2_SCREEN_CONSTANTS[2] / 1.2
+    assert used > (1 << 24)
+    assert 0 < ratio <= 0.8
+    assert margin_max <= 4096
+
+
+def _s2_scale_case(case, n, seed):
+    g = torch.Generator().manual_seed(seed)
+    if case == "unit":
+        x = torch.randn(n, generator=g)
+    elif case == "gradient":       # beta ~ +60: the margin grows with |beta|
+        x = torch.randn(n, generator=g) * 3e-6
+    elif case == "large":          # beta negative
+        x = torch.randn(n, generator=g) * 2e5
+    elif case == "relu":
+        x = torch.randn(n, generator=g).clamp_(min=0)
+    elif case == "heavy_tail":     # small alpha
+        x = torch.randn(n, generator=g) * torch.exp2(4 * torch.randn(n, generator=g))
+    else:
+        raise KeyError(case)
+    return x
+
+
+@pytest.mark.parametrize("rounding", ["stochastic", "nearest"])
+@pytest.mark.parametrize("case", ["unit", "gradient", "large", "relu", "heavy_tail"])
+def test_s2fp8_apply_screened_path_bit_exact_at_2_pow_24(case, rounding):
+    """2^24 elements per case: a few thousand of them fall within the margin of a carry and are recomputed; all
+    of them must carry the bits torch's CUDA operators give."""
+    n = 1 << 24
+    xd = _s2_scale_case(case, n, seed=len(case)).to(DEV)
+    mu_max = cabi.s2fp8_stats(xd)
+    if rounding == "stochastic":
+        r = torch.randint(0, 2**31 - 1, (n,), generator=torch.Generator(device=DEV).manual_seed(5), dtype=torch.int32,
+                          device=DEV)
+        got = cabi.s2fp8_apply(xd, mu_max, cabi.floatq_params(5, 2), rand_bits=r)
+    else:
+        r = torch.full((n,), 1 << 20, dtype=torch.int32, device=DEV)
+        got = cabi.s2fp8_apply(xd, mu_max, cabi.floatq_params(5, 2, rounding=0))
+    want, _, _, _ = os2.s2fp8(xd, r, mu=mu_max[0].clone(), m=mu_max[1].clone())
+    diff = (got.view(torch.int32) != want.view(torch.int32)) & ~(torch.isnan(got) & torch.isnan(want))
+    assert int(diff.sum()) == 0, f"{case}: {int(diff.sum())} of {n} differ, first at {int(diff.nonzero()[0])}"
+
+
+@pytest.mark.parametrize("case", ["unit", "gradient", "relu"])
+def test_s2fp8_apply_adversarial_random_numbers_at_the_carry(case):
+    """Random integers chosen so that bits(v) + r lands within +-3 of a multiple of 2^21 for EVERY element: the
+    rounding direction then hangs on the last bits of powf.  An approximate pow that was trusted there would be
+    wrong on about half of them; the screen must send all of them to the exact path."""
+    n = 1 << 20
+    xd = _s2_scale_case(case, n, seed=9).to(DEV)
+    mu_max = cabi.s2fp8_stats(xd)
+    mu, m = mu_max[0].clone(), mu_max[1].clone()
+    alpha = 15.0 / (m - mu)
+    beta_pow2 = 2.0 ** (-alpha * mu)
+    pre = xd.abs().pow_(alpha).mul_(beta_pow2)            # v, as the reference's chain computes it on this GPU
+    d = torch.randint(-3, 4, (n,), device=DEV, dtype=torch.int32)
+    r = (-(pre.view(torch.int32)) + d) & ((1 << 21) - 1)  # bits(v) + r == d (mod 2^21)
+    got = cabi.s2fp8_apply(xd, mu_max, cabi.floatq_params(5, 2), rand_bits=r)
+    want, _, _, _ = os2.s2fp8(xd, r, mu=mu, m=m)
+    diff = (got.view(torch.int32) != want.view(torch.int32)) & ~(torch.isnan(got) & torch.isnan(want))
+    assert int(diff.sum()) == 0, f"{case}: {int(diff.sum())} of {n} differ, first at {int(diff.nonzero()[0])}"
+
+
 def test_s2fp8_plugin_vs_cpu_oracle_tolerance():
     """Against the CPU evaluation (different libm): the quantised intermediate may flip on a
     vanishing fraction of elements; everywhere else the result agrees to 4 ulp."""

@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--compress", default="smart", choices=["smart", "fp8", "s2fp8", "fp16", "bf16", "fp32"])
     ap.add_argument("--codec", default="b200", choices=["b200", "reference-eager"])
     ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--lr", type=float, default=None,
+                    help="learning rate (default: SGD 0.1 / AdamW 2e-5). With 8-bit codecs on EVERY tensor and random data "
+                         "0.1 diverges within ~50 steps; a run whose loss is not finite times the codecs' NaN paths")
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--no-batched-optimizer", action="store_true",
                     help="per-tensor optimizer-side calls (the reference's loop) instead of compress_many")
@@ -114,7 +117,7 @@ def build_model(model_name, batch, image, seq, device):
 def run_training(model_name="resnet34", batch=32, image=224, seq=128, compress="smart", steps=50, warmup=10,
                  device=None, world=1, local=0, codec="b200", only=DATA_STRUCTURES, batched_optimizer=True,
                  packed_activations=False, compress_loss_flag=False, profile=False, seed=1234, clocks=None,
-                 cuda_graph=False, compress_allreduce=""):
+                 cuda_graph=False, compress_allreduce="", lr=None):
     """`steps` timed training steps after `warmup` untimed ones; returns a dict (device-timed, max over ranks)."""
     from smart_compress.util.pytorch.autograd import packed_saved_tensors
     from smart_compress.util.train import build_compression, compress_loss, compression_argv, parse_compression_args
@@ -147,9 +150,9 @@ def run_training(model_name="resnet34", batch=32, image=224, seq=128, compress="
     rest = [p for m in model.modules() if type(m) != nn.BatchNorm2d for p in m.parameters(recurse=False)]
     groups = [dict(params=bn, no_weight_compression=True), dict(params=rest)] if bn else [dict(params=rest)]
     if model_name.startswith("resnet"):
-        inner = torch.optim.SGD(groups, lr=0.1, momentum=0.9, weight_decay=0)
+        inner = torch.optim.SGD(groups, lr=0.1 if lr is None else lr, momentum=0.9, weight_decay=0)
     else:
-        inner = torch.optim.AdamW(groups, lr=2e-5, capturable=bool(cuda_graph))
+        inner = torch.optim.AdamW(groups, lr=2e-5 if lr is None else lr, capturable=bool(cuda_graph))
 
     if codec == "reference-eager":
         assert compress == "smart"
@@ -294,7 +297,7 @@ def main():
     r = run_training(a.model, a.batch, a.image, a.seq, a.compress, a.steps, a.warmup, device, world, local,
                      codec=a.codec, only=tuple(a.only.split(",")), batched_optimizer=not a.no_batched_optimizer,
                      packed_activations=a.packed_activations, compress_loss_flag=a.compress_loss, profile=a.profile,
-                     cuda_graph=a.cuda_graph, compress_allreduce=a.compress_allreduce)
+                     cuda_graph=a.cuda_graph, compress_allreduce=a.compress_allreduce, lr=a.lr)
     if rank == 0:
         prof = r.pop("profile", None)
         line = {"metric": f"{a.model}_train_{r['unit'].replace('/', '_per_')}", **r, "higher_is_better": True,
