@@ -54,6 +54,9 @@ def parse():
                     help="keep autograd's saved tensors as packed SmaQ streams (not in the reference; changes numerics); "
                          "exact: compacted to their used words (5.0x), capacity: 8 bits per element (4.0x)")
     ap.add_argument("--compress_loss", action="store_true")
+    ap.add_argument("--find-nonfinite", action="store_true",
+                    help="debugging: report the first codec call that turns a finite tensor into a non-finite one "
+                         "(synchronises every call; per-tensor optimizer calls)")
     ap.add_argument("--compress-allreduce", default="", choices=["", "p2p", "nccl"],
                     help="gradient compression fused with the all-reduce (smart_compress/util/pytorch/allreduce.py; not in the "
                          "reference, changes numerics): DDP's fp32 all-reduce is replaced by packed SmaQ streams read over NVLink")
@@ -117,7 +120,7 @@ def build_model(model_name, batch, image, seq, device):
 def run_training(model_name="resnet34", batch=32, image=224, seq=128, compress="smart", steps=50, warmup=10,
                  device=None, world=1, local=0, codec="b200", only=DATA_STRUCTURES, batched_optimizer=True,
                  packed_activations=False, compress_loss_flag=False, profile=False, seed=1234, clocks=None,
-                 cuda_graph=False, compress_allreduce="", lr=None):
+                 cuda_graph=False, compress_allreduce="", lr=None, find_nonfinite=False):
     """`steps` timed training steps after `warmup` untimed ones; returns a dict (device-timed, max over ranks)."""
     from smart_compress.util.pytorch.autograd import packed_saved_tensors
     from smart_compress.util.train import build_compression, compress_loss, compression_argv, parse_compression_args
@@ -129,6 +132,9 @@ def run_training(model_name="resnet34", batch=32, image=224, seq=128, compress="
         argv.append("--no_compress")
     hp = parse_compression_args(argv)
     calls = Counter()
+    nonfinite = {}
+    if find_nonfinite:
+        batched_optimizer = False
 
     class Counting:  # counts calls per tag; forwards compress_many when allowed
         def __init__(self, inner):
@@ -138,7 +144,14 @@ def run_training(model_name="resnet34", batch=32, image=224, seq=128, compress="
 
         def __call__(self, t, tag=None, **kw):
             calls[tag] += 1
-            return self.inner(t, tag=tag, **kw)
+            out = self.inner(t, tag=tag, **kw)
+            if find_nonfinite and not nonfinite and bool(torch.isfinite(t).all()) and not bool(torch.isfinite(out).all()):
+                a = t.abs()
+                nonfinite.update(call=sum(calls.values()), tag=tag, numel=t.numel(), shape=list(t.shape),
+                                 absmax=float(a.max()), absmin_nonzero=float(a[a > 0].min()) if bool((a > 0).any()) else 0.0,
+                                 zero_fraction=float((a == 0).float().mean()),
+                                 bad_out_fraction=float((~torch.isfinite(out)).float().mean()))
+            return out
 
         def _many(self, tensors, kwargs_list=None, tag=None):
             calls[f"{tag} (batched)"] += len(tensors)
@@ -248,6 +261,7 @@ def run_training(model_name="resnet34", batch=32, image=224, seq=128, compress="
         "codec_calls_per_step": per_step_calls if cuda_graph else
                                 {str(k): v // steps for k, v in sorted(calls.items(), key=lambda kv: str(kv[0]))},
         "cuda_graph": bool(cuda_graph),
+        "first_nonfinite": nonfinite or None,
         "compress_allreduce": compress_allreduce or None,
         "allreduce_stats": None if car is None else dict(car.stats),
     }
@@ -297,7 +311,8 @@ def main():
     r = run_training(a.model, a.batch, a.image, a.seq, a.compress, a.steps, a.warmup, device, world, local,
                      codec=a.codec, only=tuple(a.only.split(",")), batched_optimizer=not a.no_batched_optimizer,
                      packed_activations=a.packed_activations, compress_loss_flag=a.compress_loss, profile=a.profile,
-                     cuda_graph=a.cuda_graph, compress_allreduce=a.compress_allreduce, lr=a.lr)
+                     cuda_graph=a.cuda_graph, compress_allreduce=a.compress_allreduce, lr=a.lr,
+                     find_nonfinite=a.find_nonfinite)
     if rank == 0:
         prof = r.pop("profile", None)
         line = {"metric": f"{a.model}_train_{r['unit'].replace('/', '_per_')}", **r, "higher_is_better": True,
