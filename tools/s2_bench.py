@@ -56,7 +56,10 @@ def main():
             N.check(lib.smaq_s2fp8_apply(x.data_ptr(), y.data_ptr(), n, mm.data_ptr(), None, C.byref(p8), st), "apply")
 
         out = {"input": name, "log2n": a.log2n, "lib": os.path.basename(os.environ.get("SMAQ_B200_LIB", "libsmaq_b200.so"))}
-        for label, fn, bytes_per in (("stats", stats, 4), ("apply", apply, 8)):
+        def fp8():
+            N.check(lib.smaq_float_quantize(x.data_ptr(), y.data_ptr(), n, None, C.byref(p8), st), "fp8")
+
+        for label, fn, bytes_per in (("stats", stats, 4), ("apply", apply, 8), ("fp8", fp8, 8)):
             stats()
             for _ in range(3):
                 fn()
