@@ -403,9 +403,11 @@ def run_b200(args):
     # ---- end to end through the plugin API with host buffers ---------------------------------------------
     if not args.no_e2e:
         e2e_steps = max(1, min(args.steps, 20))
-        # at N > 1 the pinned pages are first-touched on the GPU's own NUMA node (at N = 1 the CPU baseline leg
-        # later in this process wants every core)
-        numa = bind_to_gpu_cpus(local) if world > 1 else "not bound (single GPU)"
+        # the pinned pages are first-touched on the GPU's own NUMA node (a box whose launcher started the process
+        # on the other socket moved them over the inter-socket link: 115 instead of 94-98 ms per step); at N = 1 the
+        # affinity is restored after this leg — the CPU baseline later in this process wants every core
+        affinity_before = os.sched_getaffinity(0)
+        numa = bind_to_gpu_cpus(local)
         hx = torch.empty(n, dtype=torch.float32, pin_memory=True)
         hy = torch.empty(n, dtype=torch.float32, pin_memory=True)
         hx.copy_(x)
@@ -471,6 +473,8 @@ def run_b200(args):
         }
         x = dxs[0]
         del hx, hy, dys
+        if world == 1:
+            os.sched_setaffinity(0, affinity_before)
 
     # ---- size / codec sweep and the CPU baseline: rank 0 at N = 1 only ---------------------------------------
     if world == 1 and not args.no_sweep:

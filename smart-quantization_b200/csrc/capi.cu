@@ -38,9 +38,17 @@ int sm_count() {
   return v;
 }
 
-bool dependent_launch_enabled() {
-  static const bool on = [] { const char* e = getenv("SMAQ_DEPENDENT_LAUNCH"); return !e || atoi(e) != 0; }();
-  return on;
+static int dependent_launch_level() {
+  static const int level = [] { const char* e = getenv("SMAQ_DEPENDENT_LAUNCH"); return e ? atoi(e) : 2; }();
+  return level;
+}
+bool dependent_launch_enabled() { return dependent_launch_level() != 0; }
+
+void set_first_kernel_dependent(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr) {
+  attr->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr->val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = dependent_launch_level() >= 2 ? 1 : 0;
 }
 
 void set_dependent_launch(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr) {

@@ -24,6 +24,11 @@ int sm_count();  // cached per device, immutable once read
 // SMAQ_DEPENDENT_LAUNCH=0 makes them ordinary launches (tools/compress_ab.sh).
 bool dependent_launch_enabled();
 void set_dependent_launch(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr);
+// The FIRST kernel of a codec call as a programmatic dependent of whatever kernel precedes it in the stream (level 2,
+// the default; SMAQ_DEPENDENT_LAUNCH=1 keeps only the launches inside a call).  Such a kernel executes
+// griddepcontrol.wait before it touches global memory, so it is correct behind any producer; what it gains is that
+// its launch no longer waits for the producer's completion + memory flush to be processed by the front end.
+void set_first_kernel_dependent(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr);
 
 #define SMAQ_CUDA_OK(expr)                                                              \
   do {                                                                                  \

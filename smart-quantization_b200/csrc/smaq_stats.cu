@@ -28,6 +28,9 @@ __global__ void __launch_bounds__(kStatsThreads, SMAQ_STATS_CTAS_PER_SM) stats_k
                                                               float* __restrict__ out, StatsWs* ws) {
   __shared__ Acc smem[kStatsThreads / 32];
   __shared__ bool is_last;
+  // launched as a programmatic dependent of the tensor's producer (set_first_kernel_dependent): nothing is read
+  // before that kernel has completed; behind an ordinary launch this returns at once
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // a kernel launched behind this one as a programmatic dependent (smaq_compress's round trip) may become resident
   // as soon as this grid's CTAs leave; it waits for this grid's completion before it reads mean/std
   asm volatile("griddepcontrol.launch_dependents;");
@@ -140,11 +143,15 @@ static int launch_stats(const float* x, int64_t n, int unbiased, float* out, voi
   // the arrival ticket must start at zero; the kernel's last block leaves it at zero again, so a workspace
   // that was zeroed once (smaq_compress_workspace_init) needs no memset node per call
   if (!ticket_is_zero && grid > 1) SMAQ_CUDA_OK(cudaMemsetAsync(ws, 0, 16, stream));
-  if (aligned16(x))
-    stats_kernel<kKind, true><<<grid, kStatsThreads, 0, stream>>>(x, n, unbiased, out, (StatsWs*)ws);
-  else
-    stats_kernel<kKind, false><<<grid, kStatsThreads, 0, stream>>>(x, n, unbiased, out, (StatsWs*)ws);
-  SMAQ_LAUNCH_OK();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kStatsThreads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  set_first_kernel_dependent(cfg, attr);
+  StatsWs* sws = (StatsWs*)ws;
+  if (aligned16(x)) SMAQ_CUDA_OK(cudaLaunchKernelEx(&cfg, stats_kernel<kKind, true>, x, n, unbiased, out, sws));
+  else SMAQ_CUDA_OK(cudaLaunchKernelEx(&cfg, stats_kernel<kKind, false>, x, n, unbiased, out, sws));
   return SMAQ_OK;
 }
 
