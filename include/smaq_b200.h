@@ -125,7 +125,10 @@ int smaq_roundtrip_bn(const float* x, float* y, int64_t n, const float* mean_std
  * (smart.py:130-182 with the reference's default flags): what the training hooks issue hundreds of
  * times per step.  Two kernels on `stream`: the statistics kernel and, as a programmatic dependent launch that
  * overlaps its tail (up to 2^27 elements; SMAQ_DEPENDENT_LAUNCH=0 in the environment: an ordinary launch), the
- * round trip; bit-identical to smaq_stats_full followed by smaq_roundtrip.  The statistics live in the workspace
+ * round trip; bit-identical to smaq_stats_full followed by smaq_roundtrip.  The statistics kernel itself (and the
+ * kernel of smaq_float_quantize) is launched as a programmatic dependent of whatever precedes it on `stream`: it
+ * executes griddepcontrol.wait before touching memory, so any producer is safe, and the launch gap behind the
+ * producer disappears (SMAQ_DEPENDENT_LAUNCH=1: only the launches inside a call are dependent).  The statistics live in the workspace
  * (last 256 bytes: mean, std).  y may alias x.
  * The workspace is initialised ONCE after allocation with smaq_compress_workspace_init (it zeroes the arrival
  * ticket of the statistics pass; every call leaves it zero again, so no memset node is issued per call).  Calls
