@@ -605,6 +605,13 @@ def sweep(args, device, peak):
         reps = 20 if log2n <= 26 else 1
         t_stats, _ = time_kernel(lambda: lib.smaq_stats_full(x.data_ptr(), n, 1, ms.data_ptr(), sws.data_ptr(), sws_b, st), reps=reps)
         t_rt, _ = time_kernel(lambda: lib.smaq_roundtrip(x.data_ptr(), y.data_ptr(), n, ms.data_ptr(), None, C.byref(params), st), reps=reps)
+        # the call the training hooks make: statistics + round trip behind one entry point (dependent launches, no
+        # memset node — smaq_stats_full above zeroes its ticket with one per call), 12 B/element
+        cws_b = lib.smaq_compress_workspace_bytes(n)
+        cws = torch.empty(cws_b, dtype=torch.uint8, device=device)
+        N.check(lib.smaq_compress_workspace_init(cws.data_ptr(), cws_b, st), "smaq_compress_workspace_init")
+        t_cmp, _ = time_kernel(lambda: lib.smaq_compress(x.data_ptr(), y.data_ptr(), n, None, C.byref(params),
+                                                         cws.data_ptr(), cws_b, st), reps=reps)
         t_enc, _ = time_kernel(lambda: lib.smaq_encode(x.data_ptr(), n, ms.data_ptr(), None, C.byref(params),
                                                        packed.data_ptr(), packed.numel(), ws.data_ptr(), ws.numel(), st), reps=reps)
         t_dec, _ = time_kernel(lambda: lib.smaq_decode(packed.data_ptr(), packed.numel(), n, 6, 8, 0, y.data_ptr(), st), reps=reps)
@@ -615,6 +622,8 @@ def sweep(args, device, peak):
                              ("decode", t_dec, "decode")):
             gbs = bpe[key] * n / (t * 1e-3) / 1e9
             row[name] = {"ms": round(t, 4), "gbs": round(gbs, 1), "frac": round(gbs / peak, 3)}
+        gbs = 12.0 * n / (t_cmp * 1e-3) / 1e9
+        row["compress"] = {"ms": round(t_cmp, 4), "gbs": round(gbs, 1), "frac": round(gbs / peak, 3)}
         out["smaq"].append(row)
         if log2n == top:
             r = {}
